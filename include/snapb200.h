@@ -1,0 +1,158 @@
+/*
+ * snapb200.h -- C ABI of the B200-native matrix-free spectral embedding.
+ *
+ * This is the drop-in boundary for the native entry points the reference binds
+ * through PyO3 (all paths relative to the SnapATAC2 source tree):
+ *
+ *   spectral_embedding(anndata, selected_features, n_components, random_state,
+ *                      feature_weights=None) -> (evals f64[k], evecs f64[n,k])
+ *       snapatac2-python/src/embedding.rs:24-59   (registered src/lib.rs:79)
+ *   multi_spectral_embedding(anndata[], selected_features[], weights[],
+ *                      n_components, random_state)
+ *       snapatac2-python/src/embedding.rs:388-452 (registered src/lib.rs:80)
+ *
+ * The reference does everything behind one call; here the same work is split
+ * into load -> prepare -> eigsh so that the intermediate quantities north_star
+ * gates (IDF weights, degree vector) and the operator alone can be checked
+ * and profiled.  The Python mirror `snapatac2_b200.tl.spectral` strings them
+ * together behind the reference's signature (tools/_embedding.py:129-141).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; the message
+ *     is available from snapb200_last_error() (thread-local);
+ *   - plain pointers and sizes only; the caller owns every host pointer, the
+ *     library owns all device memory inside the context;
+ *   - one context = one GPU = one host thread; multi-GPU is one process (or
+ *     thread) per GPU, joined by snapb200_comm_init (NCCL over NVLink);
+ *   - rows (cells) are sharded: a context holds global rows
+ *     [row0, row0 + n_local) of an n_global x m matrix;
+ *   - there is no CPU fallback: every entry point needs a CUDA device.
+ */
+#ifndef SNAPB200_H
+#define SNAPB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct snapb200_ctx snapb200_ctx;
+
+/* Phase timings and solver diagnostics of the last prepare/eigsh calls. */
+typedef struct snapb200_stats {
+    double ms_load;        /* host->device copy + format conversion           */
+    double ms_transpose;   /* building the feature-major copy                  */
+    double ms_prepare;     /* IDF, row norms, column sums, degrees (a3-a5)     */
+    double ms_eigsh;       /* whole eigensolve (a6+a7)                         */
+    double ms_spmm;        /* time inside the two SpMM passes                  */
+    double ms_ortho;       /* Gram / projection / CholQR kernels               */
+    double ms_comm;        /* NCCL all-reduces                                 */
+    double ms_host;        /* host-side Rayleigh-Ritz                          */
+    double max_residual;   /* max ||A v - theta v|| estimate over the k pairs  */
+    int64_t n_ops;         /* block operator applications                      */
+    int64_t n_restarts;    /* thick restarts                                   */
+    int64_t basis_cols;    /* Krylov basis width at exit                       */
+    int64_t block;         /* block width b                                    */
+    int64_t nnz_local;     /* stored entries on this shard                     */
+    int64_t kernel_launches; /* CUDA kernels launched by the library so far    */
+    int64_t reserved[5];
+} snapb200_stats;
+
+/* Library / error plumbing. */
+const char* snapb200_last_error(void);
+int  snapb200_version(void);
+
+/* Context: binds `device` (cudaSetDevice ordinal) and a private stream. */
+int  snapb200_create(int device, snapb200_ctx** out);
+int  snapb200_destroy(snapb200_ctx* ctx);
+
+/* Multi-GPU (one rank per context).  `id` is an opaque 128-byte NCCL unique
+ * id produced on rank 0 and distributed by the caller (torch.distributed,
+ * MPI, a file ...).  Without comm_init the context is a single-rank job. */
+int  snapb200_comm_unique_id(char id[128]);
+int  snapb200_comm_init(snapb200_ctx* ctx, int rank, int nranks, const char id[128]);
+
+/* Load this rank's row shard of X as CSR (replaces the slice + try_convert of
+ * embedding.rs:36-41).  `indptr` has n_local+1 entries (relative to the
+ * shard), `indices` are column ids < m, sorted within a row.  *_bits is 32 or
+ * 64.  `values` may be NULL (binarised pattern: every stored entry is 1);
+ * otherwise value_kind selects 1=f32, 2=f64, 3=u32, 4=i32, 5=i64, 6=u64 and
+ * the values are converted to f32.  `on_device` != 0 means the pointers are
+ * device pointers on this context's GPU (e.g. torch CUDA tensors). */
+int  snapb200_load_csr(snapb200_ctx* ctx, int64_t n_local, int64_t n_global, int64_t row0,
+                       int64_t m, const void* indptr, int indptr_bits,
+                       const void* indices, int indices_bits,
+                       const void* values, int value_kind, int on_device);
+
+/* Column selection on the device (to_select_elem + slice_axis(1, ..),
+ * embedding.rs:36-39): keep[j] != 0 keeps column j; surviving columns are
+ * renumbered densely.  Must be called between load and prepare. */
+int  snapb200_select_features(snapb200_ctx* ctx, const uint8_t* keep, int64_t m);
+
+/* Synthetic planted-cluster pattern rows generated on the device
+ * (SURVEY.md 8d); bit-identical to snapatac2_b200.synth.generate_rows for the
+ * same tables.  feat_cdf has m+1 entries, cluster_cdf/block_start K+1,
+ * alpha K (32.32 fixed point, see synth.py). */
+int  snapb200_generate(snapb200_ctx* ctx, int64_t n_local, int64_t n_global, int64_t row0,
+                       int64_t m, int nnz_row, int n_clusters, uint64_t seed,
+                       const uint64_t* feat_cdf, const uint64_t* cluster_cdf,
+                       const int64_t* block_start, const uint64_t* alpha);
+
+/* Shard geometry and export of the loaded/generated CSR (tests, e2e bench). */
+int  snapb200_shape(snapb200_ctx* ctx, int64_t* n_local, int64_t* m, int64_t* nnz_local);
+int  snapb200_export_csr(snapb200_ctx* ctx, int64_t* indptr, int32_t* indices, float* values_or_null);
+
+/* User feature weights (embedding.rs:42-43); NULL restores IDF.  Length m
+ * (the *selected* feature count). */
+int  snapb200_set_feature_weights(snapb200_ctx* ctx, const double* w, int64_t m);
+
+/* a3-a5: IDF weights (embedding.rs:269-286), row L2 norms (:315-326), column
+ * sums and degrees with self-similarity removed (:139-152).  Also builds the
+ * feature-major copy used by pass 1.  Outputs may be NULL; idf_out has m
+ * entries, degree_out n_local (degree = X c - 1, i.e. 1/dinv). */
+int  snapb200_prepare(snapb200_ctx* ctx, double* idf_out, double* degree_out);
+
+/* Multi-view support (embedding.rs:417-442): Frobenius norm of the
+ * off-diagonal cosine similarity over the given local rows, and a uniform
+ * scale applied to this view's normalised rows before hstack. */
+int  snapb200_view_frobenius(snapb200_ctx* ctx, const int64_t* rows, int64_t n_rows, double* out);
+
+/* a6 alone: Y = X~ (X~^T V) - dinv .* V on b vectors (embedding.rs:162-163).
+ * V and Y are host, row-major n_local x b, b in {4, 8, 16}. */
+int  snapb200_operator_apply(snapb200_ctx* ctx, const float* V, float* Y, int b);
+
+/* Device-only timing of `iters` operator applications on resident random
+ * vectors (for the roofline line of bench.py); returns average milliseconds
+ * of pass 1 (X^T V), the all-reduce, and pass 2 (X W). */
+int  snapb200_operator_time(snapb200_ctx* ctx, int b, int iters, int flush_l2,
+                            double* ms_pass1, double* ms_comm, double* ms_pass2);
+
+/* a7: k largest-magnitude eigenpairs of the normalised similarity operator,
+ * sorted by descending eigenvalue, trivial pair (lambda = 1) included -- what
+ * scipy eigsh(which='LM') + argsort()[::-1] returns at embedding.rs:164-171.
+ * Block Lanczos with full re-orthogonalisation and thick restart.
+ * evals: k doubles.  evecs: n_local x k doubles, row-major (this rank's rows).
+ * tol <= 0 selects the default (1e-5 relative residual); block 0 -> default. */
+int  snapb200_eigsh(snapb200_ctx* ctx, int k, int64_t seed, double tol,
+                    int block, int max_basis, int max_ops,
+                    double* evals, double* evecs);
+
+int  snapb200_get_stats(snapb200_ctx* ctx, snapb200_stats* out);
+
+/* The context's CUDA stream (a cudaStream_t), so a caller can record its own
+ * events around library calls (bench.py wraps it in torch.cuda.ExternalStream). */
+int  snapb200_get_stream(snapb200_ctx* ctx, void** stream);
+
+/* Test hooks (no reference counterpart).  dense_selftest runs the FP64
+ * tensor-core Gram / projection / rotation kernels against plain fp64 loops on
+ * random data and returns the worst relative error; sym_eig is the host-side
+ * Rayleigh-Ritz eigensolver (a: n x n row-major, destroyed; eigenvalues
+ * ascending in w, eigenvectors in the columns of a) and needs no GPU. */
+int  snapb200_dense_selftest(snapb200_ctx* ctx, int64_t n, int ncq, int p, double* max_rel_err);
+int  snapb200_sym_eig(int n, double* a, double* w);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNAPB200_H */

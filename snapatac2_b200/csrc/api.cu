@@ -1,0 +1,411 @@
+// C ABI of libsnapb200 (see include/snapb200.h for the contract and the
+// reference entry points each function stands in for).
+#include "ctx.cuh"
+#include "dense.cuh"
+
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+namespace snapb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+namespace {
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return 1;
+    } catch (...) {
+        set_last_error("unknown error");
+        return 1;
+    }
+}
+
+void bind(snapb200_ctx* c) {
+    SB_CHECK(c != nullptr, "null context");
+    SB_CUDA(cudaSetDevice(c->device));
+}
+
+__global__ void narrow_i64_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n,
+                                  int64_t limit, int* __restrict__ bad) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (; i < n; i += stride) {
+        int64_t v = in[i];
+        if (v < 0 || v >= limit) *bad = 1;
+        out[i] = static_cast<int32_t>(v);
+    }
+}
+__global__ void check_i32_kernel(const int32_t* __restrict__ in, int64_t n, int64_t limit, int* __restrict__ bad) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (; i < n; i += stride) {
+        int32_t v = in[i];
+        if (v < 0 || v >= limit) *bad = 1;
+    }
+}
+template <typename T>
+__global__ void to_f32_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t n) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (; i < n; i += stride) out[i] = static_cast<float>(in[i]);
+}
+__global__ void widen_i32_kernel(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+__global__ void ones_check_kernel(const float* __restrict__ v, int64_t n, int* __restrict__ not_one) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (; i < n; i += stride)
+        if (v[i] != 1.0f) *not_one = 1;
+}
+
+int stream_blocks(snapb200_ctx* c, int64_t n) {
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 256), static_cast<int64_t>(c->num_sms) * 16)));
+}
+
+size_t value_size(int kind) {
+    switch (kind) {
+        case 1: return 4; case 2: return 8; case 3: return 4; case 4: return 4; case 5: return 8; case 6: return 8;
+        default: throw Error("load_csr: unknown value_kind");
+    }
+}
+
+// Copy `count` elements of `elem` bytes from src (host or device) into a device
+// staging buffer in chunks and hand every chunk to `consume(dev_ptr, offset, len)`.
+template <typename F>
+void staged_copy(snapb200_ctx* c, const void* src, size_t elem, int64_t count, bool on_device, F&& consume) {
+    if (count == 0) return;
+    if (on_device) {
+        consume(src, 0, count);
+        return;
+    }
+    const int64_t chunk = std::min<int64_t>(count, (256ll << 20) / static_cast<int64_t>(elem));
+    DevBuf<unsigned char> stage[2];
+    stage[0].alloc(chunk * elem);
+    stage[1].alloc(chunk * elem);
+    int which = 0;
+    for (int64_t off = 0; off < count; off += chunk, which ^= 1) {
+        const int64_t len = std::min(chunk, count - off);
+        SB_CUDA(cudaMemcpyAsync(stage[which].p, static_cast<const unsigned char*>(src) + off * elem, len * elem,
+                                cudaMemcpyHostToDevice, c->stream));
+        consume(stage[which].p, off, len);
+    }
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, int64_t m, const void* indptr,
+              int indptr_bits, const void* indices, int indices_bits, const void* values, int value_kind,
+              int on_device) {
+    SB_CHECK(n_local >= 0 && n_global >= n_local && row0 >= 0 && row0 + n_local <= n_global, "load_csr: bad shard geometry");
+    SB_CHECK(m >= 1 && m < (1ll << 31), "load_csr: m must be in [1, 2^31)");
+    SB_CHECK(indptr_bits == 32 || indptr_bits == 64, "load_csr: indptr_bits must be 32 or 64");
+    SB_CHECK(indices_bits == 32 || indices_bits == 64, "load_csr: indices_bits must be 32 or 64");
+    SB_CHECK(indptr != nullptr, "load_csr: null indptr");
+    cudaStream_t st = c->stream;
+    SB_CUDA(cudaEventRecord(c->ev0, st));
+    const bool dev = on_device != 0;
+    Csr& X = c->X;
+    c->Xt.clear();
+    X.nrows = n_local;
+    X.ncols = m;
+    X.ptr.alloc(n_local + 1);
+
+    // ---- indptr (small): bring to int64 on the device, read nnz back
+    const cudaMemcpyKind kind = dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (indptr_bits == 64) {
+        SB_CUDA(cudaMemcpyAsync(X.ptr.p, indptr, sizeof(int64_t) * (n_local + 1), kind, st));
+    } else {
+        DevBuf<int32_t> tmp;
+        tmp.alloc(n_local + 1);
+        SB_CUDA(cudaMemcpyAsync(tmp.p, indptr, sizeof(int32_t) * (n_local + 1), kind, st));
+        widen_i32_kernel<<<static_cast<unsigned>(ceil_div(n_local + 1, 256)), 256, 0, st>>>(tmp.p, X.ptr.p, n_local + 1);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+        SB_CUDA(cudaStreamSynchronize(st));
+    }
+    int64_t ends[2] = {0, 0};
+    SB_CUDA(cudaMemcpyAsync(&ends[0], X.ptr.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(&ends[1], X.ptr.p + n_local, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    SB_CHECK(ends[0] == 0, "load_csr: indptr[0] must be 0 (shard-relative)");
+    const int64_t nnz = ends[1];
+    SB_CHECK(nnz >= 0, "load_csr: negative nnz");
+    SB_CHECK(nnz == 0 || indices != nullptr, "load_csr: null indices");
+    X.nnz = nnz;
+    X.idx.alloc(std::max<int64_t>(1, nnz));
+
+    DevBuf<int> bad;
+    bad.alloc(1);
+    SB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    // ---- column indices: int32 on the device, range-checked
+    if (indices_bits == 32) {
+        if (nnz > 0) {
+            SB_CUDA(cudaMemcpyAsync(X.idx.p, indices, sizeof(int32_t) * nnz, kind, st));
+            check_i32_kernel<<<stream_blocks(c, nnz), 256, 0, st>>>(X.idx.p, nnz, m, bad.p);
+            SB_LAUNCH_CHECK();
+            count_launch(c);
+        }
+    } else {
+        staged_copy(c, indices, 8, nnz, dev, [&](const void* p, int64_t off, int64_t len) {
+            narrow_i64_kernel<<<stream_blocks(c, len), 256, 0, st>>>(static_cast<const int64_t*>(p), X.idx.p + off, len, m, bad.p);
+            SB_LAUNCH_CHECK();
+            count_launch(c);
+        });
+    }
+    // ---- values (optional): f32 on the device; an all-ones array is dropped
+    X.val.release();
+    if (values != nullptr && nnz > 0) {
+        X.val.alloc(nnz);
+        const size_t es = value_size(value_kind);
+        staged_copy(c, values, es, nnz, dev, [&](const void* p, int64_t off, int64_t len) {
+            const int g = stream_blocks(c, len);
+            float* out = X.val.p + off;
+            switch (value_kind) {
+                case 1: SB_CUDA(cudaMemcpyAsync(out, p, sizeof(float) * len, cudaMemcpyDeviceToDevice, st)); break;
+                case 2: to_f32_kernel<double><<<g, 256, 0, st>>>(static_cast<const double*>(p), out, len); break;
+                case 3: to_f32_kernel<uint32_t><<<g, 256, 0, st>>>(static_cast<const uint32_t*>(p), out, len); break;
+                case 4: to_f32_kernel<int32_t><<<g, 256, 0, st>>>(static_cast<const int32_t*>(p), out, len); break;
+                case 5: to_f32_kernel<int64_t><<<g, 256, 0, st>>>(static_cast<const int64_t*>(p), out, len); break;
+                case 6: to_f32_kernel<uint64_t><<<g, 256, 0, st>>>(static_cast<const uint64_t*>(p), out, len); break;
+            }
+            SB_LAUNCH_CHECK();
+            count_launch(c);
+        });
+        DevBuf<int> not_one;
+        not_one.alloc(1);
+        SB_CUDA(cudaMemsetAsync(not_one.p, 0, sizeof(int), st));
+        ones_check_kernel<<<stream_blocks(c, nnz), 256, 0, st>>>(X.val.p, nnz, not_one.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+        int h = 0;
+        SB_CUDA(cudaMemcpyAsync(&h, not_one.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (!h) X.val.release();   // binarised input: pattern-only kernels
+    }
+    int hbad = 0;
+    SB_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaEventRecord(c->ev1, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    SB_CHECK(!hbad, "load_csr: column index out of range");
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->stats.ms_load = ms;
+    c->n_local = n_local;
+    c->n_global = n_global;
+    c->row0 = row0;
+    c->m = m;
+    c->loaded = true;
+    c->prepared = false;
+    c->stats.nnz_local = nnz;
+}
+
+}  // namespace
+}  // namespace snapb
+
+using namespace snapb;
+
+extern "C" {
+
+const char* snapb200_last_error(void) { return g_last_error.c_str(); }
+int snapb200_version(void) { return 100; }
+
+int snapb200_create(int device, snapb200_ctx** out) {
+    return guarded([&] {
+        SB_CHECK(out != nullptr, "create: null out pointer");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw Error("no CUDA device available: libsnapb200 has no CPU fallback (an NVIDIA B200 is required)");
+        SB_CHECK(device >= 0 && device < count, "create: device ordinal out of range");
+        SB_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        SB_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            throw Error(std::string("libsnapb200 is built for sm_100a only; device is ") + prop.name);
+        auto* c = new snapb200_ctx();
+        c->device = device;
+        c->num_sms = prop.multiProcessorCount;
+        SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreate(&c->ev0));
+        SB_CUDA(cudaEventCreate(&c->ev1));
+        *out = c;
+    });
+}
+
+int snapb200_destroy(snapb200_ctx* c) {
+    return guarded([&] {
+        if (!c) return;
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+        comm_destroy(c);
+        if (c->ev0) cudaEventDestroy(c->ev0);
+        if (c->ev1) cudaEventDestroy(c->ev1);
+        cudaStream_t st = c->stream;
+        delete c;
+        if (st) cudaStreamDestroy(st);
+    });
+}
+
+int snapb200_comm_unique_id(char id[128]) {
+    return guarded([&] { comm_unique_id(id); });
+}
+int snapb200_comm_init(snapb200_ctx* c, int rank, int nranks, const char id[128]) {
+    return guarded([&] { bind(c); comm_init(c, rank, nranks, id); });
+}
+
+int snapb200_load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, int64_t m, const void* indptr,
+                      int indptr_bits, const void* indices, int indices_bits, const void* values, int value_kind,
+                      int on_device) {
+    return guarded([&] {
+        bind(c);
+        load_csr(c, n_local, n_global, row0, m, indptr, indptr_bits, indices, indices_bits, values, value_kind, on_device);
+    });
+}
+
+int snapb200_select_features(snapb200_ctx* c, const uint8_t* keep, int64_t m) {
+    return guarded([&] { bind(c); select_features(c, keep, m); });
+}
+
+int snapb200_generate(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, int64_t m, int nnz_row,
+                      int n_clusters, uint64_t seed, const uint64_t* feat_cdf, const uint64_t* cluster_cdf,
+                      const int64_t* block_start, const uint64_t* alpha) {
+    return guarded([&] {
+        bind(c);
+        c->Xt.clear();
+        generate_rows(c, n_local, n_global, row0, m, nnz_row, n_clusters, seed, feat_cdf, cluster_cdf, block_start, alpha);
+    });
+}
+
+int snapb200_shape(snapb200_ctx* c, int64_t* n_local, int64_t* m, int64_t* nnz_local) {
+    return guarded([&] {
+        SB_CHECK(c && c->loaded, "shape: no matrix loaded");
+        if (n_local) *n_local = c->n_local;
+        if (m) *m = c->m;
+        if (nnz_local) *nnz_local = c->X.nnz;
+    });
+}
+
+int snapb200_export_csr(snapb200_ctx* c, int64_t* indptr, int32_t* indices, float* values) {
+    return guarded([&] {
+        bind(c);
+        SB_CHECK(c->loaded, "export_csr: no matrix loaded");
+        const Csr& X = c->X;
+        if (indptr) SB_CUDA(cudaMemcpyAsync(indptr, X.ptr.p, sizeof(int64_t) * (X.nrows + 1), cudaMemcpyDeviceToHost, c->stream));
+        if (indices && X.nnz > 0)
+            SB_CUDA(cudaMemcpyAsync(indices, X.idx.p, sizeof(int32_t) * X.nnz, cudaMemcpyDeviceToHost, c->stream));
+        if (values && X.nnz > 0) {
+            if (X.has_values()) {
+                SB_CUDA(cudaMemcpyAsync(values, X.val.p, sizeof(float) * X.nnz, cudaMemcpyDeviceToHost, c->stream));
+            } else {
+                SB_CUDA(cudaStreamSynchronize(c->stream));
+                std::fill(values, values + X.nnz, 1.0f);
+            }
+        }
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int snapb200_set_feature_weights(snapb200_ctx* c, const double* w, int64_t m) {
+    return guarded([&] {
+        SB_CHECK(c != nullptr, "null context");
+        if (w == nullptr) c->user_weights.clear();
+        else c->user_weights.assign(w, w + m);
+        c->prepared = false;
+    });
+}
+
+int snapb200_prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
+    return guarded([&] { bind(c); prepare(c, idf_out, degree_out); });
+}
+
+int snapb200_view_frobenius(snapb200_ctx* c, const int64_t* rows, int64_t n_rows, double* out) {
+    return guarded([&] { bind(c); view_frobenius(c, rows, n_rows, out); });
+}
+
+int snapb200_operator_apply(snapb200_ctx* c, const float* V, float* Y, int b) {
+    return guarded([&] {
+        bind(c);
+        SB_CHECK(c->prepared, "operator_apply: call prepare first");
+        const int64_t len = std::max<int64_t>(1, c->n_local * b);
+        c->opV.ensure(len);
+        c->opY.ensure(len);
+        SB_CUDA(cudaMemcpyAsync(c->opV.p, V, sizeof(float) * c->n_local * b, cudaMemcpyHostToDevice, c->stream));
+        operator_apply_dev(c, c->opV.p, b, c->opY.p, b, b);
+        SB_CUDA(cudaMemcpyAsync(Y, c->opY.p, sizeof(float) * c->n_local * b, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int snapb200_operator_time(snapb200_ctx* c, int b, int iters, int flush, double* ms_pass1, double* ms_comm,
+                           double* ms_pass2) {
+    return guarded([&] {
+        bind(c);
+        SB_CHECK(c->prepared, "operator_time: call prepare first");
+        SB_CHECK(iters >= 1, "operator_time: iters must be >= 1");
+        const int64_t len = std::max<int64_t>(1, c->n_local * b);
+        c->opV.ensure(len);
+        c->opY.ensure(len);
+        DenseOps<8> ops;
+        for (int j = 0; j < b; j += 4) {
+            // fill opV with hash noise, 4 columns at a time through the B=4 generator
+            DenseOps<4> o4;
+            o4.random_block(c, c->opV.p + j, b, c->n_local, 99, 1000 + j);
+        }
+        cudaEvent_t evs[4];
+        for (auto& e : evs) SB_CUDA(cudaEventCreate(&e));
+        double p1 = 0, cm = 0, p2 = 0;
+        for (int it = 0; it < iters + 1; ++it) {   // iteration 0 is a warm-up
+            if (flush) flush_l2(c);
+            operator_apply_dev(c, c->opV.p, b, c->opY.p, b, b, evs);
+            SB_CUDA(cudaEventSynchronize(evs[3]));
+            if (it == 0) continue;
+            float a = 0.f, bb = 0.f, cc = 0.f;
+            SB_CUDA(cudaEventElapsedTime(&a, evs[0], evs[1]));
+            SB_CUDA(cudaEventElapsedTime(&bb, evs[1], evs[2]));
+            SB_CUDA(cudaEventElapsedTime(&cc, evs[2], evs[3]));
+            p1 += a; cm += bb; p2 += cc;
+        }
+        for (auto& e : evs) cudaEventDestroy(e);
+        if (ms_pass1) *ms_pass1 = p1 / iters;
+        if (ms_comm) *ms_comm = cm / iters;
+        if (ms_pass2) *ms_pass2 = p2 / iters;
+    });
+}
+
+int snapb200_eigsh(snapb200_ctx* c, int k, int64_t seed, double tol, int block, int max_basis, int max_ops,
+                   double* evals, double* evecs) {
+    return guarded([&] { bind(c); eigsh(c, k, seed, tol, block, max_basis, max_ops, evals, evecs); });
+}
+
+int snapb200_get_stats(snapb200_ctx* c, snapb200_stats* out) {
+    return guarded([&] {
+        SB_CHECK(c && out, "get_stats: null argument");
+        *out = c->stats;
+    });
+}
+
+int snapb200_get_stream(snapb200_ctx* c, void** stream) {
+    return guarded([&] {
+        SB_CHECK(c && stream, "get_stream: null argument");
+        *stream = reinterpret_cast<void*>(c->stream);
+    });
+}
+
+// ---- test hooks (not part of the reference-facing surface) -----------------
+int snapb200_dense_selftest(snapb200_ctx* c, int64_t n, int ncq, int p, double* max_rel_err) {
+    return guarded([&] { bind(c); *max_rel_err = dense_selftest(c, n, ncq, p); });
+}
+int snapb200_sym_eig(int n, double* a, double* w) {
+    return guarded([&] { sym_eig(n, a, w); });
+}
+
+}  // extern "C"

@@ -1,0 +1,162 @@
+// Context and device-side data structures of libsnapb200.
+#pragma once
+
+#include "common.cuh"
+#include "../../include/snapb200.h"
+
+#include <vector>
+
+namespace snapb {
+
+// Owning device buffer (freed with the context or on reassignment).
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    int64_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void alloc(int64_t count) {
+        release();
+        if (count > 0) {
+            SB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), sizeof(T) * static_cast<size_t>(count)));
+        }
+        n = count;
+    }
+    void ensure(int64_t count) {
+        if (count > n) alloc(count);
+    }
+    void swap(DevBuf& o) {
+        T* tp = p; p = o.p; o.p = tp;
+        int64_t tn = n; n = o.n; o.n = tn;
+    }
+};
+
+template <typename T>
+struct PinBuf {
+    T* p = nullptr;
+    int64_t n = 0;
+    PinBuf() = default;
+    PinBuf(const PinBuf&) = delete;
+    PinBuf& operator=(const PinBuf&) = delete;
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+    void ensure(int64_t count) {
+        if (count <= n) return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        SB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&p), sizeof(T) * static_cast<size_t>(count)));
+        n = count;
+    }
+};
+
+// CSR pattern (+ optional f32 values) resident on the device.
+struct Csr {
+    int64_t nrows = 0, ncols = 0, nnz = 0;
+    DevBuf<int64_t> ptr;   // nrows + 1
+    DevBuf<int32_t> idx;   // nnz, sorted within a row
+    DevBuf<float> val;     // nnz or empty (binarised)
+    bool has_values() const { return val.p != nullptr; }
+    void clear() {
+        nrows = ncols = nnz = 0;
+        ptr.release();
+        idx.release();
+        val.release();
+    }
+};
+
+struct Comm;  // NCCL wrapper (comm.cu)
+
+}  // namespace snapb
+
+// The public opaque type.
+struct snapb200_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = snapb::kNumSMsB200;
+
+    // multi-GPU
+    snapb::Comm* comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    // shard geometry
+    int64_t n_local = 0, n_global = 0, row0 = 0, m = 0;
+    bool loaded = false, prepared = false;
+
+    snapb::Csr X;    // cells x features (this rank's rows)
+    snapb::Csr Xt;   // features x local cells (built by prepare)
+
+    // user feature weights (host copy, optional)
+    std::vector<double> user_weights;
+
+    // prepare() products
+    snapb::DevBuf<double> w;        // m   feature weights (IDF or user)
+    snapb::DevBuf<double> rho;      // n   row L2 norms of the weighted rows
+    snapb::DevBuf<double> csum;     // m   column sums of Xhat
+    snapb::DevBuf<double> degree;   // n   d_i = Xhat c - 1
+    snapb::DevBuf<float> r;         // n   sqrt(dinv)/rho  (row scale of X~)
+    snapb::DevBuf<float> dinv;      // n   1/d
+    snapb::DevBuf<float> w2;        // m   w^2 (f32)
+    snapb::DevBuf<float> u1;        // n   sqrt(d)/||sqrt(d)||, trivial eigenvector
+    double view_scale = 1.0;        // multi-view scale folded into w
+
+    // operator workspaces
+    snapb::DevBuf<float> Vr;        // n x b  r .* V
+    snapb::DevBuf<float> W;         // m x b  X^T (r V), then w^2-scaled
+    snapb::DevBuf<float> opV, opY;  // operator_apply / operator_time staging
+
+    // scratch
+    snapb::DevBuf<unsigned char> scratch;
+    snapb::PinBuf<unsigned char> pinned;
+
+    snapb200_stats stats{};
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace snapb {
+
+// ---- comm.cu
+void comm_unique_id(char id[128]);
+void comm_init(snapb200_ctx* c, int rank, int nranks, const char id[128]);
+void comm_destroy(snapb200_ctx* c);
+void allreduce_f32(snapb200_ctx* c, float* buf, int64_t count);
+void allreduce_f64(snapb200_ctx* c, double* buf, int64_t count);
+void allreduce_i64(snapb200_ctx* c, int64_t* buf, int64_t count);
+
+// ---- synth.cu
+void generate_rows(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, int64_t m,
+                   int nnz_row, int n_clusters, uint64_t seed, const uint64_t* feat_cdf,
+                   const uint64_t* cluster_cdf, const int64_t* block_start, const uint64_t* alpha);
+
+// ---- util.cu
+void exclusive_scan_i64(snapb200_ctx* c, const int64_t* in, int64_t* out, int64_t n);  // out has n+1
+void exclusive_scan_i32_to_i64(snapb200_ctx* c, const int32_t* in, int64_t* out, int64_t n);
+void fill_f32(snapb200_ctx* c, float* p, float v, int64_t n);
+void flush_l2(snapb200_ctx* c);
+
+// ---- prep.cu
+void select_features(snapb200_ctx* c, const uint8_t* keep_host, int64_t m);
+void build_transpose(snapb200_ctx* c);
+void prepare(snapb200_ctx* c, double* idf_out, double* degree_out);
+void view_frobenius(snapb200_ctx* c, const int64_t* rows, int64_t n_rows, double* out);
+
+// ---- spmm.cu
+// Y[n x b] (leading dim ldy) = X~ X~^T V - dinv .* V, V with leading dim ldv.
+// evs (optional, 4 events): recorded before pass 1, after pass 1, after the
+// all-reduce, after pass 2.
+void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, int b,
+                        cudaEvent_t* evs = nullptr);
+
+// ---- lanczos.cu
+void eigsh(snapb200_ctx* c, int k, int64_t seed, double tol, int block, int max_basis, int max_ops,
+           double* evals, double* evecs);
+
+inline void count_launch(snapb200_ctx* c, int64_t n = 1) { c->stats.kernel_launches += n; }
+
+}  // namespace snapb

@@ -1,0 +1,466 @@
+// Small dense algebra of the block Lanczos solver: the tall-skinny Gram
+// (Q^T Z), projection (Z -= Q H) and basis rotation (Q S) products.
+//
+// These are the only dense contractions on the path.  They run on the tensor
+// cores in FULL FP64 (DMMA, mma.sync.m8n8k4.f64) with the basis stored in
+// fp32 and widened on load: fp64 has no tcgen05 kind, so the m8n8k4 DMMA is
+// the tensor path for this precision; B200 sustains the same ~40 TFLOP/s on it
+// as on the FP64 CUDA cores, and the products are HBM-bound (they stream Q).
+// All reductions are fixed-order (per-CTA partials, then one reduce kernel), so
+// the solver is bitwise reproducible.
+#include "ctx.cuh"
+#include "dense.cuh"
+
+#include <cmath>
+#include <vector>
+
+namespace snapb {
+
+namespace {
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// --------------------------------------------------------------------------
+// Gram: partial[cta][ncq x B] = Q[rows of cta, 0:ncq]^T Z[rows of cta, 0:B]
+// grid = (row chunks, column groups of 64); 8 warps per CTA.
+// DMMA roles: m = 8 basis columns, n = 8 block columns, k = 4 rows.
+// Column permutation inside a 32-column group so that one float4 load feeds
+// four tiles: tile t, fragment row mi  <->  column 32*(t/4) + 4*mi + (t%4).
+// --------------------------------------------------------------------------
+constexpr int kGramWarps = 8;
+constexpr int kGramCols = 64;  // basis columns per CTA (8 tiles)
+
+template <int B>
+__global__ void __launch_bounds__(kGramWarps * 32)
+gram_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const float* __restrict__ Z, int64_t ldz, int64_t n,
+            double* __restrict__ partial) {
+    constexpr int NT = (B + 7) / 8;
+    __shared__ double red[kGramWarps][NT][64];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int mi = lane >> 2, ki = lane & 3;
+    const int c_base = blockIdx.y * kGramCols;
+
+    int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
+    chunk = (chunk + 3) / 4 * 4;
+    const int64_t r_lo = min(n, static_cast<int64_t>(blockIdx.x) * chunk);
+    const int64_t r_hi = min(n, r_lo + chunk);
+
+    double acc[8][NT][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t)
+#pragma unroll
+        for (int u = 0; u < NT; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
+
+    // which of the two 32-column groups of this CTA have columns < ncq
+    const bool g0 = (c_base + 4 * mi) < ncq;
+    const bool g1 = (c_base + 32 + 4 * mi) < ncq;
+
+    for (int64_t r = r_lo + 4 * warp; r < r_hi; r += 4 * kGramWarps) {
+        const int64_t row = r + ki;
+        const bool valid = row < r_hi;
+        double bf[NT];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) {
+            const int col = u * 8 + mi;
+            bf[u] = (valid && col < B) ? static_cast<double>(Z[row * ldz + col]) : 0.0;
+        }
+        float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+        if (valid && g0) a0 = *reinterpret_cast<const float4*>(Q + row * ldq + c_base + 4 * mi);
+        if (valid && g1) a1 = *reinterpret_cast<const float4*>(Q + row * ldq + c_base + 32 + 4 * mi);
+        const double av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+#pragma unroll
+            for (int u = 0; u < NT; ++u) dmma884(acc[t][u][0], acc[t][u][1], av[t], bf[u]);
+    }
+
+    // fixed-order reduction over the CTA's warps, one tile row at a time
+    double* out = partial + static_cast<int64_t>(blockIdx.x) * ncq * B;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+#pragma unroll
+        for (int u = 0; u < NT; ++u) {
+            red[warp][u][lane * 2] = acc[t][u][0];
+            red[warp][u][lane * 2 + 1] = acc[t][u][1];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < NT * 64; e += blockDim.x) {
+            const int u = e / 64, f = e % 64;
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < kGramWarps; ++w) s += red[w][u][f];
+            // fragment element f -> lane f/2, slot f%2 -> C row (lane>>2), C col (lane&3)*2 + slot
+            const int fl = f >> 1, fmi = fl >> 2, fni = (fl & 3) * 2 + (f & 1);
+            const int col = c_base + 32 * (t >> 2) + 4 * fmi + (t & 3);   // basis column (H row)
+            const int bc = u * 8 + fni;                                    // block column (H col)
+            if (col < ncq && bc < B) out[static_cast<int64_t>(col) * B + bc] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// H[e] = sum over CTAs (fixed order) of partial[cta][e]
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, int n_parts, int64_t len,
+                                       double* __restrict__ out) {
+    int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= len) return;
+    double s = 0.0;
+    for (int p = 0; p < n_parts; ++p) s += partial[static_cast<int64_t>(p) * len + e];
+    out[e] = s;
+}
+
+// --------------------------------------------------------------------------
+// Cholesky of the B x B Gram matrix, G = R^T R (R upper), plus R^-1.
+// A pivot below 1e-24 * max diagonal marks a dependent (or zero) column: its
+// output column is zeroed and flagged.  One thread; B <= 16.
+// out layout (doubles): R[B*B], Rinv[B*B], Rtot[B*B], flags[B]
+// Rtot = R * Rprev (Rprev = previous round's Rtot, or identity when first).
+// --------------------------------------------------------------------------
+template <int B>
+__global__ void chol_kernel(const double* __restrict__ G, const double* __restrict__ ref_diag,
+                            double* __restrict__ out, int first) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double R[B][B], Ri[B][B];
+    double* Rg = out;
+    double* Rig = out + B * B;
+    double* Rt = out + 2 * B * B;
+    double* flags = out + 3 * B * B;
+    double dmax = 0.0;
+    for (int j = 0; j < B; ++j) dmax = fmax(dmax, G[j * B + j]);
+    for (int i = 0; i < B; ++i)
+        for (int j = 0; j < B; ++j) { R[i][j] = 0.0; Ri[i][j] = 0.0; }
+    bool dep[B];
+    for (int j = 0; j < B; ++j) {
+        // column j of R: R[i][j] for i <= j
+        for (int i = 0; i < j; ++i) {
+            double s = G[i * B + j];
+            for (int k = 0; k < i; ++k) s -= R[k][i] * R[k][j];
+            R[i][j] = dep[i] ? 0.0 : s / R[i][i];
+        }
+        double d = G[j * B + j];
+        for (int k = 0; k < j; ++k) d -= R[k][j] * R[k][j];
+        dep[j] = !(d > 1e-24 * dmax) || !(dmax > 0.0);
+        // column norm collapsed by >1e5 under projection: it lies in the span of the basis
+        if (ref_diag && !(d > 1e-10 * ref_diag[j * B + j])) dep[j] = true;
+        R[j][j] = dep[j] ? 1.0 : sqrt(d);
+        if (dep[j]) for (int i = 0; i < j; ++i) R[i][j] = 0.0;
+    }
+    // inverse of upper-triangular R by back substitution, column by column
+    for (int j = 0; j < B; ++j) {
+        Ri[j][j] = 1.0 / R[j][j];
+        for (int i = j - 1; i >= 0; --i) {
+            double s = 0.0;
+            for (int k = i + 1; k <= j; ++k) s -= R[i][k] * Ri[k][j];
+            Ri[i][j] = s / R[i][i];
+        }
+    }
+    for (int j = 0; j < B; ++j)
+        if (dep[j]) {
+            for (int i = 0; i < B; ++i) Ri[i][j] = 0.0;   // zero the dependent output column
+            R[j][j] = 0.0;                                 // and its coupling
+        }
+    double prev[B][B];
+    for (int i = 0; i < B; ++i)
+        for (int j = 0; j < B; ++j) prev[i][j] = first ? (i == j ? 1.0 : 0.0) : Rt[i * B + j];
+    for (int i = 0; i < B; ++i)
+        for (int j = 0; j < B; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < B; ++k) s += R[i][k] * prev[k][j];
+            Rg[i * B + j] = R[i][j];
+            Rig[i * B + j] = Ri[i][j];
+            Rt[i * B + j] = s;
+        }
+    for (int j = 0; j < B; ++j) flags[j] = first ? (dep[j] ? 1.0 : 0.0) : fmax(flags[j], dep[j] ? 1.0 : 0.0);
+}
+
+// dst[i, 0:B] = Z[i, 0:B] * Rinv   (fp64 math, fp32 storage)
+template <int B>
+__global__ void apply_rinv_kernel(const float* __restrict__ Z, int64_t ldz, const double* __restrict__ Rinv,
+                                  int64_t n, float* __restrict__ dst, int64_t ldd) {
+    __shared__ double Ri[B * B];
+    for (int e = threadIdx.x; e < B * B; e += blockDim.x) Ri[e] = Rinv[e];
+    __syncthreads();
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double z[B];
+#pragma unroll
+    for (int k = 0; k < B; ++k) z[k] = static_cast<double>(Z[i * ldz + k]);
+#pragma unroll
+    for (int j = 0; j < B; ++j) {
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k <= j; ++k) s = fma(z[k], Ri[k * B + j], s);
+        dst[i * ldd + j] = static_cast<float>(s);
+    }
+}
+
+// --------------------------------------------------------------------------
+// Tall product  C[n x P] = Q[n x ncq] S[ncq x P]  (S fp64, row-major, ld = lds)
+// MODE 0: Z(f32, ldo) -= C     MODE 1: out f32 = C     MODE 2: out f64 = C
+// DMMA roles: m = 8 rows, n = 8 output columns, k = 4 basis columns.
+// k permutation inside a 16-column group so that one float4 load feeds four
+// k-steps: step s, fragment k index ki  <->  column 16*g + 4*ki + s.
+// ncq must be a multiple of 8 (so it is a multiple of 4 for the float4 loads).
+// --------------------------------------------------------------------------
+template <int NT, int MODE>
+__global__ void __launch_bounds__(256)
+tall_gemm_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const double* __restrict__ S, int lds, int p_valid,
+                 int64_t n, void* __restrict__ outp, int64_t ldo) {
+    const int lane = threadIdx.x & 31;
+    const int mi = lane >> 2, ki = lane & 3;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int col_off = blockIdx.y * NT * 8;   // output column group
+
+    for (int64_t r0 = warp * 8; r0 < n; r0 += nwarps * 8) {
+        const int64_t row = r0 + mi;
+        const bool valid = row < n;
+        double acc[NT][2];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) acc[u][0] = acc[u][1] = 0.0;
+
+        for (int kb = 0; kb < ncq; kb += 16) {
+            const int c = kb + 4 * ki;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && c < ncq) a = *reinterpret_cast<const float4*>(Q + row * ldq + c);
+            const double av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int kc = c + s;   // basis column of this lane's k index in step s
+#pragma unroll
+                for (int u = 0; u < NT; ++u) {
+                    const int oc = col_off + u * 8 + mi;   // B fragment: row ki (-> kc), col mi
+                    const double b = (kc < ncq && oc < lds) ? __ldg(S + static_cast<int64_t>(kc) * lds + oc) : 0.0;
+                    dmma884(acc[u][0], acc[u][1], av[s], b);
+                }
+            }
+        }
+        if (valid) {
+#pragma unroll
+            for (int u = 0; u < NT; ++u) {
+                const int oc = col_off + u * 8 + ki * 2;
+                if (MODE == 0) {
+                    float* z = reinterpret_cast<float*>(outp) + row * ldo + oc;
+                    if (oc < p_valid) z[0] = static_cast<float>(static_cast<double>(z[0]) - acc[u][0]);
+                    if (oc + 1 < p_valid) z[1] = static_cast<float>(static_cast<double>(z[1]) - acc[u][1]);
+                } else if (MODE == 1) {
+                    float* o = reinterpret_cast<float*>(outp) + row * ldo + oc;
+                    if (oc < p_valid) o[0] = static_cast<float>(acc[u][0]);
+                    if (oc + 1 < p_valid) o[1] = static_cast<float>(acc[u][1]);
+                } else {
+                    double* o = reinterpret_cast<double*>(outp) + row * ldo + oc;
+                    if (oc < p_valid) o[0] = acc[u][0];
+                    if (oc + 1 < p_valid) o[1] = acc[u][1];
+                }
+            }
+        }
+    }
+}
+
+// Random start block: Z[i, j] = U(-0.5, 0.5) keyed by (seed, global row, j);
+// identical for any row sharding.
+template <int B>
+__global__ void random_block_kernel(float* __restrict__ Z, int64_t ldz, int64_t n, int64_t row0, uint64_t seed,
+                                    uint64_t stream) {
+    int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n * B) return;
+    int64_t i = t / B;
+    int j = static_cast<int>(t - i * B);
+    uint64_t h = mix64(seed ^ 0x5bd1e995u, static_cast<uint64_t>(row0 + i), (stream << 8) + static_cast<uint64_t>(j));
+    Z[i * ldz + j] = static_cast<float>(static_cast<double>(h >> 11) * (1.0 / 9007199254740992.0) - 0.5);
+}
+
+__global__ void copy_cols_kernel(const float* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd,
+                                 int64_t n, int ncols) {
+    int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n * ncols) return;
+    int64_t i = t / ncols;
+    int j = static_cast<int>(t - i * ncols);
+    dst[i * ldd + j] = src[i * lds + j];
+}
+
+// ---- plain reference kernels for the self test (no tensor cores) ---------
+__global__ void ref_gram_kernel(const float* Q, int64_t ldq, int ncq, const float* Z, int64_t ldz, int B, int64_t n,
+                                double* H) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ncq * B) return;
+    int cq = e / B, cb = e % B;
+    double s = 0.0;
+    for (int64_t i = 0; i < n; ++i) s += static_cast<double>(Q[i * ldq + cq]) * static_cast<double>(Z[i * ldz + cb]);
+    H[e] = s;
+}
+__global__ void ref_tall_kernel(const float* Q, int64_t ldq, int ncq, const double* S, int lds, int p, int64_t n,
+                                double* out) {
+    int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n * p) return;
+    int64_t i = t / p;
+    int j = static_cast<int>(t - i * p);
+    double s = 0.0;
+    for (int k = 0; k < ncq; ++k) s += static_cast<double>(Q[i * ldq + k]) * S[static_cast<int64_t>(k) * lds + j];
+    out[t] = s;
+}
+
+inline int row_chunks(snapb200_ctx* c, int64_t n) {
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c->num_sms * 2, ceil_div(n, 256))));
+}
+
+}  // namespace
+
+// ==========================================================================
+// host wrappers
+// ==========================================================================
+template <int B>
+void DenseOps<B>::gram(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Z, int64_t ldz, int64_t n,
+                       double* H) {
+    SB_CHECK(ncq % 4 == 0 && ldq % 4 == 0, "gram: basis width must be a multiple of 4");
+    const int parts = row_chunks(c, n);
+    const int64_t len = static_cast<int64_t>(ncq) * B;
+    partial.ensure(static_cast<int64_t>(parts) * len);
+    dim3 grid(parts, static_cast<unsigned>(ceil_div(ncq, kGramCols)));
+    gram_kernel<B><<<grid, kGramWarps * 32, 0, c->stream>>>(Q, ldq, ncq, Z, ldz, n, partial.p);
+    SB_LAUNCH_CHECK();
+    reduce_partials_kernel<<<static_cast<unsigned>(ceil_div(len, 128)), 128, 0, c->stream>>>(partial.p, parts, len, H);
+    SB_LAUNCH_CHECK();
+    count_launch(c, 2);
+}
+
+template <int B>
+void DenseOps<B>::zz(snapb200_ctx* c, const float* Z, int64_t ldz, int64_t n, double* G) {
+    gram(c, Z, ldz, B, Z, ldz, n, G);   // Z^T Z through the same DMMA kernel
+}
+
+template <int B>
+void DenseOps<B>::chol(snapb200_ctx* c, const double* G, const double* ref_diag, double* out, bool first) {
+    chol_kernel<B><<<1, 32, 0, c->stream>>>(G, ref_diag, out, first ? 1 : 0);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+}
+
+template <int B>
+void DenseOps<B>::apply_rinv(snapb200_ctx* c, const float* Z, int64_t ldz, const double* Rinv, int64_t n, float* dst,
+                             int64_t ldd) {
+    if (n == 0) return;
+    apply_rinv_kernel<B><<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, c->stream>>>(Z, ldz, Rinv, n, dst, ldd);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+}
+
+template <int B>
+void DenseOps<B>::project_out(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const double* H, int64_t n,
+                              float* Z, int64_t ldz) {
+    if (n == 0) return;
+    constexpr int NT = (B + 7) / 8;
+    int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 64), c->num_sms * 8)));
+    tall_gemm_kernel<NT, 0><<<blocks, 256, 0, c->stream>>>(Q, ldq, ncq, H, B, B, n, Z, ldz);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+}
+
+void tall_gemm_f32(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const double* S, int lds, int p, int64_t n,
+                   float* out, int64_t ldo) {
+    if (n == 0) return;
+    SB_CHECK(ncq % 8 == 0, "tall_gemm: basis width must be a multiple of 8");
+    dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 64), c->num_sms * 8))),
+              static_cast<unsigned>(ceil_div(p, 32)));
+    tall_gemm_kernel<4, 1><<<grid, 256, 0, c->stream>>>(Q, ldq, ncq, S, lds, p, n, out, ldo);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+}
+
+void tall_gemm_f64(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const double* S, int lds, int p, int64_t n,
+                   double* out, int64_t ldo) {
+    if (n == 0) return;
+    SB_CHECK(ncq % 8 == 0, "tall_gemm: basis width must be a multiple of 8");
+    dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 64), c->num_sms * 8))),
+              static_cast<unsigned>(ceil_div(p, 32)));
+    tall_gemm_kernel<4, 2><<<grid, 256, 0, c->stream>>>(Q, ldq, ncq, S, lds, p, n, out, ldo);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+}
+
+template <int B>
+void DenseOps<B>::random_block(snapb200_ctx* c, float* Z, int64_t ldz, int64_t n, uint64_t seed, uint64_t stream) {
+    if (n == 0) return;
+    random_block_kernel<B><<<static_cast<unsigned>(ceil_div(n * B, 256)), 256, 0, c->stream>>>(Z, ldz, n, c->row0, seed,
+                                                                                            stream);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+}
+
+void copy_cols(snapb200_ctx* c, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int ncols) {
+    if (n == 0 || ncols == 0) return;
+    copy_cols_kernel<<<static_cast<unsigned>(ceil_div(n * ncols, 256)), 256, 0, c->stream>>>(src, lds, dst, ldd, n, ncols);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+}
+
+template struct DenseOps<4>;
+template struct DenseOps<8>;
+template struct DenseOps<16>;
+
+// Self test: DMMA kernels against plain fp64 loops on random data.
+double dense_selftest(snapb200_ctx* c, int64_t n, int ncq, int p) {
+    SB_CHECK(ncq % 8 == 0 && ncq >= 8 && p >= 1 && p <= 64, "selftest: bad sizes");
+    constexpr int B = 8;
+    const int64_t ldq = ncq + 8;
+    DevBuf<float> Q, Z, Z2, O32;
+    DevBuf<double> H, Href, S, O64, Oref;
+    Q.alloc(n * ldq); Z.alloc(n * B); Z2.alloc(n * B); O32.alloc(n * p);
+    H.alloc(ncq * B); Href.alloc(ncq * B); S.alloc(static_cast<int64_t>(ncq) * p); O64.alloc(n * p); Oref.alloc(n * p);
+    DenseOps<B> ops;
+    for (int j = 0; j < ldq; j += B) ops.random_block(c, Q.p + j, ldq, n, 11, 100 + j);
+    ops.random_block(c, Z.p, B, n, 12, 7);
+    std::vector<double> hs(static_cast<size_t>(ncq) * p);
+    for (size_t e = 0; e < hs.size(); ++e) hs[e] = static_cast<double>(mix64(3, e, 5) >> 11) / 9007199254740992.0 - 0.5;
+    SB_CUDA(cudaMemcpyAsync(S.p, hs.data(), sizeof(double) * hs.size(), cudaMemcpyHostToDevice, c->stream));
+
+    double worst = 0.0;
+    auto compare = [&](const double* a, const double* b, int64_t len) {
+        std::vector<double> ha(len), hb(len);
+        SB_CUDA(cudaMemcpyAsync(ha.data(), a, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaMemcpyAsync(hb.data(), b, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        double scale = 1e-30, err = 0.0;
+        for (int64_t i = 0; i < len; ++i) { scale = std::max(scale, fabs(hb[i])); err = std::max(err, fabs(ha[i] - hb[i])); }
+        worst = std::max(worst, err / scale);
+    };
+    // gram
+    ops.gram(c, Q.p, ldq, ncq, Z.p, B, n, H.p);
+    ref_gram_kernel<<<static_cast<unsigned>(ceil_div(ncq * B, 64)), 64, 0, c->stream>>>(Q.p, ldq, ncq, Z.p, B, B, n, Href.p);
+    SB_LAUNCH_CHECK();
+    compare(H.p, Href.p, ncq * B);
+    // tall gemm f64
+    tall_gemm_f64(c, Q.p, ldq, ncq, S.p, p, p, n, O64.p, p);
+    ref_tall_kernel<<<static_cast<unsigned>(ceil_div(n * p, 256)), 256, 0, c->stream>>>(Q.p, ldq, ncq, S.p, p, p, n, Oref.p);
+    SB_LAUNCH_CHECK();
+    compare(O64.p, Oref.p, n * p);
+    // projection: Z2 = Z - Q H  vs reference using ref_tall on H
+    SB_CUDA(cudaMemcpyAsync(Z2.p, Z.p, sizeof(float) * n * B, cudaMemcpyDeviceToDevice, c->stream));
+    ops.project_out(c, Q.p, ldq, ncq, Href.p, n, Z2.p, B);
+    {
+        DevBuf<double> QH;
+        QH.alloc(n * B);
+        ref_tall_kernel<<<static_cast<unsigned>(ceil_div(n * B, 256)), 256, 0, c->stream>>>(Q.p, ldq, ncq, Href.p, B, B, n, QH.p);
+        SB_LAUNCH_CHECK();
+        std::vector<float> hz(n * B), hz2(n * B);
+        std::vector<double> hq(n * B);
+        SB_CUDA(cudaMemcpyAsync(hz.data(), Z.p, sizeof(float) * n * B, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaMemcpyAsync(hz2.data(), Z2.p, sizeof(float) * n * B, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaMemcpyAsync(hq.data(), QH.p, sizeof(double) * n * B, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        double scale = 1e-30, err = 0.0;
+        for (int64_t i = 0; i < n * B; ++i) {
+            double want = static_cast<double>(hz[i]) - hq[i];
+            scale = std::max(scale, fabs(want));
+            err = std::max(err, fabs(want - static_cast<double>(hz2[i])));
+        }
+        worst = std::max(worst, err / scale / 64.0);   // fp32 store rounding allowed
+    }
+    return worst;
+}
+
+}  // namespace snapb

@@ -1,0 +1,484 @@
+// prepare(): feature selection, deterministic transpose, IDF weights, row
+// norms, column sums and degrees (reference: snapatac2-python/src/embedding.rs
+// :269-286 idf, :315-326 normalize, :139-152 degree block of spectral_mf).
+//
+// All of these are one-off O(nnz) passes.  The m- and n-length vectors they
+// gather from are kept in fp64 so the IDF / degree parity gates (1e-5) are met
+// with a wide margin; the index stream is the only large traffic.
+#include "ctx.cuh"
+
+#include <math.h>
+#include <vector>
+
+namespace snapb {
+
+namespace {
+
+// ------------------------------------------------------------------------
+// Feature selection (embedding.rs:36-39)
+// ------------------------------------------------------------------------
+__global__ void count_kept_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                  const int64_t* __restrict__ remap, const uint8_t* __restrict__ keep,
+                                  int64_t nrows, int32_t* __restrict__ len) {
+    int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = warp; r < nrows; r += nwarps) {
+        int cnt = 0;
+        for (int64_t p = ptr[r] + lane; p < ptr[r + 1]; p += 32) cnt += keep[idx[p]] ? 1 : 0;
+        cnt = static_cast<int>(warp_sum(static_cast<float>(cnt)) + 0.5f);
+        if (lane == 0) len[r] = cnt;
+    }
+}
+
+__global__ void compact_kept_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                    const float* __restrict__ val, const int64_t* __restrict__ remap,
+                                    const uint8_t* __restrict__ keep, int64_t nrows,
+                                    const int64_t* __restrict__ nptr, int32_t* __restrict__ nidx,
+                                    float* __restrict__ nval) {
+    int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = warp; r < nrows; r += nwarps) {
+        int64_t out = nptr[r];
+        int64_t s = ptr[r], e = ptr[r + 1];
+        for (int64_t base = s; base < e; base += 32) {
+            int64_t p = base + lane;
+            int j = (p < e) ? idx[p] : 0;
+            bool k = (p < e) && keep[j];
+            unsigned mask = __ballot_sync(0xffffffffu, k);
+            if (k) {
+                int off = __popc(mask & ((1u << lane) - 1u));
+                nidx[out + off] = static_cast<int32_t>(remap[j]);
+                if (val) nval[out + off] = val[p];
+            }
+            out += __popc(mask);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------
+// Deterministic transpose: column histogram, scan, then per row slab a
+// feature x slab-row bitmap (atomicOr is order independent) that one thread
+// per feature walks in row order.  Output rows (features) therefore list
+// their cells in ascending order regardless of scheduling.
+// ------------------------------------------------------------------------
+__global__ void col_count_kernel(const int32_t* __restrict__ idx, int64_t nnz, int32_t* __restrict__ cnt) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (; i < nnz; i += stride) atomicAdd(&cnt[ld_stream_int(idx + i)], 1);
+}
+
+__global__ void bitmap_set_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                  int64_t r0, int64_t r1, int64_t m, uint32_t* __restrict__ bm) {
+    int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = r0 + warp; r < r1; r += nwarps) {
+        int64_t il = r - r0;
+        uint32_t* plane = bm + (il >> 5) * m;
+        uint32_t bit = 1u << (il & 31);
+        for (int64_t p = ptr[r] + lane; p < ptr[r + 1]; p += 32) atomicOr(plane + ld_stream_int(idx + p), bit);
+    }
+}
+
+// position of column j inside row r (indices sorted) -- values path only
+__device__ __forceinline__ int64_t find_in_row(const int32_t* __restrict__ idx, int64_t s, int64_t e, int32_t j) {
+    while (s < e) {
+        int64_t mid = (s + e) >> 1;
+        if (idx[mid] < j) s = mid + 1; else e = mid;
+    }
+    return s;
+}
+
+__global__ void bitmap_emit_kernel(const uint32_t* __restrict__ bm, int64_t m, int planes, int64_t r0,
+                                   int64_t* __restrict__ cursor, int32_t* __restrict__ tidx,
+                                   const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                   const float* __restrict__ val, float* __restrict__ tval) {
+    int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    int64_t cur = cursor[j];
+    for (int k = 0; k < planes; ++k) {
+        uint32_t word = bm[static_cast<int64_t>(k) * m + j];
+        while (word) {
+            int bit = __ffs(word) - 1;
+            word &= word - 1;
+            int64_t r = r0 + k * 32 + bit;
+            tidx[cur] = static_cast<int32_t>(r);
+            if (val) tval[cur] = val[find_in_row(idx, ptr[r], ptr[r + 1], static_cast<int32_t>(j))];
+            ++cur;
+        }
+    }
+    cursor[j] = cur;
+}
+
+// ------------------------------------------------------------------------
+// IDF (embedding.rs:269-286)
+// ------------------------------------------------------------------------
+__global__ void df_minmax_kernel(const int64_t* __restrict__ df, int64_t m, int64_t* __restrict__ mm) {
+    // single block
+    __shared__ int64_t smin[256], smax[256];
+    int64_t lo = INT64_MAX, hi = INT64_MIN;
+    for (int64_t j = threadIdx.x; j < m; j += blockDim.x) {
+        int64_t v = df[j];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+    smin[threadIdx.x] = lo;
+    smax[threadIdx.x] = hi;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            smin[threadIdx.x] = min(smin[threadIdx.x], smin[threadIdx.x + s]);
+            smax[threadIdx.x] = max(smax[threadIdx.x], smax[threadIdx.x + s]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { mm[0] = smin[0]; mm[1] = smax[0]; }
+}
+
+__global__ void idf_kernel(const int64_t* __restrict__ df, const int64_t* __restrict__ mm, int64_t m,
+                           double n_total, double* __restrict__ w) {
+    int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    if (mm[0] == mm[1]) { w[j] = 1.0; return; }      // all_equal -> ones (:273-274)
+    double x = static_cast<double>(df[j]);
+    if (x == 0.0) x = 1.0;                            // :277-278
+    else if (x == n_total) x = n_total - 1.0;         // :279-280
+    w[j] = log(n_total / x);                          // :282
+}
+
+__global__ void i32_to_i64_kernel(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+// ------------------------------------------------------------------------
+// fp64 gather SpMVs, one warp per row
+// ------------------------------------------------------------------------
+// MODE 0: out[r] = sqrt(sum (val*vec[idx])^2)            row norms   (:321-323)
+// MODE 1: out[r] = scale[r] * sum val*vec[idx]           column sums (:139-144) / degrees (:145)
+template <int MODE>
+__global__ void __launch_bounds__(256)
+spmv_f64_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
+                const double* __restrict__ vec, const double* __restrict__ scale, double shift, int64_t nrows,
+                double* __restrict__ out) {
+    int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t r = warp; r < nrows; r += nwarps) {
+        int64_t s = ptr[r], e = ptr[r + 1];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int64_t p = s + lane;
+        for (; p + 96 < e; p += 128) {
+            int j0 = ld_stream_int(idx + p), j1 = ld_stream_int(idx + p + 32);
+            int j2 = ld_stream_int(idx + p + 64), j3 = ld_stream_int(idx + p + 96);
+            double x0 = vec[j0], x1 = vec[j1], x2 = vec[j2], x3 = vec[j3];
+            if (val) {
+                x0 *= static_cast<double>(val[p]);      x1 *= static_cast<double>(val[p + 32]);
+                x2 *= static_cast<double>(val[p + 64]); x3 *= static_cast<double>(val[p + 96]);
+            }
+            if (MODE == 0) { a0 += x0 * x0; a1 += x1 * x1; a2 += x2 * x2; a3 += x3 * x3; }
+            else           { a0 += x0;      a1 += x1;      a2 += x2;      a3 += x3; }
+        }
+        for (; p < e; p += 32) {
+            double x0 = vec[ld_stream_int(idx + p)];
+            if (val) x0 *= static_cast<double>(val[p]);
+            a0 += (MODE == 0) ? x0 * x0 : x0;
+        }
+        double acc = warp_sum((a0 + a1) + (a2 + a3));
+        if (lane == 0) {
+            if (MODE == 0) out[r] = sqrt(acc);
+            else out[r] = (scale ? scale[r] : 1.0) * acc + shift;
+        }
+    }
+}
+
+__global__ void recip_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = 1.0 / in[i];
+}
+__global__ void mul_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int64_t n) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] * b[i];
+}
+
+// sum of degrees + count of degenerate rows (block partials, fixed order)
+__global__ void degree_stats_kernel(const double* __restrict__ d, int64_t n, double* __restrict__ part_sum,
+                                    int64_t* __restrict__ part_bad) {
+    __shared__ double ssum[256];
+    __shared__ int64_t sbad[256];
+    double s = 0.0;
+    int64_t bad = 0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        double v = d[i];
+        if (!(v > 0.0) || isinf(v)) ++bad; else s += v;
+    }
+    ssum[threadIdx.x] = s;
+    sbad[threadIdx.x] = bad;
+    __syncthreads();
+    for (int k = blockDim.x / 2; k > 0; k >>= 1) {
+        if (threadIdx.x < k) { ssum[threadIdx.x] += ssum[threadIdx.x + k]; sbad[threadIdx.x] += sbad[threadIdx.x + k]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part_sum[blockIdx.x] = ssum[0]; part_bad[blockIdx.x] = sbad[0]; }
+}
+
+__global__ void derive_rows_kernel(const double* __restrict__ d, const double* __restrict__ rho, double inv_norm,
+                                   int64_t n, float* __restrict__ r, float* __restrict__ dinv, float* __restrict__ u1) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double di = d[i];
+    double inv = 1.0 / di;
+    dinv[i] = static_cast<float>(inv);
+    r[i] = static_cast<float>(sqrt(inv) / rho[i]);
+    u1[i] = static_cast<float>(sqrt(di) * inv_norm);
+}
+__global__ void derive_cols_kernel(const double* __restrict__ w, int64_t m, float* __restrict__ w2) {
+    int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j < m) w2[j] = static_cast<float>(w[j] * w[j]);
+}
+
+inline int grid_for_rows(snapb200_ctx* c, int64_t nrows) {
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(nrows, 8), static_cast<int64_t>(c->num_sms) * 16)));
+}
+inline unsigned grid1d(int64_t n, int threads = 256) { return static_cast<unsigned>(std::max<int64_t>(1, ceil_div(n, threads))); }
+
+float elapsed_ms(snapb200_ctx* c) {
+    SB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    SB_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    SB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    return ms;
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------
+void select_features(snapb200_ctx* c, const uint8_t* keep_host, int64_t m) {
+    SB_CHECK(c->loaded, "select_features: no matrix loaded");
+    SB_CHECK(m == c->m, "select_features: mask length must equal the number of columns");
+    Csr& X = c->X;
+    DevBuf<uint8_t> keep;
+    DevBuf<int32_t> keep32, len;
+    DevBuf<int64_t> remap, nptr;
+    keep.alloc(m);
+    SB_CUDA(cudaMemcpyAsync(keep.p, keep_host, static_cast<size_t>(m), cudaMemcpyHostToDevice, c->stream));
+    std::vector<int32_t> k32(static_cast<size_t>(m));
+    int64_t m_new = 0;
+    for (int64_t j = 0; j < m; ++j) { k32[j] = keep_host[j] ? 1 : 0; m_new += k32[j]; }
+    SB_CHECK(m_new > 0, "select_features: no feature selected");
+    keep32.alloc(m);
+    SB_CUDA(cudaMemcpyAsync(keep32.p, k32.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, c->stream));
+    remap.alloc(m + 1);
+    exclusive_scan_i32_to_i64(c, keep32.p, remap.p, m);
+
+    len.alloc(std::max<int64_t>(1, X.nrows));
+    nptr.alloc(X.nrows + 1);
+    int g = grid_for_rows(c, X.nrows);
+    count_kept_kernel<<<g, 256, 0, c->stream>>>(X.ptr.p, X.idx.p, remap.p, keep.p, X.nrows, len.p);
+    SB_LAUNCH_CHECK();
+    exclusive_scan_i32_to_i64(c, len.p, nptr.p, X.nrows);
+    int64_t nnz = 0;
+    SB_CUDA(cudaMemcpyAsync(&nnz, nptr.p + X.nrows, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    DevBuf<int32_t> nidx;
+    DevBuf<float> nval;
+    nidx.alloc(std::max<int64_t>(1, nnz));
+    if (X.has_values()) nval.alloc(std::max<int64_t>(1, nnz));
+    compact_kept_kernel<<<g, 256, 0, c->stream>>>(X.ptr.p, X.idx.p, X.val.p, remap.p, keep.p, X.nrows, nptr.p,
+                                                 nidx.p, nval.p);
+    SB_LAUNCH_CHECK();
+    count_launch(c, 2);
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    X.ptr.swap(nptr);
+    X.idx.swap(nidx);
+    if (X.has_values()) X.val.swap(nval);
+    X.nnz = nnz;
+    X.ncols = m_new;
+    c->m = m_new;
+    c->prepared = false;
+    c->stats.nnz_local = nnz;
+}
+
+// --------------------------------------------------------------------------
+// Builds c->Xt and leaves the local column counts in `cnt_out` (m int32).
+static void build_transpose_impl(snapb200_ctx* c, DevBuf<int32_t>& cnt) {
+    Csr& X = c->X;
+    Csr& T = c->Xt;
+    const int64_t m = c->m, n = X.nrows, nnz = X.nnz;
+    T.nrows = m;
+    T.ncols = n;
+    T.nnz = nnz;
+    cnt.alloc(m);
+    SB_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int32_t) * m, c->stream));
+    if (nnz > 0) {
+        int blocks = static_cast<int>(std::min<int64_t>(ceil_div(nnz, 256), static_cast<int64_t>(c->num_sms) * 32));
+        col_count_kernel<<<blocks, 256, 0, c->stream>>>(X.idx.p, nnz, cnt.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
+    T.ptr.alloc(m + 1);
+    exclusive_scan_i32_to_i64(c, cnt.p, T.ptr.p, m);
+    T.idx.alloc(std::max<int64_t>(1, nnz));
+    if (X.has_values()) T.val.alloc(std::max<int64_t>(1, nnz)); else T.val.release();
+    if (nnz == 0 || n == 0) return;
+
+    DevBuf<int64_t> cursor;
+    cursor.alloc(m);
+    SB_CUDA(cudaMemcpyAsync(cursor.p, T.ptr.p, sizeof(int64_t) * m, cudaMemcpyDeviceToDevice, c->stream));
+
+    // slab height: bitmap of m x S bits kept around 64 MB
+    int64_t S = ((512ll << 20) / std::max<int64_t>(m, 1)) / 32 * 32;
+    S = std::max<int64_t>(32, std::min<int64_t>(S, 8192));
+    S = std::min<int64_t>(S, ceil_div(n, 32) * 32);
+    const int planes = static_cast<int>(S / 32);
+    DevBuf<uint32_t> bm;
+    bm.alloc(static_cast<int64_t>(planes) * m);
+    for (int64_t r0 = 0; r0 < n; r0 += S) {
+        int64_t r1 = std::min<int64_t>(n, r0 + S);
+        SB_CUDA(cudaMemsetAsync(bm.p, 0, sizeof(uint32_t) * static_cast<size_t>(planes) * m, c->stream));
+        int g = grid_for_rows(c, r1 - r0);
+        bitmap_set_kernel<<<g, 256, 0, c->stream>>>(X.ptr.p, X.idx.p, r0, r1, m, bm.p);
+        SB_LAUNCH_CHECK();
+        int pl = static_cast<int>(ceil_div(r1 - r0, 32));
+        bitmap_emit_kernel<<<grid1d(m), 256, 0, c->stream>>>(bm.p, m, pl, r0, cursor.p, T.idx.p, X.ptr.p, X.idx.p,
+                                                            X.val.p, T.val.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c, 2);
+    }
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+}
+
+void build_transpose(snapb200_ctx* c) {
+    DevBuf<int32_t> cnt;
+    build_transpose_impl(c, cnt);
+}
+
+// --------------------------------------------------------------------------
+void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
+    SB_CHECK(c->loaded, "prepare: no matrix loaded");
+    Csr& X = c->X;
+    const int64_t m = c->m, n = c->n_local;
+    SB_CHECK(m >= 1, "prepare: matrix has no columns");
+    cudaStream_t st = c->stream;
+
+    // ---- feature-major copy + local document frequencies
+    SB_CUDA(cudaEventRecord(c->ev0, st));
+    DevBuf<int32_t> cnt;
+    build_transpose_impl(c, cnt);
+    c->stats.ms_transpose = elapsed_ms(c);
+
+    SB_CUDA(cudaEventRecord(c->ev0, st));
+    // ---- weights
+    c->w.alloc(m);
+    if (!c->user_weights.empty()) {
+        SB_CHECK(static_cast<int64_t>(c->user_weights.size()) == m,
+                 "feature_weights length must equal the number of selected features");
+        SB_CUDA(cudaMemcpyAsync(c->w.p, c->user_weights.data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    } else {
+        DevBuf<int64_t> df, mm;
+        df.alloc(m);
+        mm.alloc(2);
+        i32_to_i64_kernel<<<grid1d(m), 256, 0, st>>>(cnt.p, df.p, m);
+        SB_LAUNCH_CHECK();
+        allreduce_i64(c, df.p, m);
+        df_minmax_kernel<<<1, 256, 0, st>>>(df.p, m, mm.p);
+        SB_LAUNCH_CHECK();
+        idf_kernel<<<grid1d(m), 256, 0, st>>>(df.p, mm.p, m, static_cast<double>(c->n_global), c->w.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c, 3);
+        SB_CUDA(cudaStreamSynchronize(st));
+    }
+    cnt.release();
+
+    // ---- row norms rho_i = || w .* x_i ||                       (:315-326)
+    c->rho.alloc(std::max<int64_t>(1, n));
+    c->degree.alloc(std::max<int64_t>(1, n));
+    c->csum.alloc(m);
+    DevBuf<double> rinv, wc;
+    rinv.alloc(std::max<int64_t>(1, n));
+    wc.alloc(m);
+    if (n > 0) {
+        spmv_f64_kernel<0><<<grid_for_rows(c, n), 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, c->w.p, nullptr, 0.0, n,
+                                                               c->rho.p);
+        SB_LAUNCH_CHECK();
+        recip_kernel<<<grid1d(n), 256, 0, st>>>(c->rho.p, rinv.p, n);
+        SB_LAUNCH_CHECK();
+        count_launch(c, 2);
+    }
+    // ---- column sums c_j = w_j sum_i x_ij / rho_i               (:139-144)
+    spmv_f64_kernel<1><<<grid_for_rows(c, m), 256, 0, st>>>(c->Xt.ptr.p, c->Xt.idx.p, c->Xt.val.p, rinv.p, c->w.p,
+                                                           0.0, m, c->csum.p);
+    SB_LAUNCH_CHECK();
+    allreduce_f64(c, c->csum.p, m);
+    mul_kernel<<<grid1d(m), 256, 0, st>>>(c->w.p, c->csum.p, wc.p, m);
+    SB_LAUNCH_CHECK();
+    count_launch(c, 2);
+    // ---- degrees d_i = (1/rho_i) sum_j x_ij w_j c_j - 1         (:145-146)
+    if (n > 0) {
+        spmv_f64_kernel<1><<<grid_for_rows(c, n), 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, wc.p, rinv.p, -1.0, n,
+                                                               c->degree.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
+    // ---- global sum of degrees, degenerate-row check
+    const int nb = 256;
+    DevBuf<double> psum;
+    DevBuf<int64_t> pbad;
+    psum.alloc(nb);
+    pbad.alloc(nb);
+    degree_stats_kernel<<<nb, 256, 0, st>>>(c->degree.p, n, psum.p, pbad.p);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+    std::vector<double> hsum(nb);
+    std::vector<int64_t> hbad(nb);
+    SB_CUDA(cudaMemcpyAsync(hsum.data(), psum.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(hbad.data(), pbad.p, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    double tot[2] = {0.0, 0.0};
+    for (int i = 0; i < nb; ++i) { tot[0] += hsum[i]; tot[1] += static_cast<double>(hbad[i]); }
+    if (c->nranks > 1) {
+        DevBuf<double> t2;
+        t2.alloc(2);
+        SB_CUDA(cudaMemcpyAsync(t2.p, tot, sizeof(double) * 2, cudaMemcpyHostToDevice, st));
+        allreduce_f64(c, t2.p, 2);
+        SB_CUDA(cudaMemcpyAsync(tot, t2.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+    }
+    if (degree_out && n > 0)
+        SB_CUDA(cudaMemcpyAsync(degree_out, c->degree.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    if (idf_out) SB_CUDA(cudaMemcpyAsync(idf_out, c->w.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    if (tot[1] > 0.0) {
+        char buf[256];
+        snprintf(buf, sizeof(buf),
+                 "%lld cell(s) have an empty row or a non-positive degree after feature weighting; the reference "
+                 "produces NaN here (embedding.rs:146,152,323)", static_cast<long long>(tot[1]));
+        throw Error(buf);
+    }
+
+    // ---- derived f32 vectors used by the operator
+    c->r.alloc(std::max<int64_t>(1, n));
+    c->dinv.alloc(std::max<int64_t>(1, n));
+    c->u1.alloc(std::max<int64_t>(1, n));
+    c->w2.alloc(m);
+    if (n > 0) {
+        derive_rows_kernel<<<grid1d(n), 256, 0, st>>>(c->degree.p, c->rho.p, 1.0 / sqrt(tot[0]), n, c->r.p, c->dinv.p,
+                                                     c->u1.p);
+        SB_LAUNCH_CHECK();
+    }
+    derive_cols_kernel<<<grid1d(m), 256, 0, st>>>(c->w.p, m, c->w2.p);
+    SB_LAUNCH_CHECK();
+    count_launch(c, 2);
+    SB_CUDA(cudaStreamSynchronize(st));
+    c->stats.ms_prepare = elapsed_ms(c);
+    c->prepared = true;
+}
+
+void view_frobenius(snapb200_ctx*, const int64_t*, int64_t, double*) {
+    throw Error("view_frobenius: multi-view support is not built yet");
+}
+
+}  // namespace snapb

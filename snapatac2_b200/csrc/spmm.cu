@@ -1,0 +1,165 @@
+// The matrix-free operator  Y = X~ (X~^T V) - dinv .* V  on a block of b vectors
+// (reference: the closure f(v) at snapatac2-python/src/embedding.rs:162-163,
+// applied one vector at a time by ARPACK; here b vectors per sweep).
+//
+// Factored form:  X~ = diag(r) P diag(w)  with P the stored
+// pattern (times the raw values when the matrix is not binarised),
+// r_i = sqrt(dinv_i)/rho_i.  Hence
+//   pass 1:  W  = w^2 .* ( P^T (r .* V) )      gather over the feature-major copy
+//   (all-reduce of W over the row shards)
+//   pass 2:  Y  = r .* ( P W ) - dinv .* V      gather over the cell-major rows
+// Both passes are gathers (no atomics), so results are bitwise reproducible.
+// The only large traffic is the int32 index stream: 4 B/nnz per pass.
+#include "ctx.cuh"
+
+#include <algorithm>
+
+namespace snapb {
+
+namespace {
+
+template <int B>
+__global__ void scale_rows_kernel(const float* __restrict__ V, int64_t ldv, const float* __restrict__ r, int64_t n,
+                                  float* __restrict__ out) {
+    int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n * B) return;
+    int64_t i = t / B;
+    int k = static_cast<int>(t - i * B);
+    out[t] = r[i] * V[i * ldv + k];
+}
+
+// out[row, 0:B] = rowscale[row] * sum_p val_p * in[idx_p, 0:B]  - subscale[row] * sub[row, 0:B]
+// one warp per row; `in` is packed (leading dimension B).
+template <int B, bool HAS_VAL, bool HAS_SUB>
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
+                   const float* __restrict__ in, const float* __restrict__ rowscale, int64_t nrows,
+                   float* __restrict__ out, int64_t ldo, const float* __restrict__ subscale,
+                   const float* __restrict__ sub, int64_t lds) {
+    constexpr int Q = B / 4;  // float4 per dense row
+    const float4* __restrict__ in4 = reinterpret_cast<const float4*>(in);
+    int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+
+    for (int64_t row = warp; row < nrows; row += nwarps) {
+        const int64_t s = ptr[row], e = ptr[row + 1];
+        float4 acc[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+        int64_t p = s + lane;
+        // 4 independent gathers in flight per lane
+        for (; p + 96 < e; p += 128) {
+            int j[4];
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                j[u] = ld_stream_int(idx + p + 32 * u);
+                v[u] = HAS_VAL ? ld_stream_float(val + p + 32 * u) : 1.f;
+            }
+            float4 x[4][Q];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < Q; ++q) x[u][q] = __ldg(in4 + static_cast<int64_t>(j[u]) * Q + q);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int q = 0; q < Q; ++q) {
+                    if (HAS_VAL) {
+                        acc[q].x = fmaf(v[u], x[u][q].x, acc[q].x); acc[q].y = fmaf(v[u], x[u][q].y, acc[q].y);
+                        acc[q].z = fmaf(v[u], x[u][q].z, acc[q].z); acc[q].w = fmaf(v[u], x[u][q].w, acc[q].w);
+                    } else {
+                        acc[q].x += x[u][q].x; acc[q].y += x[u][q].y; acc[q].z += x[u][q].z; acc[q].w += x[u][q].w;
+                    }
+                }
+        }
+        for (; p < e; p += 32) {
+            int j = ld_stream_int(idx + p);
+            float v = HAS_VAL ? ld_stream_float(val + p) : 1.f;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                float4 x = __ldg(in4 + static_cast<int64_t>(j) * Q + q);
+                acc[q].x = fmaf(v, x.x, acc[q].x); acc[q].y = fmaf(v, x.y, acc[q].y);
+                acc[q].z = fmaf(v, x.z, acc[q].z); acc[q].w = fmaf(v, x.w, acc[q].w);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            acc[q].x = warp_sum(acc[q].x); acc[q].y = warp_sum(acc[q].y);
+            acc[q].z = warp_sum(acc[q].z); acc[q].w = warp_sum(acc[q].w);
+        }
+        if (lane == 0) {
+            const float rs = rowscale[row];
+            float* o = out + row * ldo;
+#pragma unroll
+            for (int q = 0; q < Q; ++q) {
+                float4 y = make_float4(rs * acc[q].x, rs * acc[q].y, rs * acc[q].z, rs * acc[q].w);
+                if (HAS_SUB) {
+                    const float ss = subscale[row];
+                    const float* sp = sub + row * lds + 4 * q;
+                    y.x -= ss * sp[0]; y.y -= ss * sp[1]; y.z -= ss * sp[2]; y.w -= ss * sp[3];
+                }
+                *reinterpret_cast<float4*>(o + 4 * q) = y;
+            }
+        }
+    }
+}
+
+inline int grid_rows(snapb200_ctx* c, int64_t nrows) {
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(nrows, 8), static_cast<int64_t>(c->num_sms) * 16)));
+}
+
+template <int B>
+void apply_impl(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, cudaEvent_t* evs) {
+    const int64_t n = c->n_local, m = c->m;
+    cudaStream_t st = c->stream;
+    c->Vr.ensure(std::max<int64_t>(1, n * B));
+    c->W.ensure(m * B);
+    if (n > 0) {
+        scale_rows_kernel<B><<<static_cast<unsigned>(ceil_div(n * B, 256)), 256, 0, st>>>(V, ldv, c->r.p, n, c->Vr.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
+    if (evs) SB_CUDA(cudaEventRecord(evs[0], st));
+    // pass 1: W = w^2 .* P^T (r V)
+    if (c->Xt.has_values())
+        gather_rows_kernel<B, true, false><<<grid_rows(c, m), 256, 0, st>>>(
+            c->Xt.ptr.p, c->Xt.idx.p, c->Xt.val.p, c->Vr.p, c->w2.p, m, c->W.p, B, nullptr, nullptr, 0);
+    else
+        gather_rows_kernel<B, false, false><<<grid_rows(c, m), 256, 0, st>>>(
+            c->Xt.ptr.p, c->Xt.idx.p, nullptr, c->Vr.p, c->w2.p, m, c->W.p, B, nullptr, nullptr, 0);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+    if (evs) SB_CUDA(cudaEventRecord(evs[1], st));
+    allreduce_f32(c, c->W.p, m * B);
+    if (evs) SB_CUDA(cudaEventRecord(evs[2], st));
+    // pass 2: Y = r .* (P W) - dinv .* V
+    if (n > 0) {
+        if (c->X.has_values())
+            gather_rows_kernel<B, true, true><<<grid_rows(c, n), 256, 0, st>>>(
+                c->X.ptr.p, c->X.idx.p, c->X.val.p, c->W.p, c->r.p, n, Y, ldy, c->dinv.p, V, ldv);
+        else
+            gather_rows_kernel<B, false, true><<<grid_rows(c, n), 256, 0, st>>>(
+                c->X.ptr.p, c->X.idx.p, nullptr, c->W.p, c->r.p, n, Y, ldy, c->dinv.p, V, ldv);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
+    if (evs) SB_CUDA(cudaEventRecord(evs[3], st));
+}
+
+}  // namespace
+
+void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, int b, cudaEvent_t* evs) {
+    SB_CHECK(c->prepared, "operator: call prepare first");
+    SB_CHECK(ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "operator: Y must be 16-byte aligned");
+    switch (b) {
+        case 4: apply_impl<4>(c, V, ldv, Y, ldy, evs); break;
+        case 8: apply_impl<8>(c, V, ldv, Y, ldy, evs); break;
+        case 16: apply_impl<16>(c, V, ldv, Y, ldy, evs); break;
+        default: throw Error("operator: block width must be 4, 8 or 16");
+    }
+}
+
+}  // namespace snapb

@@ -1,0 +1,193 @@
+"""Thin object wrapper over one ``snapb200_ctx`` (one GPU).
+
+Host-side plumbing only: numpy buffers in, numpy buffers out.  All compute
+happens in the hand-written CUDA kernels behind the C ABI.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+
+
+class Engine:
+    def __init__(self, device: int | None = None):
+        lib = _lib.load()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self._lib = lib
+        self._ctx = C.c_void_p()
+        _lib.check(lib.snapb200_create(int(device), C.byref(self._ctx)))
+        self.device = int(device)
+        self.rank, self.nranks = 0, 1
+        self.n_local = self.n_global = self.row0 = self.m = 0
+
+    # ------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self._lib.snapb200_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------ multi-GPU
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _lib.check(_lib.load().snapb200_comm_unique_id(buf))
+        return buf.raw
+
+    def init_comm(self, rank: int, nranks: int, unique_id: bytes):
+        assert len(unique_id) == 128
+        _lib.check(self._lib.snapb200_comm_init(self._ctx, int(rank), int(nranks), unique_id))
+        self.rank, self.nranks = int(rank), int(nranks)
+
+    # ------------------------------------------------------------ data in
+    def load_arrays(self, indptr, indices, values, n_local, m, n_global=None, row0=0, on_device=False):
+        """Load a CSR row shard from raw arrays (numpy, or torch CUDA tensors
+        with ``on_device=True``).  ``values=None`` means a binarised pattern."""
+        n_global = n_local if n_global is None else n_global
+        bits = lambda a: 8 * (a.itemsize if isinstance(a, np.ndarray) else a.element_size())
+        vk = 0
+        if values is not None:
+            dt = values.dtype if isinstance(values, np.ndarray) else np.dtype(str(values.dtype).replace("torch.", ""))
+            vk = _lib.value_kind(dt)
+            if vk is None:
+                raise TypeError(f"unsupported value dtype {dt}")
+        _lib.check(self._lib.snapb200_load_csr(
+            self._ctx, int(n_local), int(n_global), int(row0), int(m),
+            _lib.ptr(indptr), bits(indptr), _lib.ptr(indices), bits(indices),
+            _lib.ptr(values), int(vk), 1 if on_device else 0))
+        self.n_local, self.n_global, self.row0, self.m = int(n_local), int(n_global), int(row0), int(m)
+
+    def load_csr(self, X, n_global=None, row0=0, binarized: bool | None = None):
+        """Load a scipy CSR row shard.  ``binarized=True`` skips the values
+        (caller guarantees every stored entry is 1)."""
+        if not sp.issparse(X):
+            X = sp.csr_matrix(np.asarray(X))
+        if X.format != "csr":
+            raise ValueError("X must be a CSR matrix (the reference rejects CSC input as well)")
+        if not X.has_sorted_indices:
+            X = X.sorted_indices()
+        indptr = np.ascontiguousarray(X.indptr)
+        indices = np.ascontiguousarray(X.indices)
+        values = None
+        if not binarized:
+            values = np.ascontiguousarray(X.data)
+            if _lib.value_kind(values.dtype) is None:
+                values = values.astype(np.float64)
+        self.load_arrays(indptr, indices, values, X.shape[0], X.shape[1], n_global, row0)
+
+    def generate(self, spec, row0=0, n_local=None):
+        """Synthetic planted-cluster rows generated on the device."""
+        n_local = spec.n - row0 if n_local is None else n_local
+        fc = np.ascontiguousarray(spec.feat_cdf, dtype=np.uint64)
+        cc = np.ascontiguousarray(spec.cluster_cdf, dtype=np.uint64)
+        bs = np.ascontiguousarray(spec.block_start, dtype=np.int64)
+        al = np.ascontiguousarray(spec.alpha, dtype=np.uint64)
+        _lib.check(self._lib.snapb200_generate(
+            self._ctx, int(n_local), int(spec.n), int(row0), int(spec.m), int(spec.nnz_row),
+            int(spec.n_clusters), C.c_uint64(spec.seed), _lib.ptr(fc), _lib.ptr(cc), _lib.ptr(bs), _lib.ptr(al)))
+        self.n_local, self.n_global, self.row0, self.m = int(n_local), int(spec.n), int(row0), int(spec.m)
+
+    def shape(self):
+        n, m, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        _lib.check(self._lib.snapb200_shape(self._ctx, C.byref(n), C.byref(m), C.byref(nnz)))
+        return n.value, m.value, nnz.value
+
+    def export_arrays(self, indptr=None, indices=None, values=None, with_values=False):
+        """Copy the resident CSR back into (optionally caller-provided) host arrays."""
+        n, m, nnz = self.shape()
+        indptr = np.empty(n + 1, dtype=np.int64) if indptr is None else indptr
+        indices = np.empty(nnz, dtype=np.int32) if indices is None else indices
+        if with_values and values is None:
+            values = np.empty(nnz, dtype=np.float32)
+        _lib.check(self._lib.snapb200_export_csr(self._ctx, _lib.ptr(indptr), _lib.ptr(indices), _lib.ptr(values)))
+        return indptr, indices, values
+
+    def export_csr(self) -> sp.csr_matrix:
+        n, m, nnz = self.shape()
+        indptr, indices, values = self.export_arrays(with_values=True)
+        if nnz < 2**31 - 1:
+            indptr = indptr.astype(np.int32)
+        return sp.csr_matrix((values, indices.astype(indptr.dtype, copy=False), indptr), shape=(n, m))
+
+    # ------------------------------------------------------------ path
+    def select_features(self, keep_mask):
+        keep = np.ascontiguousarray(np.asarray(keep_mask, dtype=bool).astype(np.uint8))
+        _lib.check(self._lib.snapb200_select_features(self._ctx, _lib.ptr(keep), int(keep.shape[0])))
+        self.m = int(keep.sum())
+
+    def set_feature_weights(self, w):
+        if w is None:
+            _lib.check(self._lib.snapb200_set_feature_weights(self._ctx, None, 0))
+        else:
+            w = np.ascontiguousarray(w, dtype=np.float64)
+            _lib.check(self._lib.snapb200_set_feature_weights(self._ctx, _lib.ptr(w), int(w.shape[0])))
+
+    def prepare(self, want_outputs=True):
+        """a3-a5.  Returns ``(idf[m], degree[n_local])`` (or None, None)."""
+        idf = np.empty(self.m, dtype=np.float64) if want_outputs else None
+        deg = np.empty(self.n_local, dtype=np.float64) if want_outputs else None
+        _lib.check(self._lib.snapb200_prepare(self._ctx, _lib.ptr(idf), _lib.ptr(deg)))
+        return idf, deg
+
+    def operator_apply(self, V):
+        V = np.ascontiguousarray(V, dtype=np.float32)
+        assert V.ndim == 2 and V.shape[0] == self.n_local
+        Y = np.empty_like(V)
+        _lib.check(self._lib.snapb200_operator_apply(self._ctx, _lib.ptr(V), _lib.ptr(Y), int(V.shape[1])))
+        return Y
+
+    def operator_time(self, b=8, iters=5, flush_l2=True):
+        p1, cm, p2 = C.c_double(), C.c_double(), C.c_double()
+        _lib.check(self._lib.snapb200_operator_time(self._ctx, int(b), int(iters), 1 if flush_l2 else 0,
+                                                    C.byref(p1), C.byref(cm), C.byref(p2)))
+        return p1.value, cm.value, p2.value
+
+    def eigsh(self, k, seed=0, tol=0.0, block=0, max_basis=0, max_ops=0, out_evecs=None):
+        evals = np.empty(k, dtype=np.float64)
+        evecs = np.empty((self.n_local, k), dtype=np.float64) if out_evecs is None else out_evecs
+        _lib.check(self._lib.snapb200_eigsh(self._ctx, int(k), int(seed), float(tol), int(block),
+                                            int(max_basis), int(max_ops), _lib.ptr(evals), _lib.ptr(evecs)))
+        return evals, evecs
+
+    def stats(self) -> dict:
+        s = _lib.Stats()
+        _lib.check(self._lib.snapb200_get_stats(self._ctx, C.byref(s)))
+        return s.as_dict()
+
+    def stream_handle(self) -> int:
+        """Raw ``cudaStream_t`` of the context (for torch.cuda.ExternalStream)."""
+        h = C.c_void_p()
+        _lib.check(self._lib.snapb200_get_stream(self._ctx, C.byref(h)))
+        return int(h.value or 0)
+
+    def dense_selftest(self, n=4099, ncq=136, p=30) -> float:
+        err = C.c_double()
+        _lib.check(self._lib.snapb200_dense_selftest(self._ctx, int(n), int(ncq), int(p), C.byref(err)))
+        return err.value
+
+
+def sym_eig(a: np.ndarray):
+    """Host Rayleigh-Ritz eigensolver of the library (no GPU needed)."""
+    a = np.array(a, dtype=np.float64, order="C")
+    n = a.shape[0]
+    w = np.empty(n, dtype=np.float64)
+    _lib.check(_lib.load().snapb200_sym_eig(n, _lib.ptr(a), _lib.ptr(w)))
+    return w, a

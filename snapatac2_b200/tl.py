@@ -1,0 +1,194 @@
+"""``snap.tl.spectral`` / ``snap.tl.multi_spectral`` on a B200.
+
+Host-side mirror of the reference's operator interface for this path
+(``snapatac2-python/python/snapatac2/tools/_embedding.py:129-295`` and
+``:483-540``): same names, same argument meaning, same side effects
+(``adata.obsm['X_spectral']``, ``adata.uns['spectral_eigenvalue']``), same
+exceptions.  Where the reference calls ``internal.spectral_embedding``
+(``_embedding.py:249`` -> ``snapatac2-python/src/embedding.rs:24-59``) this
+module drives ``libsnapb200.so`` through ctypes instead.
+
+There is no CPU fallback: the jaccard metric and the Nystrom ``sample_size``
+path of the reference are outside this build and raise NotImplementedError.
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import Literal
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import dist
+from .engine import Engine
+
+_engine: Engine | None = None
+
+
+def default_engine() -> Engine:
+    """Process-wide engine on ``cuda:LOCAL_RANK`` (created on first use and, under
+    torch.distributed, joined to a communicator spanning the world)."""
+    global _engine
+    if _engine is None:
+        _engine = Engine()
+        dist.attach_engine_comm(_engine)
+    return _engine
+
+
+def _resolve_features(adata, features):
+    """_embedding.py:225-229: a string names a boolean column of ``adata.var``."""
+    if isinstance(features, str):
+        if features in adata.var:
+            col = adata.var[features]
+            return col.to_numpy() if hasattr(col, "to_numpy") else np.asarray(col)
+        raise NameError("Please call `select_features` first or explicitly set `features = None`")
+    return features
+
+
+def _feature_mask(features, n_vars, feature_weights):
+    """Boolean keep-mask (+ weights re-ordered to ascending column order).
+
+    The reference slices columns in the order given (``to_select_elem``,
+    embedding.rs:36-39) and indexes ``feature_weights`` by the *sliced*
+    position (:321).  Column order does not change the embedding, so integer
+    index arrays are turned into a mask and the weights permuted to match.
+    """
+    if features is None:
+        return None, feature_weights
+    f = np.asarray(features)
+    if f.dtype == bool:
+        if f.shape[0] != n_vars:
+            raise ValueError("boolean feature mask must have length n_vars")
+        return f, feature_weights
+    idx = f.astype(np.int64)
+    idx = np.where(idx < 0, idx + n_vars, idx)
+    if idx.size and (idx.min() < 0 or idx.max() >= n_vars):
+        raise IndexError("feature index out of range")
+    if np.unique(idx).size != idx.size:
+        raise ValueError("duplicate feature indices are not supported")
+    mask = np.zeros(n_vars, dtype=bool)
+    mask[idx] = True
+    if feature_weights is not None:
+        order = np.argsort(idx, kind="stable")
+        feature_weights = np.asarray(feature_weights, dtype=np.float64)[order]
+    return mask, feature_weights
+
+
+def _get_csr(adata):
+    X = adata.X
+    if hasattr(X, "__getitem__") and not sp.issparse(X) and not isinstance(X, np.ndarray):
+        X = X[...]   # backed / lazy element
+    if isinstance(X, np.ndarray):
+        X = sp.csr_matrix(X)
+    if not sp.issparse(X) or X.format != "csr":
+        raise ValueError("adata.X must be a CSR matrix")
+    return X
+
+
+def spectral_embedding(engine: Engine, X, selected_features, n_components, random_state,
+                       feature_weights=None, *, n_global=None, row0=0, binarized=None,
+                       tol=0.0, block=0, max_basis=0, max_ops=0, return_parts=False):
+    """Counterpart of the PyO3 entry ``internal.spectral_embedding``
+    (embedding.rs:24-59): load -> [select] -> [weights] -> prepare -> eigsh."""
+    mask, fw = _feature_mask(selected_features, X.shape[1], feature_weights)
+    engine.load_csr(X, n_global=n_global, row0=row0, binarized=binarized)
+    if mask is not None:
+        engine.select_features(mask)
+    engine.set_feature_weights(fw)
+    idf, degree = engine.prepare(want_outputs=return_parts)
+    evals, evecs = engine.eigsh(n_components, seed=random_state, tol=tol, block=block,
+                                max_basis=max_basis, max_ops=max_ops)
+    if return_parts:
+        return evals, evecs, idf, degree
+    return evals, evecs
+
+
+def spectral(
+    adata,
+    n_comps: int = 30,
+    features: str | np.ndarray | None = "selected",
+    random_state: int = 0,
+    sample_size: int | float | None = None,
+    sample_method: Literal["random", "degree"] = "random",
+    chunk_size: int = 20000,
+    distance_metric: Literal["jaccard", "cosine"] = "cosine",
+    weighted_by_sd: bool = True,
+    feature_weights: list[float] | None = None,
+    inplace: bool = True,
+    *,
+    engine: Engine | None = None,
+    tol: float = 0.0,
+    block: int = 0,
+) -> tuple[np.ndarray, np.ndarray] | None:
+    """Laplacian-eigenmaps embedding, matrix-free, on the GPU.
+
+    Same call as ``snap.tl.spectral`` (tools/_embedding.py:129-141).  Under
+    ``torchrun`` every rank passes the AnnData holding *its* contiguous block
+    of cells (rank order = row order); eigenvalues are replicated and every
+    rank receives the embedding of its own rows.
+
+    Extra keyword-only knobs: ``engine`` (reuse a context), ``tol`` (relative
+    residual, default 1e-5; the reference asks ARPACK for machine precision),
+    ``block`` (Lanczos block width 4/8/16, default 8).
+    """
+    np.random.seed(random_state)                                    # :223
+
+    features = _resolve_features(adata, features)                   # :225-229
+
+    rank, ws = dist.world()
+    n_local = adata.n_obs
+    if ws > 1:
+        n_locals = dist.allgather_ints(n_local)
+        n_global, row0 = sum(n_locals), dist.shard_offsets(n_locals)[rank]
+    else:
+        n_global, row0 = n_local, 0
+
+    n_comps = min(adata.n_vars - 1, n_global - 1, n_comps)          # :231
+
+    n_sample = n_global                                             # :233-245
+    if sample_size is None:
+        sample_size = n_sample
+    elif isinstance(sample_size, int):
+        if sample_size <= 1:
+            raise ValueError("when sample_size is an integer, it should be > 1")
+        if sample_size > n_sample:
+            sample_size = n_sample
+    else:
+        if sample_size <= 0.0 or sample_size > 1.0:
+            raise ValueError("when sample_size is a float, it should be > 0 and <= 1")
+        sample_size = int(sample_size * n_sample)
+
+    if sample_size < n_sample:
+        raise NotImplementedError(
+            "the Nystrom approximation (sample_size < n_obs) is not part of the B200 path: the full "
+            "matrix-free operator is used instead; pass sample_size=None")
+    if distance_metric != "cosine":
+        raise NotImplementedError("only distance_metric='cosine' (the matrix-free path) runs on the GPU")
+
+    eng = engine if engine is not None else default_engine()
+    X = _get_csr(adata)
+    evals, evecs = spectral_embedding(eng, X, features, n_comps, random_state, feature_weights,
+                                      n_global=n_global, row0=row0, tol=tol, block=block)   # :249
+    logging.getLogger(__name__).info("spectral: %s", eng.stats())
+
+    if weighted_by_sd:                                              # :286-289
+        idx = [i for i in range(evals.shape[0]) if evals[i] > 0]
+        evals = evals[idx]
+        evecs = evecs[:, idx] * np.sqrt(evals)
+
+    if inplace:                                                     # :291-293
+        adata.uns["spectral_eigenvalue"] = evals
+        adata.obsm["X_spectral"] = evecs
+        return None
+    return evals, evecs
+
+
+def multi_spectral(adatas, n_comps: int = 30, features="selected", weights=None,
+                   random_state: int = 0, weighted_by_sd: bool = True):
+    """``snap.tl.multi_spectral`` (tools/_embedding.py:483-540).
+
+    Scope row (f)-2 of SURVEY.md section 8; the device-side view builder is not
+    in this round's build.
+    """
+    raise NotImplementedError("multi_spectral: the multi-view builder is not built yet (SURVEY.md 8f, rank 2)")

@@ -1,0 +1,174 @@
+"""GPU (-m gpu): the CUDA path through the C ABI against the CPU oracle, the
+committed golden vectors, and size-independent properties.
+
+Tolerances are north_star's: IDF weights and degrees 1e-5 relative,
+eigenvalues 1e-4 relative, eigenvectors |cos| >= 0.999 per component (subspace
+comparison inside near-degenerate clusters)."""
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+from conftest import load_golden, eigvec_agreement
+from snapatac2_b200 import synth, tl, MiniAnnData
+
+pytestmark = pytest.mark.gpu
+
+TOL_VEC = 1e-5      # idf, degree
+TOL_EVAL = 1e-4
+MIN_COS = 0.999
+
+
+def _check_against(z_evals, z_evecs, evals, evecs, skip_cluster_tail=False):
+    np.testing.assert_allclose(evals, z_evals, rtol=TOL_EVAL, atol=1e-9)
+    cos = eigvec_agreement(z_evals, z_evecs, evecs)
+    assert cos.min() >= MIN_COS, cos
+
+
+def test_dense_tensor_core_kernels_selftest(engine):
+    # DMMA Gram / projection / rotation against plain fp64 loops
+    for n, ncq, p in ((4099, 136, 30), (257, 8, 8), (1000, 64, 64), (33, 48, 5)):
+        assert engine.dense_selftest(n, ncq, p) < 1e-11
+
+
+def test_generator_is_bit_identical_to_host(engine):
+    spec = synth.make_spec(700, 30000, 900, n_clusters=16, seed=6)
+    engine.generate(spec)
+    dev = engine.export_csr()
+    host = synth.generate_csr(spec)
+    assert np.array_equal(dev.indptr, host.indptr)
+    assert np.array_equal(dev.indices, host.indices)
+    # a row shard regenerates exactly its rows
+    engine.generate(spec, row0=200, n_local=300)
+    part = engine.export_csr()
+    ref = host[200:500]
+    assert np.array_equal(part.indptr, ref.indptr) and np.array_equal(part.indices, ref.indices)
+
+
+@pytest.mark.parametrize("name", ["tile_600x4000", "counts_300x1000", "masked_400x3000"])
+def test_golden_vectors(engine, name):
+    X, z = load_golden(name)
+    feats = z["features"] if "features" in z else None
+    fw = z["feature_weights"] if "feature_weights" in z else None
+    evals, evecs, idf, deg = tl.spectral_embedding(engine, X, feats, int(z["k"]), 0, fw, return_parts=True)
+    np.testing.assert_allclose(idf, z["idf"], rtol=TOL_VEC)
+    np.testing.assert_allclose(deg, z["degree"], rtol=TOL_VEC)
+    _check_against(z["evals"], z["evecs"], evals, evecs)
+    assert evals[0] == pytest.approx(1.0, abs=1e-6)         # trivial pair kept
+    assert np.all(np.diff(evals) <= 0)                      # argsort()[::-1]
+
+
+def test_golden_dense_50x100_exhausts_krylov_space(engine):
+    # the reference's own test input shape (tests/test_tools.py:95-110): n=50, k=30
+    X, z = load_golden("dense_50x100")
+    evals, evecs, idf, deg = tl.spectral_embedding(engine, X, None, int(z["k"]), 0, return_parts=True)
+    np.testing.assert_allclose(idf, z["idf"], rtol=TOL_VEC)
+    np.testing.assert_allclose(deg, z["degree"], rtol=TOL_VEC)
+    np.testing.assert_allclose(evals, z["evals"], rtol=TOL_EVAL, atol=1e-7)
+    # eigenvalues here sit in one tight cluster: compare the invariant subspace
+    qa, _ = np.linalg.qr(evecs)
+    qb, _ = np.linalg.qr(z["evecs"])
+    assert np.linalg.svd(qa.T @ qb, compute_uv=False).min() > 0.99
+
+
+def test_operator_matches_oracle(engine):
+    spec = synth.make_spec(900, 20000, 500, n_clusters=14, seed=12)
+    X = synth.generate_csr(spec, dtype=np.float64)
+    engine.load_csr(X)
+    engine.set_feature_weights(None)
+    idf, deg = engine.prepare()
+    mat = sp.csr_matrix(X)
+    w = oracle.idf(mat)
+    xt, dinv, _, degree = oracle.operator_pieces(oracle.normalize(mat, w))
+    np.testing.assert_allclose(idf, w, rtol=TOL_VEC)
+    np.testing.assert_allclose(deg, degree, rtol=TOL_VEC)
+    rng = np.random.default_rng(0)
+    for b in (4, 8, 16):
+        V = rng.standard_normal((900, b)).astype(np.float32)
+        Y = engine.operator_apply(V)
+        want = xt @ (xt.T @ V.astype(np.float64)) - dinv[:, None] * V
+        err = np.abs(Y - want).max() / np.abs(want).max()
+        assert err < 2e-5, (b, err)
+    # linearity (size-independent property)
+    V1 = rng.standard_normal((900, 8)).astype(np.float32)
+    V2 = rng.standard_normal((900, 8)).astype(np.float32)
+    lhs = engine.operator_apply(V1 + V2)
+    rhs = engine.operator_apply(V1) + engine.operator_apply(V2)
+    assert np.abs(lhs - rhs).max() / np.abs(rhs).max() < 1e-5
+
+
+def test_config1_parity_against_oracle(engine):
+    # BASELINE.json configs[0]: 5k x 100k, ~3k nnz/cell, n_comps=30
+    spec = synth.make_spec(5000, 100000, 3000, n_clusters=48, seed=0)
+    engine.generate(spec)
+    X = engine.export_csr()
+    assert np.array_equal(X.indices, synth.generate_csr(spec).indices)
+    ev_o, evec_o, w_o, deg_o = oracle.spectral_embedding(X, None, 30, 0, return_parts=True)
+    engine.set_feature_weights(None)
+    idf, deg = engine.prepare()
+    np.testing.assert_allclose(idf, w_o, rtol=TOL_VEC)
+    np.testing.assert_allclose(deg, deg_o, rtol=TOL_VEC)
+    for block in (8, 4, 16):
+        evals, evecs = engine.eigsh(30, seed=0, block=block)
+        _check_against(ev_o, evec_o, evals, evecs)
+        st = engine.stats()
+        assert st["n_ops"] < 60 and st["max_residual"] < 1e-6
+
+
+def test_thick_restart_small_basis(engine):
+    X, z = load_golden("tile_600x4000")
+    engine.load_csr(X)
+    engine.set_feature_weights(None)
+    engine.prepare(want_outputs=False)
+    evals, evecs = engine.eigsh(int(z["k"]), seed=1, max_basis=48)     # forces restarts
+    assert engine.stats()["n_restarts"] >= 1
+    _check_against(z["evals"], z["evecs"], evals, evecs)
+
+
+def test_bitwise_reproducible(engine):
+    # the reference's only pinned property for this path (tests/test_tools.py:104-108)
+    X, z = load_golden("tile_600x4000")
+    ad = MiniAnnData(X)
+    runs = [tl.spectral(ad, n_comps=8, features=None, random_state=0, inplace=False, engine=engine)[1]
+            for _ in range(3)]
+    for r in runs[1:]:
+        np.testing.assert_array_equal(r, runs[0])
+
+
+def test_wrapper_side_effects_and_weighting(engine):
+    X, z = load_golden("counts_300x1000")
+    ad = MiniAnnData(X)
+    assert tl.spectral(ad, n_comps=5, features=None, engine=engine) is None
+    ev = ad.uns["spectral_eigenvalue"]
+    emb = ad.obsm["X_spectral"]
+    assert ev.dtype == np.float64 and emb.dtype == np.float64 and emb.shape == (300, len(ev))
+    keep = z["evals"] > 0
+    np.testing.assert_allclose(ev, z["evals"][keep], rtol=TOL_EVAL)
+    want = z["evecs"][:, keep] * np.sqrt(z["evals"][keep])
+    cos = np.abs(np.sum(emb * want, axis=0)) / (np.linalg.norm(emb, axis=0) * np.linalg.norm(want, axis=0))
+    assert cos.min() > MIN_COS
+    # integer index array as `features` (preprocessing/_basic.py:1069) == boolean mask
+    idx = np.flatnonzero(np.arange(1000) % 3 != 0)
+    a = tl.spectral(ad, n_comps=4, features=idx, weighted_by_sd=False, inplace=False, engine=engine)
+    mask = np.zeros(1000, bool)
+    mask[idx] = True
+    b = tl.spectral(ad, n_comps=4, features=mask, weighted_by_sd=False, inplace=False, engine=engine)
+    np.testing.assert_array_equal(a[0], b[0])
+    ev_o, _ = oracle.spectral_embedding(X, mask, 4, 0)
+    np.testing.assert_allclose(a[0], ev_o, rtol=TOL_EVAL)
+
+
+def test_degenerate_rows_are_reported(engine):
+    X = sp.csr_matrix(np.array([[1, 1, 0, 0], [0, 0, 0, 0], [0, 1, 1, 0], [1, 0, 1, 1.0]]))
+    with pytest.raises(RuntimeError, match="empty row or a non-positive degree"):
+        tl.spectral_embedding(engine, X, None, 2, 0)
+
+
+def test_int64_indices_and_count_dtypes(engine):
+    X, z = load_golden("counts_300x1000")
+    engine.load_arrays(X.indptr.astype(np.int64), X.indices.astype(np.int64), X.data.astype(np.uint32), 300, 1000)
+    engine.set_feature_weights(None)
+    idf, deg = engine.prepare()
+    np.testing.assert_allclose(idf, z["idf"], rtol=TOL_VEC)
+    np.testing.assert_allclose(deg, z["degree"], rtol=TOL_VEC)

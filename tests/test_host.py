@@ -1,0 +1,157 @@
+"""CPU: host-side logic -- library loads and exports the whole C ABI, the host
+Rayleigh-Ritz eigensolver, the synthetic generator's shard invariance, the
+wrapper's argument handling, the sharding helpers (incl. a world_size-2 gloo
+run)."""
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from snapatac2_b200 import synth, dist, tl, MiniAnnData, _lib
+from snapatac2_b200.engine import sym_eig
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = (ROOT / "include" / "snapb200.h").read_text()
+    declared = set(re.findall(r"\b(snapb200_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.snapb200_version() >= 100
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from snapatac2_b200 import Engine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Engine(0)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 64, 129])
+def test_sym_eig_matches_lapack(n):
+    rng = np.random.default_rng(n)
+    a = rng.standard_normal((n, n))
+    a = a + a.T
+    w, v = sym_eig(a)
+    np.testing.assert_allclose(w, np.linalg.eigvalsh(a), rtol=0, atol=1e-12 * max(1, n))
+    np.testing.assert_allclose(a @ v, v * w, atol=1e-11 * max(1, n))
+    np.testing.assert_allclose(v.T @ v, np.eye(n), atol=1e-12 * max(1, n))
+
+
+def test_sym_eig_degenerate_and_banded():
+    a = np.diag([2.0, 2.0, 2.0, -1.0, 0.0])
+    w, v = sym_eig(a)
+    np.testing.assert_allclose(w, [-1, 0, 2, 2, 2], atol=1e-14)
+    n = 40
+    t = np.diag(np.linspace(1, 2, n)) + np.diag(np.full(n - 8, 0.1), 8) + np.diag(np.full(n - 8, 0.1), -8)
+    w, v = sym_eig(t)
+    np.testing.assert_allclose(w, np.linalg.eigvalsh(t), atol=1e-13)
+
+
+def test_synth_is_shard_invariant_and_sorted():
+    spec = synth.make_spec(300, 5000, 200, n_clusters=10, seed=4)
+    full = synth.generate_csr(spec)
+    parts = [synth.generate_csr(spec, a, b) for a, b in ((0, 77), (77, 200), (200, 300))]
+    stacked = sp.vstack(parts, format="csr")
+    assert (full != stacked).nnz == 0
+    assert full.has_sorted_indices
+    rows = np.diff(full.indptr)
+    assert rows.max() <= 200 and rows.min() > 150
+    for i in range(0, 300, 37):
+        r = full.indices[full.indptr[i]:full.indptr[i + 1]]
+        assert np.all(np.diff(r) > 0)           # sorted, unique
+    z = synth.cluster_of_rows(spec, np.arange(300))
+    assert z.min() >= 0 and z.max() < 10 and len(np.unique(z)) >= 8
+
+
+def test_wrapper_argument_errors_before_any_gpu_work():
+    spec = synth.make_spec(50, 300, 20, n_clusters=3, seed=1)
+    ad = MiniAnnData(synth.generate_csr(spec))
+    with pytest.raises(NameError):
+        tl.spectral(ad)                                      # _embedding.py:229
+    with pytest.raises(ValueError):
+        tl.spectral(ad, features=None, sample_size=1)        # :238
+    with pytest.raises(ValueError):
+        tl.spectral(ad, features=None, sample_size=1.5)      # :243
+    with pytest.raises(NotImplementedError):
+        tl.spectral(ad, features=None, sample_size=10)
+    with pytest.raises(NotImplementedError):
+        tl.spectral(ad, features=None, distance_metric="jaccard")
+
+
+def test_feature_mask_and_weight_permutation():
+    mask, fw = tl._feature_mask(np.array([5, 1, 3]), 8, [50.0, 10.0, 30.0])
+    assert mask.tolist() == [False, True, False, True, False, True, False, False]
+    assert fw.tolist() == [10.0, 30.0, 50.0]
+    with pytest.raises(ValueError):
+        tl._feature_mask(np.array([1, 1]), 4, None)
+    m, _ = tl._feature_mask(np.array([True, False, True]), 3, None)
+    assert m.tolist() == [True, False, True]
+
+
+def test_row_split_helpers():
+    indptr = np.concatenate([[0], np.cumsum(np.r_[np.full(10, 100), np.full(90, 1)])])
+    b = dist.balanced_row_splits(indptr, 4)
+    assert b[0] == 0 and b[-1] == 100 and np.all(np.diff(b) >= 0)
+    nnz = np.diff(indptr[b])
+    assert nnz.max() <= 400                       # heavy rows spread, light rows lumped
+    assert dist.equal_row_splits(10, 3).tolist() == [0, 3, 6, 10]
+    assert dist.shard_offsets([3, 4, 5]) == [0, 3, 7]
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch.distributed as td
+from snapatac2_b200 import dist, synth
+td.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank, ws = dist.world()
+assert (rank, ws) == (int(sys.argv[1]), 2) and dist.is_distributed()
+# the unique-id exchange path (payload is opaque bytes)
+uid = bytes(range(128)) if rank == 0 else None
+got = dist.broadcast_bytes(uid, src=0)
+assert got == bytes(range(128))
+# shard bookkeeping: every rank generates its own row block, offsets come from an all-gather
+spec = synth.make_spec(120, 2000, 60, n_clusters=5, seed=8)
+bounds = dist.equal_row_splits(spec.n, ws)
+mine = synth.generate_csr(spec, int(bounds[rank]), int(bounds[rank + 1]))
+n_locals = dist.allgather_ints(mine.shape[0])
+assert sum(n_locals) == spec.n and dist.shard_offsets(n_locals)[rank] == int(bounds[rank])
+# global document frequencies = sum of shard counts (what the library all-reduces)
+import torch
+df = torch.from_numpy(np.bincount(mine.indices, minlength=spec.m).astype(np.int64))
+td.all_reduce(df)
+full = synth.generate_csr(spec)
+assert np.array_equal(df.numpy(), np.bincount(full.indices, minlength=spec.m))
+td.barrier()
+td.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    script = tmp_path / "worker.py"
+    script.write_text(_GLOO_WORKER.format(root=str(ROOT), port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+             for r in range(2)]
+    outs = [p.communicate(timeout=240)[0].decode() for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, o
+        assert f"ok {r}" in o
