@@ -1,0 +1,367 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ``snap.tl.spectral`` cells/s on a synthetic
+binarised tile matrix (BASELINE.json), plus the SpMM roofline line and the CPU
+baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c1|c2|c3|c4]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one full spectral embedding of the resident matrix: prepare
+(feature-major copy, IDF, row norms, column sums, degrees) + the block-Lanczos
+eigensolve + eigenvectors copied to the host.  `value` times K steps with the
+CSR already in HBM; `e2e` times the same call with the CSR in pinned host
+memory (host->device copy inside the timed region).  The workload is C3 of
+BASELINE.json (1M x 500k, ~5k nnz/cell, n_comps=30) at every N -- total work
+fixed, rows sharded across ranks ("scaling": "strong").
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+CONFIGS = {
+    # name: (n cells, m bins, nominal nnz/cell, clusters, n_comps)
+    "c1": (5_000, 100_000, 3_000, 48, 30),
+    "c2": (100_000, 500_000, 5_000, 48, 30),
+    "c3": (1_000_000, 500_000, 5_000, 48, 30),
+    "c4": (10_000_000, 500_000, 3_000, 64, 50),
+    "tiny": (2_000, 20_000, 500, 40, 30),
+}
+CONFIG_TEXT = {
+    "c1": "synthetic 5k-cell x 100k-bin binarised tile matrix (~3k nnz/cell), n_comps=30",
+    "c2": "synthetic 100k cells x 500k bins (~5k nnz/cell), n_comps=30",
+    "c3": "synthetic 1M cells x 500k bins (~5k nnz/cell), n_comps=30, row-sharded",
+    "c4": "synthetic 10M cells x 500k bins (~3k nnz/cell), n_comps=50, row-sharded",
+    "tiny": "synthetic 2k x 20k (~500 nnz/cell), n_comps=30 (harness test only)",
+}
+METRIC = "snap.tl.spectral cells/s"
+CPU_SAMPLE_ROWS = 4000
+
+
+def peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while running."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------
+# CPU legs (the only place bench.py runs oracle/)
+# --------------------------------------------------------------------------
+def cpu_oracle_step(cfg_name, rows=CPU_SAMPLE_ROWS):
+    """One run of the reference's CPU path (oracle: same scipy ARPACK call) on a
+    bounded sample: the first `rows` cells of the workload, all bins."""
+    import oracle
+    from snapatac2_b200 import synth
+    n, m, nnz_row, K, k = CONFIGS[cfg_name]
+    rows = min(rows, n)
+    spec = synth.make_spec(n, m, nnz_row, K, seed=0)
+    X = synth.generate_csr(spec, 0, rows, dtype=np.float64)
+    counter = [0]
+    t0 = time.perf_counter()
+    oracle.spectral_embedding(X, None, min(k, rows - 1), 0, counter=counter)
+    dt = time.perf_counter() - t0
+    return rows / dt, dt, counter[0], rows, X.nnz
+
+
+def thread_info():
+    info = {"cpu_count": os.cpu_count(), "OMP_NUM_THREADS": os.environ.get("OMP_NUM_THREADS")}
+    try:
+        from threadpoolctl import threadpool_info
+        info["blas_threads"] = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        pass
+    return info
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU implementation of the path (the
+    oracle restatement -- the Rust extension cannot be built here) on this box's
+    host cores.  scipy's sparse kernels are single-threaded, exactly as in the
+    reference, whose mat-vec is the same scipy call (embedding.rs:162-163)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    warm = max(0, min(args.warmup, 1))
+    for _ in range(warm):
+        cpu_oracle_step(args.config)
+    vals, times, mv = [], [], 0
+    for _ in range(steps):
+        v, dt, mv, rows, nnz = cpu_oracle_step(args.config)
+        vals.append(v); times.append(dt)
+    value = float(np.mean(vals))
+    ti = thread_info()
+    sample = (f"first {rows} cells of the workload (all {CONFIGS[args.config][1]} bins, nnz={nnz}); full oracle run incl. "
+              f"ARPACK ({mv} mat-vecs); cells/s = sample cells / wall time (cost is linear in cells)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": CONFIG_TEXT[args.config], "config": args.config},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": 1, "kind": "port", "sample": sample,
+                         "threads": ti},
+        "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as td
+
+    from snapatac2_b200 import Engine, dist, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world,
+                              device_id=torch.device("cuda", local_rank))
+
+    n, m, nnz_row, K, k = CONFIGS[args.config]
+    spec = synth.make_spec(n, m, nnz_row, K, seed=0)
+    bounds = dist.equal_row_splits(n, world)
+    row0, row1 = int(bounds[rank]), int(bounds[rank + 1])
+    n_local = row1 - row0
+
+    eng = Engine(local_rank)
+    dist.attach_engine_comm(eng)
+    ext_stream = torch.cuda.ExternalStream(eng.stream_handle(), device=torch.device("cuda", local_rank))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize()
+
+    t_gen = time.perf_counter()
+    eng.generate(spec, row0=row0, n_local=n_local)
+    _, _, nnz_local = eng.shape()
+    t_gen = time.perf_counter() - t_gen
+
+    evecs = np.empty((n_local, k), dtype=np.float64)
+
+    def step():
+        eng.prepare(want_outputs=False)
+        return eng.eigsh(k, seed=0, tol=args.tol, block=args.block, out_evecs=evecs)
+
+    for _ in range(args.warmup):
+        step()
+
+    # ---- timed region: K steps, device events on the library's stream, max over ranks
+    sampler = ClockSampler(local_rank)
+    launches0 = eng.stats()["kernel_launches"]
+    sync_all()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext_stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        evals, _ = step()
+    ev1.record(ext_stream)
+    ev1.synchronize()
+    wall = time.perf_counter() - t0
+    sync_all()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = eng.stats()["kernel_launches"] - launches0
+    stats = eng.stats()
+
+    tmax = torch.tensor([dev_ms, wall * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        td.all_reduce(tmax, op=td.ReduceOp.MAX)
+    total_ms = float(tmax[0].item())
+    wall_ms = float(tmax[1].item())
+    ms_per_step = total_ms / args.steps
+    value = n / (ms_per_step / 1e3)
+
+    # ---- roofline of the SpMM pair (the dominant kernels), timed alone with L2 flushed
+    b = stats["block"] or 8
+    p1, cm, p2 = eng.operator_time(b=b, iters=args.op_iters, flush_l2=True)
+    rt = torch.tensor([p1, cm, p2], dtype=torch.float64, device="cuda")
+    if world > 1:
+        td.all_reduce(rt, op=td.ReduceOp.MAX)
+    p1, cm, p2 = [float(x) for x in rt.tolist()]
+    bytes_p1 = 4 * nnz_local + 8 * (m + 1) + 4 * b * n_local + 4 * b * m + 4 * m          # idx, ptr, read rV, write W, w^2
+    bytes_p2 = 4 * nnz_local + 8 * (n_local + 1) + 4 * b * m + 3 * 4 * b * n_local + 8 * n_local  # idx, ptr, read W, V/Y, r/dinv
+    peak, peak_src = peak_hbm()
+    achieved = (bytes_p1 + bytes_p2) / ((p1 + p2) * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "spmm_traffic.json"
+    if tf.exists():
+        try:
+            traffic = json.loads(tf.read_text()).get("dram_bytes_per_application")
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": traffic, "peak_source": peak_src, "kernel": f"gather_rows_kernel<{b}> pass1+pass2 (one operator application)",
+        "algorithmic_bytes": bytes_p1 + bytes_p2, "ms_pass1": p1, "ms_pass2": p2, "ms_allreduce": cm,
+        "frac_pass1": bytes_p1 / (p1 * 1e-3) / 1e9 / peak, "frac_pass2": bytes_p2 / (p2 * 1e-3) / 1e9 / peak,
+        "frac_nominal_8TBs": achieved / 8000.0, "per_gpu": True,
+    }
+
+    # ---- e2e: CSR in pinned host memory -> load + prepare + eigsh -> evecs on host
+    e2e = None
+    if not args.no_e2e:
+        try:
+            h_ptr = torch.empty(n_local + 1, dtype=torch.int64).pin_memory()
+            h_idx = torch.empty(max(1, nnz_local), dtype=torch.int32).pin_memory()
+            pinned = True
+        except Exception:
+            h_ptr = torch.empty(n_local + 1, dtype=torch.int64)
+            h_idx = torch.empty(max(1, nnz_local), dtype=torch.int32)
+            pinned = False
+        np_ptr, np_idx = h_ptr.numpy(), h_idx.numpy()[:nnz_local]
+        eng.export_arrays(indptr=np_ptr, indices=np_idx)
+
+        def e2e_step():
+            eng.load_arrays(np_ptr, np_idx, None, n_local, m, n_global=n, row0=row0)
+            eng.prepare(want_outputs=False)
+            return eng.eigsh(k, seed=0, tol=args.tol, block=args.block, out_evecs=evecs)
+
+        e2e_step()   # warm-up
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            td.all_reduce(tt, op=td.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": n * args.e2e_steps / dt, "unit": "cells/s", "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "h2d_bytes_per_step": int(np_ptr.nbytes + np_idx.nbytes), "d2h_bytes_per_step": int(evecs.nbytes + 8 * k),
+               "steps": args.e2e_steps, "pinned_host": pinned, "per_rank_bytes": True,
+               "api": "Engine.load_arrays + prepare + eigsh (the calls tl.spectral makes), host numpy buffers"}
+        del h_ptr, h_idx
+
+    # ---- CPU baseline beside it (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, dt, mv, rows, nnz_s = cpu_oracle_step(args.config)
+        cpu = {"value": v, "unit": "cells/s", "cores": 1, "kind": "port",
+               "sample": f"first {rows} cells of the workload (nnz={nnz_s}), full oracle run incl. ARPACK ({mv} mat-vecs) in {dt:.1f} s; "
+                         f"scipy sparse kernels are single-threaded as in the reference",
+               "threads": thread_info()}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CONFIG_TEXT[args.config], "config": args.config, "n_cells": n, "n_bins": m,
+                       "nnz_per_gpu": nnz_local, "n_comps": k, "block": b, "tol": args.tol or 1e-5,
+                       "parallelism": f"rows/{world}", "l2": "inputs larger than L2 (index stream >> 126 MB)"
+                       if nnz_local * 4 > (256 << 20) else "inputs fit L2; operator_time flushes L2 between iterations"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "timing": {"device_ms_total": total_ms, "wall_ms_total": wall_ms, "generate_s": t_gen},
+            "solver": {kk: stats[kk] for kk in ("n_ops", "n_restarts", "basis_cols", "max_residual", "ms_transpose",
+                                                "ms_prepare", "ms_eigsh", "ms_spmm", "ms_ortho", "ms_comm", "ms_host")},
+            "evals_head": [float(x) for x in evals[:4]],
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        td.barrier()
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--config", choices=sorted(CONFIGS), default=os.environ.get("SNAPB200_BENCH_CONFIG", "c3"))
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--tol", type=float, default=0.0)
+    ap.add_argument("--op-iters", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
