@@ -56,7 +56,9 @@ typedef struct snapb200_stats {
     int64_t block;         /* block width b                                    */
     int64_t nnz_local;     /* stored entries on this shard                     */
     int64_t kernel_launches; /* CUDA kernels launched by the library so far    */
-    int64_t reserved[5];
+    double ms_format;      /* building the shared-memory tiled (sliced-ELL) copies */
+    int64_t spmm_tiled;    /* 1 if the last operator ran the tiled kernels     */
+    int64_t reserved[3];
 } snapb200_stats;
 
 /* Library / error plumbing. */
@@ -139,6 +141,11 @@ int  snapb200_eigsh(snapb200_ctx* ctx, int k, int64_t seed, double tol,
                     double* evals, double* evecs);
 
 int  snapb200_get_stats(snapb200_ctx* ctx, snapb200_stats* out);
+
+/* SpMM kernel selection: 0 = automatic (tiled for >= 2^25 stored entries and
+ * b = 8), 1 = CSR gather out of L2, 2 = shared-memory tiled sliced-ELL.  Takes
+ * effect at the next prepare. */
+int  snapb200_set_spmm_mode(snapb200_ctx* ctx, int mode);
 
 /* The context's CUDA stream (a cudaStream_t), so a caller can record its own
  * events around library calls (bench.py wraps it in torch.cuda.ExternalStream). */

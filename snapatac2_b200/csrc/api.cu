@@ -31,6 +31,7 @@ int guarded(F&& f) {
 void bind(snapb200_ctx* c) {
     SB_CHECK(c != nullptr, "null context");
     SB_CUDA(cudaSetDevice(c->device));
+    pool_set_stream(c->stream);
 }
 
 __global__ void narrow_i64_kernel(const int64_t* __restrict__ in, int32_t* __restrict__ out, int64_t n,
@@ -390,6 +391,15 @@ int snapb200_get_stats(snapb200_ctx* c, snapb200_stats* out) {
     return guarded([&] {
         SB_CHECK(c && out, "get_stats: null argument");
         *out = c->stats;
+    });
+}
+
+int snapb200_set_spmm_mode(snapb200_ctx* c, int mode) {
+    return guarded([&] {
+        SB_CHECK(c != nullptr, "null context");
+        SB_CHECK(mode >= 0 && mode <= 2, "set_spmm_mode: mode must be 0, 1 or 2");
+        c->spmm_mode = mode;
+        c->prepared = false;
     });
 }
 

@@ -8,7 +8,13 @@
 
 namespace snapb {
 
-// Owning device buffer (freed with the context or on reassignment).
+// Caching device allocator (pool.cu): stream-ordered reuse of freed blocks.
+void* pool_alloc(size_t bytes);
+void pool_free(void* p);
+void pool_trim();
+void pool_set_stream(cudaStream_t s);
+
+// Owning device buffer (released to the pool with the context or on reassignment).
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
@@ -18,15 +24,13 @@ struct DevBuf {
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFree(p);
+        if (p) pool_free(p);
         p = nullptr;
         n = 0;
     }
     void alloc(int64_t count) {
         release();
-        if (count > 0) {
-            SB_CUDA(cudaMalloc(reinterpret_cast<void**>(&p), sizeof(T) * static_cast<size_t>(count)));
-        }
+        if (count > 0) p = static_cast<T*>(pool_alloc(sizeof(T) * static_cast<size_t>(count)));
         n = count;
     }
     void ensure(int64_t count) {
@@ -70,6 +74,41 @@ struct Csr {
     }
 };
 
+// Column-tiled sliced-ELL copy of a CSR matrix for the shared-memory SpMM
+// (sell_build.cu / spmm_tiled.cu).  Columns are cut into tiles of `tile_cols`
+// columns so that a tile of the dense operand (tile_cols x 8 floats) fits in
+// shared memory; rows into `n_windows` windows of at most kSellWindowRows rows.
+// The chunk list is TILE-MAJOR: tile 0 of every window, then tile 1, ...  Inside
+// one (tile, window) the row segments are sorted by length and cut into chunks
+// of 32 (one lane per row segment; every row appears in every tile, possibly
+// with an empty segment, so each (tile, row) partial result is written exactly
+// once).  A chunk stores its entries interleaved, four per lane at a time, so a
+// warp reads 512 contiguous bytes per step.  Entries are byte offsets of the
+// dense row inside the staged tile (local column * 32), -1 = padding.  Within
+// a lane the entries are ordered so that the eight lanes of a quarter warp hit
+// eight different 16-byte bank groups (see sell_build.cu).
+struct Sell {
+    int n_windows = 0, n_tiles = 0, tile_cols = 0;
+    int64_t chunks_per_tile = 0;              // the same for every tile
+    int64_t nrows = 0, ncols = 0;
+    int64_t n_chunks = 0, n_entries = 0;      // n_entries counts padded slots
+    DevBuf<int64_t> window_start;             // n_windows + 1 row boundaries
+    DevBuf<int64_t> window_chunk0;            // n_windows + 1 first chunk of a window inside a tile
+    DevBuf<int32_t> chunk_rows;               // n_chunks * 32 (global row id, -1 = none)
+    DevBuf<int32_t> chunk_len4;               // n_chunks   (steps of 4 entries)
+    DevBuf<int64_t> chunk_off;                // n_chunks + 1, in units of 128 entries
+    DevBuf<int32_t> data;                     // n_entries
+    DevBuf<float> vals;                       // n_entries or empty
+    bool built = false;
+    void clear() {
+        window_start.release(); window_chunk0.release(); chunk_rows.release(); chunk_len4.release();
+        chunk_off.release(); data.release(); vals.release();
+        built = false; n_chunks = n_entries = 0;
+    }
+};
+constexpr int kSellTileCols = 6144;        // 6144 x 32 B = 192 KB of shared memory
+constexpr int kSellWindowRows = 8192;      // rows sorted together (one CTA-wide sort)
+
 struct Comm;  // NCCL wrapper (comm.cu)
 
 }  // namespace snapb
@@ -90,6 +129,9 @@ struct snapb200_ctx {
 
     snapb::Csr X;    // cells x features (this rank's rows)
     snapb::Csr Xt;   // features x local cells (built by prepare)
+    snapb::Sell S2;  // tiled copy of X  (pass 2: gathers W rows by feature)
+    snapb::Sell S1;  // tiled copy of Xt (pass 1: gathers r.*V rows by cell)
+    int spmm_mode = 0;   // 0 = auto, 1 = CSR gather from L2, 2 = shared-memory tiled SELL
 
     // user feature weights (host copy, optional)
     std::vector<double> user_weights;
@@ -109,6 +151,7 @@ struct snapb200_ctx {
     snapb::DevBuf<float> Vr;        // n x b  r .* V
     snapb::DevBuf<float> W;         // m x b  X^T (r V), then w^2-scaled
     snapb::DevBuf<float> opV, opY;  // operator_apply / operator_time staging
+    snapb::DevBuf<float> partial;   // n_tiles x nrows x 8 per-tile partial sums of the tiled SpMM
 
     // scratch
     snapb::DevBuf<unsigned char> scratch;
@@ -152,6 +195,14 @@ void view_frobenius(snapb200_ctx* c, const int64_t* rows, int64_t n_rows, double
 // all-reduce, after pass 2.
 void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, int b,
                         cudaEvent_t* evs = nullptr);
+
+// ---- sell_build.cu / spmm_tiled.cu
+void sell_build(snapb200_ctx* c, const Csr& M, Sell& S);
+// out[row, 0:8] = scale[row] * (M in)[row, 0:8] - (sub ? subscale[row] * sub[row*lds + 0:8] : 0)
+// through the tiled copy; `in` and `out` are packed (leading dimension 8).
+void sell_spmm8(snapb200_ctx* c, const Sell& S, const float* in, float* out, const float* scale,
+                const float* subscale, const float* sub, int64_t lds);
+bool use_tiled(const snapb200_ctx* c, int b);
 
 // ---- lanczos.cu
 void eigsh(snapb200_ctx* c, int k, int64_t seed, double tol, int block, int max_basis, int max_ops,

@@ -314,6 +314,11 @@ inline int row_chunks(snapb200_ctx* c, int64_t n) {
 // host wrappers
 // ==========================================================================
 template <int B>
+void DenseOps<B>::reserve(snapb200_ctx* c, int64_t n, int ld) {
+    partial.ensure(static_cast<int64_t>(row_chunks(c, n)) * ld * B);
+}
+
+template <int B>
 void DenseOps<B>::gram(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Z, int64_t ldz, int64_t n,
                        double* H) {
     SB_CHECK(ncq % 4 == 0 && ldq % 4 == 0, "gram: basis width must be a multiple of 4");
@@ -458,7 +463,9 @@ double dense_selftest(snapb200_ctx* c, int64_t n, int ncq, int p) {
             scale = std::max(scale, fabs(want));
             err = std::max(err, fabs(want - static_cast<double>(hz2[i])));
         }
-        worst = std::max(worst, err / scale / 64.0);   // fp32 store rounding allowed
+        // the projected block is stored in fp32 (rounding ~6e-8 relative): scale its error by 1e-5
+        // so that one fp64-grade threshold (1e-11) serves all three checks
+        worst = std::max(worst, err / scale * 1e-5);
     }
     return worst;
 }

@@ -10,6 +10,8 @@ namespace snapb {
 template <int B>
 struct DenseOps {
     DevBuf<double> partial;   // per-CTA partial sums (fixed-order reduction)
+    // size `partial` once for a basis of up to ld columns (no reallocation inside the solver loop)
+    void reserve(snapb200_ctx* c, int64_t n, int ld);
 
     // H[ncq x B] = Q[:, 0:ncq]^T Z
     void gram(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Z, int64_t ldz, int64_t n, double* H);

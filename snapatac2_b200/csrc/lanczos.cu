@@ -183,6 +183,7 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
     if (!(tol > 0.0)) tol = 1e-5;
 
     DenseOps<B> ops;
+    ops.reserve(c, n, ld);
     DevBuf<float> Q, Z, Qtmp;
     DevBuf<double> dH, dG0, dG, dChol, dS, dEvec;
     Q.alloc(std::max<int64_t>(1, n * ld));

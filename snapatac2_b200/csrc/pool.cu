@@ -1,0 +1,113 @@
+// Caching device allocator behind DevBuf.
+//
+// cudaFree synchronises the whole device and cudaMalloc of multi-GB blocks is
+// slow; a spectral() call allocates and releases dozens of temporaries (and
+// bench.py repeats the call), so freed blocks are parked here and handed out
+// again.  Reuse is stream ordered: all work of a context runs on one stream,
+// so a block freed while kernels still read it can be given to the next user
+// on the same stream safely; if a block migrates to a different stream, the
+// previous owner's stream is drained first.  On out-of-memory every parked
+// block is returned to the driver and the allocation retried.
+#include "common.cuh"
+
+#include <map>
+#include <mutex>
+#include <unordered_map>
+
+namespace snapb {
+
+namespace {
+
+struct Parked {
+    void* p;
+    cudaStream_t stream;
+};
+struct Pool {
+    std::mutex mu;
+    std::unordered_map<void*, size_t> live;                        // ptr -> bytes
+    std::map<int, std::multimap<size_t, Parked>> parked;           // device -> size -> block
+};
+Pool& pool() {
+    static Pool* p = new Pool();   // intentionally leaked: outlives static destruction order issues
+    return *p;
+}
+thread_local cudaStream_t t_stream = nullptr;
+
+size_t round_size(size_t b) {
+    const size_t g = b < (1u << 20) ? 512 : (2u << 20);
+    return (b + g - 1) / g * g;
+}
+
+void trim_locked(Pool& P, int dev) {
+    auto it = P.parked.find(dev);
+    if (it == P.parked.end()) return;
+    for (auto& kv : it->second) cudaFree(kv.second.p);
+    it->second.clear();
+}
+
+}  // namespace
+
+void pool_set_stream(cudaStream_t s) { t_stream = s; }
+
+void* pool_alloc(size_t bytes) {
+    if (bytes == 0) return nullptr;
+    bytes = round_size(bytes);
+    int dev = 0;
+    SB_CUDA(cudaGetDevice(&dev));
+    Pool& P = pool();
+    std::lock_guard<std::mutex> lock(P.mu);
+    auto& bins = P.parked[dev];
+    auto it = bins.lower_bound(bytes);
+    if (it != bins.end() && it->first <= bytes + bytes / 4 + (1u << 20)) {
+        Parked blk = it->second;
+        const size_t sz = it->first;
+        bins.erase(it);
+        if (blk.stream != t_stream && blk.stream != nullptr) cudaStreamSynchronize(blk.stream);
+        P.live[blk.p] = sz;
+        return blk.p;
+    }
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        trim_locked(P, dev);
+        e = cudaMalloc(&p, bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        char buf[256];
+        snprintf(buf, sizeof(buf), "device allocation of %.2f GB failed: %s", bytes / 1e9, cudaGetErrorString(e));
+        throw Error(buf);
+    }
+    P.live[p] = bytes;
+    return p;
+}
+
+void pool_free(void* p) {
+    if (!p) return;
+    Pool& P = pool();
+    std::lock_guard<std::mutex> lock(P.mu);
+    auto it = P.live.find(p);
+    if (it == P.live.end()) {
+        cudaFree(p);
+        return;
+    }
+    const size_t sz = it->second;
+    P.live.erase(it);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    P.parked[dev].emplace(sz, Parked{p, t_stream});
+}
+
+// Return every parked block of the current device to the driver.
+void pool_trim() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Pool& P = pool();
+    std::lock_guard<std::mutex> lock(P.mu);
+    cudaDeviceSynchronize();
+    trim_locked(P, dev);
+}
+
+}  // namespace snapb

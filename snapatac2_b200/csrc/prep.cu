@@ -474,6 +474,17 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     count_launch(c, 2);
     SB_CUDA(cudaStreamSynchronize(st));
     c->stats.ms_prepare = elapsed_ms(c);
+
+    // ---- shared-memory tiled copies for the SpMM (large problems, b = 8)
+    c->S1.clear();
+    c->S2.clear();
+    c->stats.ms_format = 0.0;
+    if (use_tiled(c, 8)) {
+        SB_CUDA(cudaEventRecord(c->ev0, st));
+        sell_build(c, c->X, c->S2);
+        sell_build(c, c->Xt, c->S1);
+        c->stats.ms_format = elapsed_ms(c);
+    }
     c->prepared = true;
 }
 

@@ -1,0 +1,271 @@
+// Shared-memory tiled SpMM over the sliced-ELL copy built by sell_build.cu:
+//     partial[t][row, 0:8] = sum over the row's entries in column tile t of in[col, 0:8]
+//     out[row, 0:8]        = scale[row] * sum_t partial[t][row, 0:8]  (- subscale[row] * sub[row, 0:8])
+//
+// sell_spmm8_kernel: one persistent CTA per SM.  The tile-major chunk list is
+// cut into gridDim.x ranges of equal stored entries; a CTA walks its range,
+// which touches one or two column tiles.  For each of them it stages the dense
+// operand tile (<= 6144 rows x 32 B = 192 KB) in shared memory with one TMA
+// bulk copy (cp.async.bulk + mbarrier), then its 24 warps pull chunks from a
+// shared counter: one lane per row segment, four entries per 128-bit index
+// load (512 contiguous bytes per warp-load, double buffered in registers),
+// two LDS.128 per entry.  The build orders entries so the LDS.128 of a quarter
+// warp are (mostly) bank-conflict free.  Every (tile, row) partial is written
+// exactly once with a plain store: no atomics, bitwise reproducible.
+//
+// Algorithmic bytes per stored entry: 4 (the int32 entry) -- the HBM roofline
+// of the pass; on chip it needs 32 B of shared-memory bandwidth per entry.
+#include "ctx.cuh"
+
+#include <algorithm>
+
+namespace snapb {
+
+namespace {
+
+constexpr int kTiledThreads = 768;
+constexpr int kTiledWarps = kTiledThreads / 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(addr), "r"(phase) : "memory");
+    }
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 ld_stream_float4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_float4(float4* p, const float4& v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+template <bool HAS_VAL>
+__device__ __forceinline__ void gather_one(int e, float v, uint32_t tile1, uint32_t tile2, float4& a, float4& b) {
+    if (e >= 0) {
+        const float4 x1 = lds128(tile1 + e);
+        const float4 x2 = lds128(tile2 + e);
+        if (HAS_VAL) {
+            a.x = fmaf(v, x1.x, a.x); a.y = fmaf(v, x1.y, a.y); a.z = fmaf(v, x1.z, a.z); a.w = fmaf(v, x1.w, a.w);
+            b.x = fmaf(v, x2.x, b.x); b.y = fmaf(v, x2.y, b.y); b.z = fmaf(v, x2.z, b.z); b.w = fmaf(v, x2.w, b.w);
+        } else {
+            a.x += x1.x; a.y += x1.y; a.z += x1.z; a.w += x1.w;
+            b.x += x2.x; b.y += x2.y; b.z += x2.z; b.w += x2.w;
+        }
+    }
+}
+template <bool HAS_VAL>
+__device__ __forceinline__ void gather_four(const int4& e, const float4& v, uint32_t tile1, uint32_t tile2, float4& a,
+                                            float4& b) {
+    gather_one<HAS_VAL>(e.x, v.x, tile1, tile2, a, b);
+    gather_one<HAS_VAL>(e.y, v.y, tile1, tile2, a, b);
+    gather_one<HAS_VAL>(e.z, v.z, tile1, tile2, a, b);
+    gather_one<HAS_VAL>(e.w, v.w, tile1, tile2, a, b);
+}
+
+// first chunk index c in [0, n] with chunk_off[c] >= target
+__device__ int64_t chunk_lower_bound(const int64_t* __restrict__ chunk_off, int64_t n, int64_t target) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (chunk_off[mid] < target) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <bool HAS_VAL, int U>
+__global__ void __launch_bounds__(kTiledThreads, 1)
+sell_spmm8_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restrict__ chunk_len4,
+                  const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ data, const float* __restrict__ vals,
+                  const float* __restrict__ in, float* __restrict__ partial, int64_t n_chunks, int64_t chunks_per_tile,
+                  int tile_cols, int64_t ncols, int64_t nrows) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* tile = reinterpret_cast<float*>(smem);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(tile_cols) * 32);
+    unsigned long long* next_chunk = reinterpret_cast<unsigned long long*>(bar + 1);
+    int64_t* range = reinterpret_cast<int64_t*>(bar + 2);   // [2]
+    const int lane = threadIdx.x & 31;
+    // lane reads half (lane & 1) of the dense row first, the other half second
+    const uint32_t tile1 = smem_u32(tile) + (lane & 1) * 16;
+    const uint32_t tile2 = smem_u32(tile) + 16 - (lane & 1) * 16;
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        // this CTA's share of the tile-major chunk list: equal stored entries
+        const int64_t groups = chunk_off[n_chunks];
+        const int64_t g_lo = static_cast<int64_t>((static_cast<__int128>(groups) * blockIdx.x) / gridDim.x);
+        const int64_t g_hi = static_cast<int64_t>((static_cast<__int128>(groups) * (blockIdx.x + 1)) / gridDim.x);
+        range[0] = (blockIdx.x == 0) ? 0 : chunk_lower_bound(chunk_off, n_chunks, g_lo);
+        range[1] = (blockIdx.x == gridDim.x - 1) ? n_chunks : chunk_lower_bound(chunk_off, n_chunks, g_hi);
+    }
+    __syncthreads();
+    const int64_t c_begin = range[0], c_end = range[1];
+    if (c_begin >= c_end) return;
+    uint32_t phase = 0;
+
+    for (int64_t t = c_begin / chunks_per_tile; t * chunks_per_tile < c_end; ++t) {
+        const int64_t lo = max(c_begin, t * chunks_per_tile);
+        const int64_t hi = min(c_end, (t + 1) * chunks_per_tile);
+        __syncthreads();   // every warp is done with the previous tile and counter
+        if (threadIdx.x == 0) {
+            *next_chunk = static_cast<unsigned long long>(lo);
+            const int64_t c0 = t * tile_cols;
+            const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(tile_cols), ncols - c0)) * 32u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(tile, in + c0 * 8, bytes, bar);
+        }
+        __syncthreads();   // counter visible
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        float* part_t = partial + t * nrows * 8;
+
+        while (true) {
+            unsigned long long cu = 0;
+            if (lane == 0) cu = atomicAdd(next_chunk, 1ull);
+            const int64_t c = static_cast<int64_t>(__shfl_sync(0xffffffffu, cu, 0));
+            if (c >= hi) break;
+            const int row = chunk_rows[c * 32 + lane];
+            const int len4 = chunk_len4[c];
+            const int4* d = reinterpret_cast<const int4*>(data) + chunk_off[c] * 32 + lane;
+            const float4* dv = HAS_VAL ? reinterpret_cast<const float4*>(vals) + chunk_off[c] * 32 + lane : nullptr;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+            const float4 ones = make_float4(1.f, 1.f, 1.f, 1.f);
+            int4 cur[U], nxt[U];
+            float4 vcur[U], vnxt[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                cur[u] = make_int4(-1, -1, -1, -1);
+                vcur[u] = ones;
+                if (u < len4) {
+                    cur[u] = ld_stream_int4(d + u * 32);
+                    if (HAS_VAL) vcur[u] = ld_stream_float4(dv + u * 32);
+                }
+            }
+            for (int g = 0; g < len4; g += U) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {   // prefetch the next U groups while this batch is consumed
+                    nxt[u] = make_int4(-1, -1, -1, -1);
+                    vnxt[u] = ones;
+                    if (g + U + u < len4) {
+                        nxt[u] = ld_stream_int4(d + (g + U + u) * 32);
+                        if (HAS_VAL) vnxt[u] = ld_stream_float4(dv + (g + U + u) * 32);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) gather_four<HAS_VAL>(cur[u], vcur[u], tile1, tile2, a, b);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    cur[u] = nxt[u];
+                    vcur[u] = vnxt[u];
+                }
+            }
+            if (row >= 0) {
+                float4* o = reinterpret_cast<float4*>(part_t + static_cast<int64_t>(row) * 8);
+                st_stream_float4(o, (lane & 1) ? b : a);
+                st_stream_float4(o + 1, (lane & 1) ? a : b);
+            }
+        }
+    }
+}
+
+// out[row, q] (float4 q of 2) = scale[row] * sum_t partial[t][row, q] - subscale[row] * sub[row, q]
+template <bool HAS_SUB>
+__global__ void __launch_bounds__(256)
+reduce_tiles_kernel(const float* __restrict__ partial, int n_tiles, int64_t nrows, const float* __restrict__ scale,
+                    const float* __restrict__ subscale, const float* __restrict__ sub, int64_t lds,
+                    float* __restrict__ out) {
+    const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // float4 index
+    if (g >= nrows * 2) return;
+    const float4* p = reinterpret_cast<const float4*>(partial) + g;
+    const int64_t stride = nrows * 2;
+    float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
+    int t = 0;
+    for (; t + 1 < n_tiles; t += 2) {      // two fixed-order chains for memory-level parallelism
+        const float4 x0 = ld_stream_float4(p + static_cast<int64_t>(t) * stride);
+        const float4 x1 = ld_stream_float4(p + static_cast<int64_t>(t + 1) * stride);
+        s0.x += x0.x; s0.y += x0.y; s0.z += x0.z; s0.w += x0.w;
+        s1.x += x1.x; s1.y += x1.y; s1.z += x1.z; s1.w += x1.w;
+    }
+    if (t < n_tiles) {
+        const float4 x0 = ld_stream_float4(p + static_cast<int64_t>(t) * stride);
+        s0.x += x0.x; s0.y += x0.y; s0.z += x0.z; s0.w += x0.w;
+    }
+    const int64_t row = g >> 1;
+    const float sc = scale[row];
+    float4 y = make_float4(sc * (s0.x + s1.x), sc * (s0.y + s1.y), sc * (s0.z + s1.z), sc * (s0.w + s1.w));
+    if (HAS_SUB) {
+        const float ss = subscale[row];
+        const float* sp = sub + row * lds + (g & 1) * 4;
+        y.x -= ss * sp[0]; y.y -= ss * sp[1]; y.z -= ss * sp[2]; y.w -= ss * sp[3];
+    }
+    reinterpret_cast<float4*>(out)[g] = y;
+}
+
+}  // namespace
+
+bool use_tiled(const snapb200_ctx* c, int b) {
+    if (b != 8) return false;
+    if (c->spmm_mode == 1) return false;
+    if (c->spmm_mode == 2) return true;
+    return c->X.nnz >= (1ll << 25);   // small problems: the CSR kernel avoids staging tiles at all
+}
+
+void sell_spmm8(snapb200_ctx* c, const Sell& S, const float* in, float* out, const float* scale,
+                const float* subscale, const float* sub, int64_t lds) {
+    SB_CHECK(S.built, "tiled SpMM: format not built");
+    cudaStream_t st = c->stream;
+    if (S.nrows == 0) return;
+    c->partial.ensure(static_cast<int64_t>(S.n_tiles) * S.nrows * 8);
+    const size_t smem = static_cast<size_t>(S.tile_cols) * 32 + 64;
+    const int grid = c->num_sms;
+    if (S.vals.p) {
+        auto k = sell_spmm8_kernel<true, 2>;
+        SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        k<<<grid, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p, S.data.p, S.vals.p, in,
+                                            c->partial.p, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols, S.nrows);
+    } else {
+        auto k = sell_spmm8_kernel<false, 4>;
+        SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        k<<<grid, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p, S.data.p, nullptr, in,
+                                            c->partial.p, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols, S.nrows);
+    }
+    SB_LAUNCH_CHECK();
+    const unsigned rb = static_cast<unsigned>(ceil_div(S.nrows * 2, 256));
+    if (sub)
+        reduce_tiles_kernel<true><<<rb, 256, 0, st>>>(c->partial.p, S.n_tiles, S.nrows, scale, subscale, sub, lds, out);
+    else
+        reduce_tiles_kernel<false><<<rb, 256, 0, st>>>(c->partial.p, S.n_tiles, S.nrows, scale, nullptr, nullptr, 0, out);
+    SB_LAUNCH_CHECK();
+    count_launch(c, 2);
+}
+
+}  // namespace snapb

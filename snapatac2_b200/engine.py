@@ -172,6 +172,11 @@ class Engine:
         _lib.check(self._lib.snapb200_get_stats(self._ctx, C.byref(s)))
         return s.as_dict()
 
+    def set_spmm_mode(self, mode: str | int):
+        """'auto' | 'csr' (gather out of L2) | 'tiled' (shared-memory sliced-ELL)."""
+        code = {"auto": 0, "csr": 1, "tiled": 2}.get(mode, mode)
+        _lib.check(self._lib.snapb200_set_spmm_mode(self._ctx, int(code)))
+
     def stream_handle(self) -> int:
         """Raw ``cudaStream_t`` of the context (for torch.cuda.ExternalStream)."""
         h = C.c_void_p()

@@ -1,0 +1,71 @@
+"""GPU (-m gpu): the shared-memory tiled (sliced-ELL) SpMM path against the
+oracle operator and against the CSR-gather path, several column tiles in both
+passes, binarised and count-valued inputs."""
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import oracle
+from conftest import eigvec_agreement
+from snapatac2_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_operator(X):
+    mat = sp.csr_matrix(X, dtype=np.float64)
+    w = oracle.idf(mat)
+    xt, dinv, _, deg = oracle.operator_pieces(oracle.normalize(mat, w))
+    return xt, dinv, w, deg
+
+
+@pytest.mark.parametrize("valued", [False, True])
+def test_tiled_operator_matches_oracle_and_csr_path(engine, valued):
+    # 14000 cells -> 3 cell tiles in pass 1; 20000 bins -> 4 feature tiles in pass 2
+    spec = synth.make_spec(14000, 20000, 300, n_clusters=20, seed=17)
+    engine.generate(spec)
+    X = engine.export_csr().astype(np.float64)
+    if valued:
+        rng = np.random.default_rng(5)
+        X.data = rng.integers(1, 6, size=X.nnz).astype(np.float64)
+    xt, dinv, w, deg = _oracle_operator(X)
+    rng = np.random.default_rng(1)
+    V = rng.standard_normal((14000, 8)).astype(np.float32)
+    want = xt @ (xt.T @ V.astype(np.float64)) - dinv[:, None] * V
+    got = {}
+    for mode in ("csr", "tiled"):
+        engine.set_spmm_mode(mode)
+        engine.load_csr(X, binarized=not valued)
+        engine.set_feature_weights(None)
+        idf, degree = engine.prepare()
+        np.testing.assert_allclose(idf, w, rtol=1e-5)
+        np.testing.assert_allclose(degree, deg, rtol=1e-5)
+        Y = engine.operator_apply(V)
+        assert engine.stats()["spmm_tiled"] == (1 if mode == "tiled" else 0)
+        err = np.abs(Y - want).max() / np.abs(want).max()
+        assert err < 2e-5, (mode, err)
+        got[mode] = Y
+        # bitwise repeatable (no atomics anywhere on the path)
+        np.testing.assert_array_equal(engine.operator_apply(V), Y)
+    assert np.abs(got["csr"] - got["tiled"]).max() / np.abs(want).max() < 1e-5
+    engine.set_spmm_mode("auto")
+
+
+def test_tiled_eigsh_parity_config1(engine):
+    spec = synth.make_spec(5000, 100000, 3000, n_clusters=48, seed=0)
+    engine.set_spmm_mode("tiled")
+    try:
+        engine.generate(spec)
+        X = engine.export_csr()
+        ev_o, evec_o, w_o, deg_o = oracle.spectral_embedding(X, None, 30, 0, return_parts=True)
+        engine.set_feature_weights(None)
+        idf, deg = engine.prepare()
+        np.testing.assert_allclose(idf, w_o, rtol=1e-5)
+        np.testing.assert_allclose(deg, deg_o, rtol=1e-5)
+        evals, evecs = engine.eigsh(30, seed=0)
+        assert engine.stats()["spmm_tiled"] == 1
+        np.testing.assert_allclose(evals, ev_o, rtol=1e-4)
+        assert eigvec_agreement(ev_o, evec_o, evecs).min() >= 0.999
+    finally:
+        engine.set_spmm_mode("auto")
