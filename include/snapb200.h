@@ -58,7 +58,8 @@ typedef struct snapb200_stats {
     int64_t kernel_launches; /* CUDA kernels launched by the library so far    */
     double ms_format;      /* building the shared-memory tiled (sliced-ELL) copies */
     int64_t spmm_tiled;    /* 1 if the last operator ran the tiled kernels     */
-    int64_t reserved[3];
+    double ms_prepare_wall; /* host wall clock of the whole prepare call        */
+    int64_t reserved[2];
 } snapb200_stats;
 
 /* Library / error plumbing. */
@@ -146,6 +147,10 @@ int  snapb200_get_stats(snapb200_ctx* ctx, snapb200_stats* out);
  * b = 8), 1 = CSR gather out of L2, 2 = shared-memory tiled sliced-ELL.  Takes
  * effect at the next prepare. */
 int  snapb200_set_spmm_mode(snapb200_ctx* ctx, int mode);
+
+/* Default Lanczos block width b (4, 8 or 16; initially 8).  prepare() builds
+ * the tiled copies for it and eigsh(block = 0) uses it. */
+int  snapb200_set_block(snapb200_ctx* ctx, int block);
 
 /* The context's CUDA stream (a cudaStream_t), so a caller can record its own
  * events around library calls (bench.py wraps it in torch.cuda.ExternalStream). */

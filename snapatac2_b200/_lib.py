@@ -21,7 +21,7 @@ SYMBOLS = [
     "snapb200_select_features", "snapb200_generate", "snapb200_shape", "snapb200_export_csr",
     "snapb200_set_feature_weights", "snapb200_prepare", "snapb200_view_frobenius",
     "snapb200_operator_apply", "snapb200_operator_time", "snapb200_eigsh", "snapb200_get_stats",
-    "snapb200_get_stream", "snapb200_set_spmm_mode",
+    "snapb200_get_stream", "snapb200_set_spmm_mode", "snapb200_set_block",
     "snapb200_dense_selftest", "snapb200_sym_eig",
 ]
 
@@ -34,7 +34,8 @@ class Stats(C.Structure):
         ("n_ops", C.c_int64), ("n_restarts", C.c_int64), ("basis_cols", C.c_int64),
         ("block", C.c_int64), ("nnz_local", C.c_int64), ("kernel_launches", C.c_int64),
         ("ms_format", C.c_double), ("spmm_tiled", C.c_int64),
-        ("reserved", C.c_int64 * 3),
+        ("ms_prepare_wall", C.c_double),
+        ("reserved", C.c_int64 * 2),
     ]
 
     def as_dict(self):
@@ -77,6 +78,7 @@ def load() -> C.CDLL:
         "snapb200_get_stats": [vp, C.POINTER(Stats)],
         "snapb200_get_stream": [vp, C.POINTER(vp)],
         "snapb200_set_spmm_mode": [vp, i32],
+        "snapb200_set_block": [vp, i32],
         "snapb200_dense_selftest": [vp, i64, i32, i32, C.POINTER(dbl)],
         "snapb200_sym_eig": [i32, vp, vp],
     }

@@ -384,7 +384,10 @@ int snapb200_operator_time(snapb200_ctx* c, int b, int iters, int flush, double*
 
 int snapb200_eigsh(snapb200_ctx* c, int k, int64_t seed, double tol, int block, int max_basis, int max_ops,
                    double* evals, double* evecs) {
-    return guarded([&] { bind(c); eigsh(c, k, seed, tol, block, max_basis, max_ops, evals, evecs); });
+    return guarded([&] {
+        bind(c);
+        eigsh(c, k, seed, tol, block > 0 ? block : c->block, max_basis, max_ops, evals, evecs);
+    });
 }
 
 int snapb200_get_stats(snapb200_ctx* c, snapb200_stats* out) {
@@ -400,6 +403,14 @@ int snapb200_set_spmm_mode(snapb200_ctx* c, int mode) {
         SB_CHECK(mode >= 0 && mode <= 2, "set_spmm_mode: mode must be 0, 1 or 2");
         c->spmm_mode = mode;
         c->prepared = false;
+    });
+}
+
+int snapb200_set_block(snapb200_ctx* c, int block) {
+    return guarded([&] {
+        SB_CHECK(c != nullptr, "null context");
+        SB_CHECK(block == 4 || block == 8 || block == 16, "set_block: block width must be 4, 8 or 16");
+        c->block = block;
     });
 }
 

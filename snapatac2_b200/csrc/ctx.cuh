@@ -88,6 +88,7 @@ struct Csr {
 // a lane the entries are ordered so that the eight lanes of a quarter warp hit
 // eight different 16-byte bank groups (see sell_build.cu).
 struct Sell {
+    int b = 0;                                // dense block width the tiles are sized for (4 or 8)
     int n_windows = 0, n_tiles = 0, tile_cols = 0;
     int64_t chunks_per_tile = 0;              // the same for every tile
     int64_t nrows = 0, ncols = 0;
@@ -106,7 +107,7 @@ struct Sell {
         built = false; n_chunks = n_entries = 0;
     }
 };
-constexpr int kSellTileCols = 6144;        // 6144 x 32 B = 192 KB of shared memory
+constexpr int kSellTileBytes = 196608;     // 192 KB of shared memory: 6144 rows (b=8) / 12288 rows (b=4)
 constexpr int kSellWindowRows = 8192;      // rows sorted together (one CTA-wide sort)
 
 struct Comm;  // NCCL wrapper (comm.cu)
@@ -132,6 +133,7 @@ struct snapb200_ctx {
     snapb::Sell S2;  // tiled copy of X  (pass 2: gathers W rows by feature)
     snapb::Sell S1;  // tiled copy of Xt (pass 1: gathers r.*V rows by cell)
     int spmm_mode = 0;   // 0 = auto, 1 = CSR gather from L2, 2 = shared-memory tiled SELL
+    int block = 8;       // default Lanczos block width (prepare builds the tiled copies for it)
 
     // user feature weights (host copy, optional)
     std::vector<double> user_weights;
@@ -197,12 +199,14 @@ void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, 
                         cudaEvent_t* evs = nullptr);
 
 // ---- sell_build.cu / spmm_tiled.cu
-void sell_build(snapb200_ctx* c, const Csr& M, Sell& S);
-// out[row, 0:8] = scale[row] * (M in)[row, 0:8] - (sub ? subscale[row] * sub[row*lds + 0:8] : 0)
-// through the tiled copy; `in` and `out` are packed (leading dimension 8).
-void sell_spmm8(snapb200_ctx* c, const Sell& S, const float* in, float* out, const float* scale,
-                const float* subscale, const float* sub, int64_t lds);
+void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b);
+// out[row, 0:b] = scale[row] * (M in)[row, 0:b] - (sub ? subscale[row] * sub[row*lds + 0:b] : 0)
+// through the tiled copy (b = S.b); `in` and `out` are packed (leading dimension b).
+void sell_spmm(snapb200_ctx* c, const Sell& S, const float* in, float* out, const float* scale,
+               const float* subscale, const float* sub, int64_t lds);
 bool use_tiled(const snapb200_ctx* c, int b);
+// (re)build S1/S2 for block width b if they are missing or sized for another width
+void ensure_tiled(snapb200_ctx* c, int b);
 
 // ---- lanczos.cu
 void eigsh(snapb200_ctx* c, int k, int64_t seed, double tol, int block, int max_basis, int max_ops,

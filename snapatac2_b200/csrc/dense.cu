@@ -204,7 +204,7 @@ __global__ void apply_rinv_kernel(const float* __restrict__ Z, int64_t ldz, cons
 // DMMA roles: m = 8 rows, n = 8 output columns, k = 4 basis columns.
 // k permutation inside a 16-column group so that one float4 load feeds four
 // k-steps: step s, fragment k index ki  <->  column 16*g + 4*ki + s.
-// ncq must be a multiple of 8 (so it is a multiple of 4 for the float4 loads).
+// ncq must be a multiple of 4 (float4 loads of the basis rows).
 // --------------------------------------------------------------------------
 template <int NT, int MODE>
 __global__ void __launch_bounds__(256)
@@ -368,7 +368,7 @@ void DenseOps<B>::project_out(snapb200_ctx* c, const float* Q, int64_t ldq, int 
 void tall_gemm_f32(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const double* S, int lds, int p, int64_t n,
                    float* out, int64_t ldo) {
     if (n == 0) return;
-    SB_CHECK(ncq % 8 == 0, "tall_gemm: basis width must be a multiple of 8");
+    SB_CHECK(ncq % 4 == 0, "tall_gemm: basis width must be a multiple of 4");
     dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 64), c->num_sms * 8))),
               static_cast<unsigned>(ceil_div(p, 32)));
     tall_gemm_kernel<4, 1><<<grid, 256, 0, c->stream>>>(Q, ldq, ncq, S, lds, p, n, out, ldo);
@@ -379,7 +379,7 @@ void tall_gemm_f32(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const 
 void tall_gemm_f64(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const double* S, int lds, int p, int64_t n,
                    double* out, int64_t ldo) {
     if (n == 0) return;
-    SB_CHECK(ncq % 8 == 0, "tall_gemm: basis width must be a multiple of 8");
+    SB_CHECK(ncq % 4 == 0, "tall_gemm: basis width must be a multiple of 4");
     dim3 grid(static_cast<unsigned>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 64), c->num_sms * 8))),
               static_cast<unsigned>(ceil_div(p, 32)));
     tall_gemm_kernel<4, 2><<<grid, 256, 0, c->stream>>>(Q, ldq, ncq, S, lds, p, n, out, ldo);

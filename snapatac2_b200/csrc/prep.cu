@@ -8,6 +8,7 @@
 #include "ctx.cuh"
 
 #include <math.h>
+#include <chrono>
 #include <vector>
 
 namespace snapb {
@@ -363,6 +364,7 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     const int64_t m = c->m, n = c->n_local;
     SB_CHECK(m >= 1, "prepare: matrix has no columns");
     cudaStream_t st = c->stream;
+    const auto wall0 = std::chrono::steady_clock::now();
 
     // ---- feature-major copy + local document frequencies
     SB_CUDA(cudaEventRecord(c->ev0, st));
@@ -479,12 +481,9 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     c->S1.clear();
     c->S2.clear();
     c->stats.ms_format = 0.0;
-    if (use_tiled(c, 8)) {
-        SB_CUDA(cudaEventRecord(c->ev0, st));
-        sell_build(c, c->X, c->S2);
-        sell_build(c, c->Xt, c->S1);
-        c->stats.ms_format = elapsed_ms(c);
-    }
+    if (use_tiled(c, c->block)) ensure_tiled(c, c->block);
+    c->stats.ms_prepare_wall =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
     c->prepared = true;
 }
 

@@ -107,26 +107,27 @@ gather_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ 
     }
 }
 
-// Shared-memory tiled path (b = 8): both passes run over the sliced-ELL copies.
-void apply_tiled8(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, cudaEvent_t* evs) {
-    SB_CHECK(ldy == 8, "tiled operator: Y must be packed (leading dimension 8)");
+// Shared-memory tiled path (b = 4 or 8): both passes run over the sliced-ELL copies.
+template <int B>
+void apply_tiled(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, cudaEvent_t* evs) {
+    SB_CHECK(ldy == B, "tiled operator: Y must be packed (leading dimension b)");
     const int64_t n = c->n_local, m = c->m;
     cudaStream_t st = c->stream;
-    c->Vr.ensure(std::max<int64_t>(1, n * 8));
-    c->W.ensure(m * 8);
+    c->Vr.ensure(std::max<int64_t>(1, n * B));
+    c->W.ensure(m * B);
     if (n > 0) {
-        scale_rows_kernel<8><<<static_cast<unsigned>(ceil_div(n * 8, 256)), 256, 0, st>>>(V, ldv, c->r.p, n, c->Vr.p);
+        scale_rows_kernel<B><<<static_cast<unsigned>(ceil_div(n * B, 256)), 256, 0, st>>>(V, ldv, c->r.p, n, c->Vr.p);
         SB_LAUNCH_CHECK();
         count_launch(c);
     }
     if (evs) SB_CUDA(cudaEventRecord(evs[0], st));
     // pass 1: W = w^2 .* P^T (r V)
-    sell_spmm8(c, c->S1, c->Vr.p, c->W.p, c->w2.p, nullptr, nullptr, 0);
+    sell_spmm(c, c->S1, c->Vr.p, c->W.p, c->w2.p, nullptr, nullptr, 0);
     if (evs) SB_CUDA(cudaEventRecord(evs[1], st));
-    allreduce_f32(c, c->W.p, m * 8);
+    allreduce_f32(c, c->W.p, m * B);
     if (evs) SB_CUDA(cudaEventRecord(evs[2], st));
     // pass 2: Y = r .* (P W) - dinv .* V
-    sell_spmm8(c, c->S2, c->W.p, Y, c->r.p, c->dinv.p, V, ldv);
+    sell_spmm(c, c->S2, c->W.p, Y, c->r.p, c->dinv.p, V, ldv);
     if (evs) SB_CUDA(cudaEventRecord(evs[3], st));
 }
 
@@ -177,9 +178,11 @@ void apply_impl(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t 
 void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, int b, cudaEvent_t* evs) {
     SB_CHECK(c->prepared, "operator: call prepare first");
     SB_CHECK(ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "operator: Y must be 16-byte aligned");
-    if (use_tiled(c, b) && c->S1.built && c->S2.built) {
+    if (use_tiled(c, b)) {
+        ensure_tiled(c, b);   // no-op when prepare() already built the copies for this width
         c->stats.spmm_tiled = 1;
-        apply_tiled8(c, V, ldv, Y, ldy, evs);
+        if (b == 8) apply_tiled<8>(c, V, ldv, Y, ldy, evs);
+        else apply_tiled<4>(c, V, ldv, Y, ldy, evs);
         return;
     }
     c->stats.spmm_tiled = 0;

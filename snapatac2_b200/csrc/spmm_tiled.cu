@@ -1,20 +1,23 @@
-// Shared-memory tiled SpMM over the sliced-ELL copy built by sell_build.cu:
-//     partial[t][row, 0:8] = sum over the row's entries in column tile t of in[col, 0:8]
-//     out[row, 0:8]        = scale[row] * sum_t partial[t][row, 0:8]  (- subscale[row] * sub[row, 0:8])
+// Shared-memory tiled SpMM over the sliced-ELL copy built by sell_build.cu
+// (b = 4 or 8 dense columns):
+//     partial[t][row, 0:b] = sum over the row's entries in column tile t of in[col, 0:b]
+//     out[row, 0:b]        = scale[row] * sum_t partial[t][row, 0:b]  (- subscale[row] * sub[row, 0:b])
 //
-// sell_spmm8_kernel: one persistent CTA per SM.  The tile-major chunk list is
+// sell_spmm_kernel: one persistent CTA per SM.  The tile-major chunk list is
 // cut into gridDim.x ranges of equal stored entries; a CTA walks its range,
 // which touches one or two column tiles.  For each of them it stages the dense
-// operand tile (<= 6144 rows x 32 B = 192 KB) in shared memory with one TMA
-// bulk copy (cp.async.bulk + mbarrier), then its 24 warps pull chunks from a
-// shared counter: one lane per row segment, four entries per 128-bit index
-// load (512 contiguous bytes per warp-load, double buffered in registers),
-// two LDS.128 per entry.  The build orders entries so the LDS.128 of a quarter
-// warp are (mostly) bank-conflict free.  Every (tile, row) partial is written
-// exactly once with a plain store: no atomics, bitwise reproducible.
+// operand tile (192 KB: 6144 rows of 32 B or 12288 rows of 16 B) in shared
+// memory with one TMA bulk copy (cp.async.bulk + mbarrier), then its 24 warps
+// pull chunks from a shared counter: one lane per row segment, four entries
+// per 128-bit index load (512 contiguous bytes per warp-load, double buffered
+// in registers), b/4 LDS.128 per entry.  The build orders entries so the
+// LDS.128 of a quarter warp are (mostly) bank-conflict free.  Every
+// (tile, row) partial is written exactly once with a plain store: no atomics,
+// bitwise reproducible.
 //
 // Algorithmic bytes per stored entry: 4 (the int32 entry) -- the HBM roofline
-// of the pass; on chip it needs 32 B of shared-memory bandwidth per entry.
+// of the pass; on chip it needs 4b bytes of shared-memory bandwidth per entry,
+// which is what bounds b = 8 (ncu: l1tex data-pipe 93% busy at C3).
 #include "ctx.cuh"
 
 #include <algorithm>
@@ -24,7 +27,6 @@ namespace snapb {
 namespace {
 
 constexpr int kTiledThreads = 768;
-constexpr int kTiledWarps = kTiledThreads / 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -67,28 +69,33 @@ __device__ __forceinline__ void st_stream_float4(float4* p, const float4& v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
+__device__ __forceinline__ void acc4(float4& a, const float4& x, float v, bool has_val) {
+    if (has_val) {
+        a.x = fmaf(v, x.x, a.x); a.y = fmaf(v, x.y, a.y); a.z = fmaf(v, x.z, a.z); a.w = fmaf(v, x.w, a.w);
+    } else {
+        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+    }
+}
 
-template <bool HAS_VAL>
+// one stored entry: B/4 LDS.128 from the staged tile
+template <int B, bool HAS_VAL>
 __device__ __forceinline__ void gather_one(int e, float v, uint32_t tile1, uint32_t tile2, float4& a, float4& b) {
     if (e >= 0) {
         const float4 x1 = lds128(tile1 + e);
-        const float4 x2 = lds128(tile2 + e);
-        if (HAS_VAL) {
-            a.x = fmaf(v, x1.x, a.x); a.y = fmaf(v, x1.y, a.y); a.z = fmaf(v, x1.z, a.z); a.w = fmaf(v, x1.w, a.w);
-            b.x = fmaf(v, x2.x, b.x); b.y = fmaf(v, x2.y, b.y); b.z = fmaf(v, x2.z, b.z); b.w = fmaf(v, x2.w, b.w);
-        } else {
-            a.x += x1.x; a.y += x1.y; a.z += x1.z; a.w += x1.w;
-            b.x += x2.x; b.y += x2.y; b.z += x2.z; b.w += x2.w;
+        acc4(a, x1, v, HAS_VAL);
+        if (B == 8) {
+            const float4 x2 = lds128(tile2 + e);
+            acc4(b, x2, v, HAS_VAL);
         }
     }
 }
-template <bool HAS_VAL>
+template <int B, bool HAS_VAL>
 __device__ __forceinline__ void gather_four(const int4& e, const float4& v, uint32_t tile1, uint32_t tile2, float4& a,
                                             float4& b) {
-    gather_one<HAS_VAL>(e.x, v.x, tile1, tile2, a, b);
-    gather_one<HAS_VAL>(e.y, v.y, tile1, tile2, a, b);
-    gather_one<HAS_VAL>(e.z, v.z, tile1, tile2, a, b);
-    gather_one<HAS_VAL>(e.w, v.w, tile1, tile2, a, b);
+    gather_one<B, HAS_VAL>(e.x, v.x, tile1, tile2, a, b);
+    gather_one<B, HAS_VAL>(e.y, v.y, tile1, tile2, a, b);
+    gather_one<B, HAS_VAL>(e.z, v.z, tile1, tile2, a, b);
+    gather_one<B, HAS_VAL>(e.w, v.w, tile1, tile2, a, b);
 }
 
 // first chunk index c in [0, n] with chunk_off[c] >= target
@@ -101,20 +108,21 @@ __device__ int64_t chunk_lower_bound(const int64_t* __restrict__ chunk_off, int6
     return lo;
 }
 
-template <bool HAS_VAL, int U>
+template <int B, bool HAS_VAL, int U>
 __global__ void __launch_bounds__(kTiledThreads, 1)
-sell_spmm8_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restrict__ chunk_len4,
-                  const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ data, const float* __restrict__ vals,
-                  const float* __restrict__ in, float* __restrict__ partial, int64_t n_chunks, int64_t chunks_per_tile,
-                  int tile_cols, int64_t ncols, int64_t nrows) {
+sell_spmm_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restrict__ chunk_len4,
+                 const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ data, const float* __restrict__ vals,
+                 const float* __restrict__ in, float* __restrict__ partial, int64_t n_chunks, int64_t chunks_per_tile,
+                 int tile_cols, int64_t ncols, int64_t nrows) {
+    constexpr int RB = 4 * B;   // bytes per dense row
     extern __shared__ __align__(128) unsigned char smem[];
     float* tile = reinterpret_cast<float*>(smem);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(tile_cols) * 32);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(tile_cols) * RB);
     unsigned long long* next_chunk = reinterpret_cast<unsigned long long*>(bar + 1);
     int64_t* range = reinterpret_cast<int64_t*>(bar + 2);   // [2]
     const int lane = threadIdx.x & 31;
-    // lane reads half (lane & 1) of the dense row first, the other half second
-    const uint32_t tile1 = smem_u32(tile) + (lane & 1) * 16;
+    // b = 8: lane reads half (lane & 1) of the dense row first, the other half second
+    const uint32_t tile1 = smem_u32(tile) + ((B == 8) ? (lane & 1) * 16 : 0);
     const uint32_t tile2 = smem_u32(tile) + 16 - (lane & 1) * 16;
 
     if (threadIdx.x == 0) {
@@ -138,15 +146,15 @@ sell_spmm8_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restr
         if (threadIdx.x == 0) {
             *next_chunk = static_cast<unsigned long long>(lo);
             const int64_t c0 = t * tile_cols;
-            const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(tile_cols), ncols - c0)) * 32u;
+            const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(tile_cols), ncols - c0)) * RB;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             mbar_expect_tx(bar, bytes);
-            tma_load_1d(tile, in + c0 * 8, bytes, bar);
+            tma_load_1d(tile, in + c0 * B, bytes, bar);
         }
         __syncthreads();   // counter visible
         mbar_wait(bar, phase);
         phase ^= 1;
-        float* part_t = partial + t * nrows * 8;
+        float* part_t = partial + t * nrows * B;
 
         while (true) {
             unsigned long long cu = 0;
@@ -181,7 +189,7 @@ sell_spmm8_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restr
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u) gather_four<HAS_VAL>(cur[u], vcur[u], tile1, tile2, a, b);
+                for (int u = 0; u < U; ++u) gather_four<B, HAS_VAL>(cur[u], vcur[u], tile1, tile2, a, b);
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     cur[u] = nxt[u];
@@ -189,24 +197,29 @@ sell_spmm8_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restr
                 }
             }
             if (row >= 0) {
-                float4* o = reinterpret_cast<float4*>(part_t + static_cast<int64_t>(row) * 8);
-                st_stream_float4(o, (lane & 1) ? b : a);
-                st_stream_float4(o + 1, (lane & 1) ? a : b);
+                float4* o = reinterpret_cast<float4*>(part_t + static_cast<int64_t>(row) * B);
+                if (B == 8) {
+                    st_stream_float4(o, (lane & 1) ? b : a);
+                    st_stream_float4(o + 1, (lane & 1) ? a : b);
+                } else {
+                    st_stream_float4(o, a);
+                }
             }
         }
     }
 }
 
-// out[row, q] (float4 q of 2) = scale[row] * sum_t partial[t][row, q] - subscale[row] * sub[row, q]
-template <bool HAS_SUB>
+// out float4 g (row = g / (B/4)) = scale[row] * sum_t partial[t] - subscale[row] * sub[row]
+template <int B, bool HAS_SUB>
 __global__ void __launch_bounds__(256)
 reduce_tiles_kernel(const float* __restrict__ partial, int n_tiles, int64_t nrows, const float* __restrict__ scale,
                     const float* __restrict__ subscale, const float* __restrict__ sub, int64_t lds,
                     float* __restrict__ out) {
+    constexpr int Q = B / 4;
     const int64_t g = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;   // float4 index
-    if (g >= nrows * 2) return;
+    if (g >= nrows * Q) return;
     const float4* p = reinterpret_cast<const float4*>(partial) + g;
-    const int64_t stride = nrows * 2;
+    const int64_t stride = nrows * Q;
     float4 s0 = make_float4(0.f, 0.f, 0.f, 0.f), s1 = s0;
     int t = 0;
     for (; t + 1 < n_tiles; t += 2) {      // two fixed-order chains for memory-level parallelism
@@ -219,53 +232,75 @@ reduce_tiles_kernel(const float* __restrict__ partial, int n_tiles, int64_t nrow
         const float4 x0 = ld_stream_float4(p + static_cast<int64_t>(t) * stride);
         s0.x += x0.x; s0.y += x0.y; s0.z += x0.z; s0.w += x0.w;
     }
-    const int64_t row = g >> 1;
+    const int64_t row = g / Q;
     const float sc = scale[row];
     float4 y = make_float4(sc * (s0.x + s1.x), sc * (s0.y + s1.y), sc * (s0.z + s1.z), sc * (s0.w + s1.w));
     if (HAS_SUB) {
         const float ss = subscale[row];
-        const float* sp = sub + row * lds + (g & 1) * 4;
+        const float* sp = sub + row * lds + (g % Q) * 4;
         y.x -= ss * sp[0]; y.y -= ss * sp[1]; y.z -= ss * sp[2]; y.w -= ss * sp[3];
     }
     reinterpret_cast<float4*>(out)[g] = y;
 }
 
-}  // namespace
-
-bool use_tiled(const snapb200_ctx* c, int b) {
-    if (b != 8) return false;
-    if (c->spmm_mode == 1) return false;
-    if (c->spmm_mode == 2) return true;
-    return c->X.nnz >= (1ll << 25);   // small problems: the CSR kernel avoids staging tiles at all
-}
-
-void sell_spmm8(snapb200_ctx* c, const Sell& S, const float* in, float* out, const float* scale,
-                const float* subscale, const float* sub, int64_t lds) {
-    SB_CHECK(S.built, "tiled SpMM: format not built");
+template <int B>
+void spmm_impl(snapb200_ctx* c, const Sell& S, const float* in, float* out, const float* scale, const float* subscale,
+               const float* sub, int64_t lds) {
     cudaStream_t st = c->stream;
-    if (S.nrows == 0) return;
-    c->partial.ensure(static_cast<int64_t>(S.n_tiles) * S.nrows * 8);
-    const size_t smem = static_cast<size_t>(S.tile_cols) * 32 + 64;
+    c->partial.ensure(static_cast<int64_t>(S.n_tiles) * S.nrows * B);
+    const size_t smem = static_cast<size_t>(S.tile_cols) * 4 * B + 64;
     const int grid = c->num_sms;
     if (S.vals.p) {
-        auto k = sell_spmm8_kernel<true, 2>;
+        auto k = sell_spmm_kernel<B, true, 2>;
         SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         k<<<grid, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p, S.data.p, S.vals.p, in,
                                             c->partial.p, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols, S.nrows);
     } else {
-        auto k = sell_spmm8_kernel<false, 4>;
+        auto k = sell_spmm_kernel<B, false, 4>;
         SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         k<<<grid, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p, S.data.p, nullptr, in,
                                             c->partial.p, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols, S.nrows);
     }
     SB_LAUNCH_CHECK();
-    const unsigned rb = static_cast<unsigned>(ceil_div(S.nrows * 2, 256));
+    const unsigned rb = static_cast<unsigned>(ceil_div(S.nrows * (B / 4), 256));
     if (sub)
-        reduce_tiles_kernel<true><<<rb, 256, 0, st>>>(c->partial.p, S.n_tiles, S.nrows, scale, subscale, sub, lds, out);
+        reduce_tiles_kernel<B, true><<<rb, 256, 0, st>>>(c->partial.p, S.n_tiles, S.nrows, scale, subscale, sub, lds, out);
     else
-        reduce_tiles_kernel<false><<<rb, 256, 0, st>>>(c->partial.p, S.n_tiles, S.nrows, scale, nullptr, nullptr, 0, out);
+        reduce_tiles_kernel<B, false><<<rb, 256, 0, st>>>(c->partial.p, S.n_tiles, S.nrows, scale, nullptr, nullptr, 0, out);
     SB_LAUNCH_CHECK();
     count_launch(c, 2);
+}
+
+}  // namespace
+
+bool use_tiled(const snapb200_ctx* c, int b) {
+    if (b != 8 && b != 4) return false;
+    if (c->spmm_mode == 1) return false;
+    if (c->spmm_mode == 2) return true;
+    return c->X.nnz >= (1ll << 25);   // small problems: the CSR kernel avoids staging tiles at all
+}
+
+void ensure_tiled(snapb200_ctx* c, int b) {
+    if (c->S1.built && c->S2.built && c->S1.b == b && c->S2.b == b) return;
+    cudaStream_t st = c->stream;
+    SB_CUDA(cudaEventRecord(c->ev0, st));
+    c->S1.clear();
+    c->S2.clear();
+    sell_build(c, c->X, c->S2, b);
+    sell_build(c, c->Xt, c->S1, b);
+    SB_CUDA(cudaEventRecord(c->ev1, st));
+    SB_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    SB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.ms_format = ms;
+}
+
+void sell_spmm(snapb200_ctx* c, const Sell& S, const float* in, float* out, const float* scale,
+               const float* subscale, const float* sub, int64_t lds) {
+    SB_CHECK(S.built, "tiled SpMM: format not built");
+    if (S.nrows == 0) return;
+    if (S.b == 8) spmm_impl<8>(c, S, in, out, scale, subscale, sub, lds);
+    else spmm_impl<4>(c, S, in, out, scale, subscale, sub, lds);
 }
 
 }  // namespace snapb

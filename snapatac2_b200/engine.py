@@ -177,6 +177,10 @@ class Engine:
         code = {"auto": 0, "csr": 1, "tiled": 2}.get(mode, mode)
         _lib.check(self._lib.snapb200_set_spmm_mode(self._ctx, int(code)))
 
+    def set_block(self, block: int):
+        """Default Lanczos block width (4, 8 or 16)."""
+        _lib.check(self._lib.snapb200_set_block(self._ctx, int(block)))
+
     def stream_handle(self) -> int:
         """Raw ``cudaStream_t`` of the context (for torch.cuda.ExternalStream)."""
         h = C.c_void_p()

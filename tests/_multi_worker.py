@@ -1,0 +1,63 @@
+"""Worker for tests/test_gpu_multi.py (run under torch.distributed.run, one rank per GPU).
+
+Shard invariance: the N-rank row-sharded solve must reproduce the 1-GPU solve
+(idf / degree to 1e-9, eigenvalues to 1e-6 relative, eigenvectors |cos| >= 0.99999)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+import torch
+import torch.distributed as td
+
+from snapatac2_b200 import Engine, MiniAnnData, dist, synth, tl
+
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"]); world = int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(local)
+td.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+mode = sys.argv[1] if len(sys.argv) > 1 else "auto"
+
+spec = synth.make_spec(9000, 60000, 1200, n_clusters=40, seed=3)
+k = 20
+bounds = dist.equal_row_splits(spec.n, world)
+r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+
+eng = Engine(local)
+eng.set_spmm_mode(mode)
+dist.attach_engine_comm(eng)
+eng.generate(spec, row0=r0, n_local=r1 - r0)
+idf, deg = eng.prepare()
+evals, evecs = eng.eigsh(k, seed=0)
+stats = eng.stats()
+
+# gather the sharded result on rank 0
+parts = [None] * world
+td.gather_object((deg, evecs), parts if rank == 0 else None, dst=0)
+
+# the public wrapper in distributed mode: every rank passes its own row block
+X_local = eng.export_csr()
+ad = MiniAnnData(X_local)
+tl._engine = eng
+ev_w, emb_w = tl.spectral(ad, n_comps=k, features=None, inplace=False, weighted_by_sd=False)
+assert np.allclose(ev_w, evals, rtol=1e-9), (ev_w, evals)
+assert emb_w.shape == (r1 - r0, k)
+
+if rank == 0:
+    deg_all = np.concatenate([p[0] for p in parts])
+    evec_all = np.concatenate([p[1] for p in parts], axis=0)
+    solo = Engine(local)
+    solo.set_spmm_mode(mode)
+    solo.generate(spec)
+    idf1, deg1 = solo.prepare()
+    ev1, evec1 = solo.eigsh(k, seed=0)
+    np.testing.assert_allclose(idf, idf1, rtol=1e-12)
+    np.testing.assert_allclose(deg_all, deg1, rtol=1e-9)
+    np.testing.assert_allclose(evals, ev1, rtol=1e-6)
+    cos = np.abs(np.sum(evec_all * evec1, axis=0)) / (np.linalg.norm(evec_all, axis=0) * np.linalg.norm(evec1, axis=0))
+    assert cos.min() > 0.99999, cos
+    assert abs(np.linalg.norm(evec_all[:, 3]) - 1.0) < 1e-5
+    print(f"MULTI_OK world={world} mode={mode} n_ops={stats['n_ops']} ms_comm={stats['ms_comm']:.3f} min_cos={cos.min():.8f}")
+    solo.close()
+td.barrier()
+eng.close()
+td.destroy_process_group()

@@ -1,6 +1,6 @@
 """GPU (-m gpu): the shared-memory tiled (sliced-ELL) SpMM path against the
 oracle operator and against the CSR-gather path, several column tiles in both
-passes, binarised and count-valued inputs."""
+passes, binarised and count-valued inputs, block widths 4 and 8."""
 
 import numpy as np
 import pytest
@@ -20,10 +20,10 @@ def _oracle_operator(X):
     return xt, dinv, w, deg
 
 
-@pytest.mark.parametrize("valued", [False, True])
-def test_tiled_operator_matches_oracle_and_csr_path(engine, valued):
-    # 14000 cells -> 3 cell tiles in pass 1; 20000 bins -> 4 feature tiles in pass 2
-    spec = synth.make_spec(14000, 20000, 300, n_clusters=20, seed=17)
+@pytest.mark.parametrize("valued,block", [(False, 8), (True, 8), (False, 4), (True, 4)])
+def test_tiled_operator_matches_oracle_and_csr_path(engine, valued, block):
+    # 27000 cells -> 3 (b=4) / 5 (b=8) cell tiles in pass 1; 30000 bins -> 3 / 5 feature tiles in pass 2
+    spec = synth.make_spec(27000, 30000, 200, n_clusters=20, seed=17)
     engine.generate(spec)
     X = engine.export_csr().astype(np.float64)
     if valued:
@@ -31,30 +31,36 @@ def test_tiled_operator_matches_oracle_and_csr_path(engine, valued):
         X.data = rng.integers(1, 6, size=X.nnz).astype(np.float64)
     xt, dinv, w, deg = _oracle_operator(X)
     rng = np.random.default_rng(1)
-    V = rng.standard_normal((14000, 8)).astype(np.float32)
+    V = rng.standard_normal((27000, block)).astype(np.float32)
     want = xt @ (xt.T @ V.astype(np.float64)) - dinv[:, None] * V
     got = {}
-    for mode in ("csr", "tiled"):
-        engine.set_spmm_mode(mode)
-        engine.load_csr(X, binarized=not valued)
-        engine.set_feature_weights(None)
-        idf, degree = engine.prepare()
-        np.testing.assert_allclose(idf, w, rtol=1e-5)
-        np.testing.assert_allclose(degree, deg, rtol=1e-5)
-        Y = engine.operator_apply(V)
-        assert engine.stats()["spmm_tiled"] == (1 if mode == "tiled" else 0)
-        err = np.abs(Y - want).max() / np.abs(want).max()
-        assert err < 2e-5, (mode, err)
-        got[mode] = Y
-        # bitwise repeatable (no atomics anywhere on the path)
-        np.testing.assert_array_equal(engine.operator_apply(V), Y)
-    assert np.abs(got["csr"] - got["tiled"]).max() / np.abs(want).max() < 1e-5
-    engine.set_spmm_mode("auto")
+    engine.set_block(block)
+    try:
+        for mode in ("csr", "tiled"):
+            engine.set_spmm_mode(mode)
+            engine.load_csr(X, binarized=not valued)
+            engine.set_feature_weights(None)
+            idf, degree = engine.prepare()
+            np.testing.assert_allclose(idf, w, rtol=1e-5)
+            np.testing.assert_allclose(degree, deg, rtol=1e-5)
+            Y = engine.operator_apply(V)
+            assert engine.stats()["spmm_tiled"] == (1 if mode == "tiled" else 0)
+            err = np.abs(Y - want).max() / np.abs(want).max()
+            assert err < 2e-5, (mode, err)
+            got[mode] = Y
+            # bitwise repeatable (no atomics anywhere on the path)
+            np.testing.assert_array_equal(engine.operator_apply(V), Y)
+        assert np.abs(got["csr"] - got["tiled"]).max() / np.abs(want).max() < 1e-5
+    finally:
+        engine.set_spmm_mode("auto")
+        engine.set_block(8)
 
 
-def test_tiled_eigsh_parity_config1(engine):
+@pytest.mark.parametrize("block", [8, 4])
+def test_tiled_eigsh_parity_config1(engine, block):
     spec = synth.make_spec(5000, 100000, 3000, n_clusters=48, seed=0)
     engine.set_spmm_mode("tiled")
+    engine.set_block(block)
     try:
         engine.generate(spec)
         X = engine.export_csr()
@@ -64,8 +70,10 @@ def test_tiled_eigsh_parity_config1(engine):
         np.testing.assert_allclose(idf, w_o, rtol=1e-5)
         np.testing.assert_allclose(deg, deg_o, rtol=1e-5)
         evals, evecs = engine.eigsh(30, seed=0)
-        assert engine.stats()["spmm_tiled"] == 1
+        st = engine.stats()
+        assert st["spmm_tiled"] == 1 and st["block"] == block
         np.testing.assert_allclose(evals, ev_o, rtol=1e-4)
         assert eigvec_agreement(ev_o, evec_o, evecs).min() >= 0.999
     finally:
         engine.set_spmm_mode("auto")
+        engine.set_block(8)
