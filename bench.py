@@ -84,7 +84,10 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def mark_begin(self):
+        self.t_begin = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -94,8 +97,15 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t_end = time.time()
+        t_begin = getattr(self, "t_begin", 0.0)
+        inside = [r for (ts, r) in self.rows if t_begin <= ts <= t_end + 0.2]
+        region = "timed region"
+        if not inside:
+            inside = [r for (_, r) in self.rows]
+            region = "warm-up + timed region (timed region shorter than the sampling period)"
         sm, smax, reasons = [], [], set()
-        for r in self.rows:
+        for r in inside:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -107,7 +117,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "sampled_over": region, "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------
@@ -230,14 +240,17 @@ def run_ours(args):
         call_ms["prepare"], call_ms["eigsh"] = 1e3 * (t_b - t_a), 1e3 * (t_c - t_b)
         return out
 
+    # the clock sampler starts before the warm-up (nvidia-smi needs ~1 s to come up); only the samples
+    # taken inside the timed region are reported (all samples under load if the region is too short)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         step()
 
     # ---- timed region: K steps, device events on the library's stream, max over ranks
-    sampler = ClockSampler(local_rank)
     launches0 = eng.stats()["kernel_launches"]
     sync_all()
-    sampler.start()
+    sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(ext_stream)
     t0 = time.perf_counter()
@@ -280,7 +293,7 @@ def run_ours(args):
             traffic = None
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": traffic, "peak_source": peak_src, "kernel": ("sell_spmm8_kernel (shared-memory tiled)" if stats.get("spmm_tiled") else f"gather_rows_kernel<{b}> (CSR, L2 gather)")
+        "traffic": traffic, "peak_source": peak_src, "kernel": (f"sell_spmm_kernel<{b}> (shared-memory tiled)" if stats.get("spmm_tiled") else f"gather_rows_kernel<{b}> (CSR, L2 gather)")
         + " pass1+pass2 = one operator application",
         "algorithmic_bytes": bytes_p1 + bytes_p2, "ms_pass1": p1, "ms_pass2": p2, "ms_allreduce": cm,
         "frac_pass1": bytes_p1 / (p1 * 1e-3) / 1e9 / peak, "frac_pass2": bytes_p2 / (p2 * 1e-3) / 1e9 / peak,
@@ -364,7 +377,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", choices=sorted(CONFIGS), default=os.environ.get("SNAPB200_BENCH_CONFIG", "c3"))
     ap.add_argument("--block", type=int, default=0)
-    ap.add_argument("--spmm", choices=["auto", "csr", "tiled"], default="auto")
+    ap.add_argument("--spmm", choices=["auto", "csr", "tiled", "auto+matched", "tiled+matched"], default="auto")
     ap.add_argument("--tol", type=float, default=0.0)
     ap.add_argument("--op-iters", type=int, default=5)
     ap.add_argument("--e2e-steps", type=int, default=2)

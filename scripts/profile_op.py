@@ -14,11 +14,13 @@ n, m, nnz_row, K, k = bench.CONFIGS[cfg]
 spec = synth.make_spec(n, m, nnz_row, K, seed=0)
 eng = Engine(0)
 eng.set_spmm_mode(mode)
+blk = 4 if what.endswith("4") else 8
+eng.set_block(blk)
 eng.generate(spec)
 t0 = time.perf_counter(); eng.prepare(want_outputs=False); t1 = time.perf_counter()
 print("prepare wall ms", 1e3 * (t1 - t0), {k2: v for k2, v in eng.stats().items() if k2.startswith("ms_")})
-if what == "op":
-    print("operator_time", eng.operator_time(b=8, iters=2, flush_l2=True))
+if what.startswith("op"):
+    print("operator_time", eng.operator_time(b=blk, iters=2, flush_l2=True))
 else:
     t0 = time.perf_counter(); ev, _ = eng.eigsh(k); t1 = time.perf_counter()
     print("eigsh wall ms", 1e3 * (t1 - t0), eng.stats())

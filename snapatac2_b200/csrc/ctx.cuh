@@ -134,6 +134,7 @@ struct snapb200_ctx {
     snapb::Sell S1;  // tiled copy of Xt (pass 1: gathers r.*V rows by cell)
     int spmm_mode = 0;   // 0 = auto, 1 = CSR gather from L2, 2 = shared-memory tiled SELL
     int block = 8;       // default Lanczos block width (prepare builds the tiled copies for it)
+    int fill_mode = 0;   // tiled format entry order: 0 = per-lane class rotation, 1 = + group matching of the remainder
 
     // user feature weights (host copy, optional)
     std::vector<double> user_weights;

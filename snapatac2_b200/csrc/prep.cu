@@ -72,14 +72,31 @@ __global__ void col_count_kernel(const int32_t* __restrict__ idx, int64_t nnz, i
 
 __global__ void bitmap_set_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                                   int64_t r0, int64_t r1, int64_t m, uint32_t* __restrict__ bm) {
+    // kSetSplit warps share a row so that a 1024-row slab keeps every SM busy
+    // (one warp per row left ~7 warps per SM and the kernel latency bound)
+    constexpr int kSetSplit = 8;
     int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     int lane = threadIdx.x & 31;
     int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    for (int64_t r = r0 + warp; r < r1; r += nwarps) {
-        int64_t il = r - r0;
+    const int64_t n_units = (r1 - r0) * kSetSplit;
+    for (int64_t u = warp; u < n_units; u += nwarps) {
+        const int64_t r = r0 + u / kSetSplit;
+        const int part = static_cast<int>(u % kSetSplit);
+        const int64_t il = r - r0;
         uint32_t* plane = bm + (il >> 5) * m;
-        uint32_t bit = 1u << (il & 31);
-        for (int64_t p = ptr[r] + lane; p < ptr[r + 1]; p += 32) atomicOr(plane + ld_stream_int(idx + p), bit);
+        const uint32_t bit = 1u << (il & 31);
+        const int64_t s = ptr[r], len = ptr[r + 1] - s;
+        const int64_t lo = s + (len * part) / kSetSplit, hi = s + (len * (part + 1)) / kSetSplit;
+        int64_t p = lo + lane;
+        for (; p + 96 < hi; p += 128) {   // four index loads in flight per lane
+            const int j0 = ld_stream_int(idx + p), j1 = ld_stream_int(idx + p + 32);
+            const int j2 = ld_stream_int(idx + p + 64), j3 = ld_stream_int(idx + p + 96);
+            atomicOr(plane + j0, bit);
+            atomicOr(plane + j1, bit);
+            atomicOr(plane + j2, bit);
+            atomicOr(plane + j3, bit);
+        }
+        for (; p < hi; p += 32) atomicOr(plane + ld_stream_int(idx + p), bit);
     }
 }
 
@@ -99,15 +116,22 @@ __global__ void bitmap_emit_kernel(const uint32_t* __restrict__ bm, int64_t m, i
     int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (j >= m) return;
     int64_t cur = cursor[j];
-    for (int k = 0; k < planes; ++k) {
-        uint32_t word = bm[static_cast<int64_t>(k) * m + j];
-        while (word) {
-            int bit = __ffs(word) - 1;
-            word &= word - 1;
-            int64_t r = r0 + k * 32 + bit;
-            tidx[cur] = static_cast<int32_t>(r);
-            if (val) tval[cur] = val[find_in_row(idx, ptr[r], ptr[r + 1], static_cast<int32_t>(j))];
-            ++cur;
+    for (int k0 = 0; k0 < planes; k0 += 8) {
+        uint32_t words[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)   // eight independent (coalesced) loads in flight
+            words[u] = (k0 + u < planes) ? bm[static_cast<int64_t>(k0 + u) * m + j] : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            uint32_t word = words[u];
+            while (word) {
+                int bit = __ffs(word) - 1;
+                word &= word - 1;
+                int64_t r = r0 + (k0 + u) * 32 + bit;
+                tidx[cur] = static_cast<int32_t>(r);
+                if (val) tval[cur] = val[find_in_row(idx, ptr[r], ptr[r + 1], static_cast<int32_t>(j))];
+                ++cur;
+            }
         }
     }
     cursor[j] = cur;
@@ -340,7 +364,7 @@ static void build_transpose_impl(snapb200_ctx* c, DevBuf<int32_t>& cnt) {
     for (int64_t r0 = 0; r0 < n; r0 += S) {
         int64_t r1 = std::min<int64_t>(n, r0 + S);
         SB_CUDA(cudaMemsetAsync(bm.p, 0, sizeof(uint32_t) * static_cast<size_t>(planes) * m, c->stream));
-        int g = grid_for_rows(c, r1 - r0);
+        int g = grid_for_rows(c, (r1 - r0) * 8);   // 8 warps per row (kSetSplit)
         bitmap_set_kernel<<<g, 256, 0, c->stream>>>(X.ptr.p, X.idx.p, r0, r1, m, bm.p);
         SB_LAUNCH_CHECK();
         int pl = static_cast<int>(ceil_div(r1 - r0, 32));

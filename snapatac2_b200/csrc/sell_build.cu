@@ -99,49 +99,116 @@ sell_plan_kernel(const int64_t* __restrict__ window_start, const int64_t* __rest
     }
 }
 
-// Per-lane class counters packed 16 bits each into 64-bit words (register only).
+// Per-lane counters packed 16 bits each into 64-bit words (register only).
 template <int NC>
-struct ClassCounters {
+struct Packed {
     uint64_t w[NC / 4];
     __device__ __forceinline__ void clear() {
 #pragma unroll
         for (int i = 0; i < NC / 4; ++i) w[i] = 0;
     }
-    // returns the count before the increment
-    __device__ __forceinline__ int bump(int cl) {
-        const int sh = 16 * (cl & 3);
-        int old = 0;
+    __device__ __forceinline__ int get(int c) const {
+        uint64_t x = w[0];
+#pragma unroll
+        for (int i = 1; i < NC / 4; ++i)
+            if ((c >> 2) == i) x = w[i];
+        return static_cast<int>((x >> (16 * (c & 3))) & 0xFFFFull);
+    }
+    __device__ __forceinline__ void add(int c, int v) {
+        const uint64_t inc = static_cast<uint64_t>(v) << (16 * (c & 3));
 #pragma unroll
         for (int i = 0; i < NC / 4; ++i)
-            if ((cl >> 2) == i) {
-                old = static_cast<int>((w[i] >> sh) & 0xFFFFull);
-                w[i] += 1ull << sh;
-            }
-        return old;
+            if ((c >> 2) == i) w[i] += inc;
     }
-    __device__ __forceinline__ int min_count() const {
+    __device__ __forceinline__ int min_all() const {
         int m = 0x7fffffff;
 #pragma unroll
-        for (int i = 0; i < NC / 4; ++i)
-#pragma unroll
-            for (int s = 0; s < 4; ++s) m = min(m, static_cast<int>((w[i] >> (16 * s)) & 0xFFFFull));
+        for (int c = 0; c < NC; ++c) m = min(m, get(c));
         return m;
     }
 };
 
-// One warp per chunk: every lane lays its row segment out in the bank-conflict
-// free order described at the top of the file.  NC = classes (4 for b=8, 8 for b=4).
+// Lanes that must read distinct bank-group classes in one LDS.128 wavefront
+// form a "group": b = 4 (NC = 8): the 8 lanes of a quarter warp;
+// b = 8 (NC = 4): the 4 even or the 4 odd lanes of a quarter warp.
+template <int NC>
+__device__ __forceinline__ int group_member(int lane) { return NC == 8 ? (lane & 7) : ((lane >> 1) & 3); }
+template <int NC>
+__device__ __forceinline__ int group_lane(int lane, int member) {
+    return NC == 8 ? ((lane & ~7) | member) : ((lane & ~7) | (member << 1) | (lane & 1));
+}
+template <int NC>
+__device__ __forceinline__ unsigned group_bits(unsigned ballot, int lane) {
+    if (NC == 8) return (ballot >> (lane & ~7)) & 0xFFu;
+    const unsigned x = (ballot >> ((lane & ~7) + (lane & 1))) & 0x55u;
+    return (x & 1u) | ((x >> 1) & 2u) | ((x >> 2) & 4u) | ((x >> 3) & 8u);
+}
+template <int NC>
+__device__ __forceinline__ unsigned rotl_nc(unsigned x, int r) {
+    return ((x << r) | (x >> (NC - r))) & ((1u << NC) - 1u);
+}
+
+// Simple per-lane layout (used for chunks longer than the staging capacity):
+// class rotation while every class has entries, the rest in column order.
 template <bool HAS_VAL, int NC>
-__global__ void __launch_bounds__(256)
+__device__ void fill_lane_simple(const int32_t* __restrict__ idx, const float* __restrict__ val, int64_t s, int64_t e,
+                                 int o, int col0, int row_bytes, int steps, int32_t* __restrict__ d,
+                                 float* __restrict__ dv) {
+    Packed<NC> cnt;
+    cnt.clear();
+    for (int64_t p = s; p < e; ++p) cnt.add(idx[p] & (NC - 1), 1);
+    const int mmin = cnt.min_all();
+    cnt.clear();
+    int left = 0;
+    for (int64_t p = s; p < e; ++p) {
+        const int j = idx[p];
+        const int cl = j & (NC - 1);
+        const int q = cnt.get(cl);
+        cnt.add(cl, 1);
+        const int k = (q < mmin) ? NC * q + ((cl - o) & (NC - 1)) : NC * mmin + left++;
+        const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
+        d[pos] = (j - col0) * row_bytes;
+        if (HAS_VAL) dv[pos] = val[p];
+    }
+    for (int k = static_cast<int>(e - s); k < steps; ++k) {
+        const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
+        d[pos] = -1;
+        if (HAS_VAL) dv[pos] = 0.f;
+    }
+}
+
+// One warp per chunk.
+//  1. The 32 row segments of the chunk are loaded cooperatively (coalesced,
+//     four segments in flight) into shared memory as 16-bit tile-local columns
+//     -- per-lane walks over global memory were latency bound.
+//  2. Every lane counts its entries per bank-group class (walks over shared
+//     memory) and either
+//     simple:  places them by class rotation while all classes have entries,
+//              the remainder in column order; or
+//     matched: buckets them by class and lays the chunk out step by step: at
+//              step k lane l takes an entry of its rotation class
+//              (k + o(l)) mod NC when it has one; lanes that do not are
+//              matched, inside their group, to the classes left free by the
+//              other members of the group (greedy, lowest lane first); a lane
+//              with slack idles rather than take a conflicting class.
+constexpr int kFillWarps = 8;
+constexpr int kColPitch = 33;   // uint16 columns staged as [position][lane], padded against bank conflicts
+
+template <bool HAS_VAL, int NC, bool MATCHED, int CAP>
+__global__ void __launch_bounds__(kFillWarps * 32)
 sell_fill_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
                  const int32_t* __restrict__ segptr, int n_tiles, int tile_cols, int row_bytes, int64_t n_chunks,
                  int64_t chunks_per_tile, const int32_t* __restrict__ chunk_rows,
                  const int32_t* __restrict__ chunk_len4, const int64_t* __restrict__ chunk_off,
                  int32_t* __restrict__ data, float* __restrict__ vals) {
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) unsigned char fill_smem[];
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    uint16_t* cols = reinterpret_cast<uint16_t*>(fill_smem) + static_cast<size_t>(wic) * CAP * kColPitch;
+    uint8_t* bkt = fill_smem + static_cast<size_t>(kFillWarps) * CAP * kColPitch * 2 + static_cast<size_t>(wic) * CAP * 32;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
-    const int o = (NC == 4) ? ((lane >> 1) & 3) : (lane & 7);
+    const int o = group_member<NC>(lane);
     for (int64_t c = warp; c < n_chunks; c += nwarps) {
         const int steps = chunk_len4[c] * 4;
         if (steps == 0) continue;
@@ -155,26 +222,123 @@ sell_fill_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
             s = ptr[row] + sp[0];
             e = ptr[row] + sp[1];
         }
-        ClassCounters<NC> cnt;
-        cnt.clear();
-        for (int64_t p = s; p < e; ++p) cnt.bump(idx[p] & (NC - 1));
-        const int mmin = cnt.min_count();
-        cnt.clear();
-        int left = 0;
         const int col0 = t * tile_cols;
-        for (int64_t p = s; p < e; ++p) {
-            const int j = idx[p];
-            const int cl = j & (NC - 1);
-            const int q = cnt.bump(cl);
-            const int k = (q < mmin) ? NC * q + ((cl - o) & (NC - 1)) : NC * mmin + left++;
-            const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
-            d[pos] = (j - col0) * row_bytes;
-            if (HAS_VAL) dv[pos] = val[p];
+        const int len = static_cast<int>(e - s);
+        if (steps > CAP) {   // warp-uniform; rare (very long segments): per-lane walks over global memory
+            fill_lane_simple<HAS_VAL, NC>(idx, val, s, e, o, col0, row_bytes, steps, d, dv);
+            continue;
         }
-        for (int k = static_cast<int>(e - s); k < steps; ++k) {
+        // ---- 1. cooperative staging of the chunk's columns
+        __syncwarp();
+        for (int seg0 = 0; seg0 < 32; seg0 += 4) {
+            int64_t ss[4];
+            int ll[4], maxl = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                ss[u] = __shfl_sync(full, s, seg0 + u);
+                ll[u] = __shfl_sync(full, len, seg0 + u);
+                maxl = max(maxl, ll[u]);
+            }
+            for (int q = lane; q < maxl; q += 32) {
+                int v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = (q < ll[u]) ? ld_stream_int(idx + ss[u] + q) : 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (q < ll[u]) cols[q * kColPitch + seg0 + u] = static_cast<uint16_t>(v[u] - col0);
+            }
+        }
+        __syncwarp();
+        // ---- 2. per-lane class counts (walk over shared memory)
+        Packed<NC> cnt;
+        cnt.clear();
+        for (int q = 0; q < len; ++q) cnt.add(cols[q * kColPitch + lane] & (NC - 1), 1);
+
+        if (!MATCHED) {
+            const int mmin = cnt.min_all();
+            cnt.clear();
+            int left = 0;
+            for (int q = 0; q < len; ++q) {
+                const int jl = cols[q * kColPitch + lane];
+                const int cl = jl & (NC - 1);
+                const int r = cnt.get(cl);
+                cnt.add(cl, 1);
+                const int k = (r < mmin) ? NC * r + ((cl - o) & (NC - 1)) : NC * mmin + left++;
+                const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
+                d[pos] = jl * row_bytes;
+                if (HAS_VAL) dv[pos] = val[s + q];
+            }
+            for (int k = len; k < steps; ++k) {
+                const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
+                d[pos] = -1;
+                if (HAS_VAL) dv[pos] = 0.f;
+            }
+            continue;
+        }
+        // ---- matched: bucket the lane's positions by class
+        Packed<NC> ofs, hd;
+        ofs.clear();
+        unsigned avail = 0;
+        {
+            int run = 0;
+#pragma unroll
+            for (int cl = 0; cl < NC; ++cl) {
+                const int n_cl = cnt.get(cl);
+                ofs.add(cl, run);
+                run += n_cl;
+                if (n_cl > 0) avail |= 1u << cl;
+            }
+        }
+        hd.clear();
+        for (int q = 0; q < len; ++q) {
+            const int cl = cols[q * kColPitch + lane] & (NC - 1);
+            bkt[(ofs.get(cl) + hd.get(cl)) * 32 + lane] = static_cast<uint8_t>(q);
+            hd.add(cl, 1);
+        }
+        hd.clear();
+        int total = len;
+        // ---- step by step layout
+        for (int k = 0; k < steps; ++k) {
+            const int dcls = (k + o) & (NC - 1);
+            const bool has = total > 0;
+            const bool primary = has && ((avail >> dcls) & 1u);
+            int cls = primary ? dcls : -1;
+            const unsigned np = __ballot_sync(full, !primary);
+            const unsigned holes = __ballot_sync(full, has && !primary);
+            if (holes) {
+                unsigned freec = rotl_nc<NC>(group_bits<NC>(np, lane), k & (NC - 1));
+                unsigned pend = group_bits<NC>(holes, lane);
+                while (__any_sync(full, pend != 0)) {
+                    const int mem = pend ? (__ffs(pend) - 1) : 0;
+                    const int src = group_lane<NC>(lane, mem);
+                    int chosen_free = -1;
+                    if (pend && lane == src) {
+                        const unsigned usable = freec & avail;
+                        if (usable) { cls = __ffs(usable) - 1; chosen_free = cls; }
+                        else if (total >= steps - k) cls = __ffs(avail) - 1;   // no slack left: accept a conflict
+                        // otherwise idle this step (the lane is shorter than the chunk, it can wait)
+                    }
+                    const int cf = __shfl_sync(full, chosen_free, src);
+                    if (pend) {
+                        if (cf >= 0) freec &= ~(1u << cf);
+                        pend &= pend - 1;
+                    }
+                }
+            }
+            int out = -1;
+            float outv = 0.f;
+            if (cls >= 0) {
+                const int h = hd.get(cls);
+                const int rel = bkt[(ofs.get(cls) + h) * 32 + lane];
+                hd.add(cls, 1);
+                if (h + 1 == cnt.get(cls)) avail &= ~(1u << cls);
+                --total;
+                out = static_cast<int>(cols[rel * kColPitch + lane]) * row_bytes;
+                if (HAS_VAL) outv = val[s + rel];
+            }
             const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
-            d[pos] = -1;
-            if (HAS_VAL) dv[pos] = 0.f;
+            d[pos] = out;
+            if (HAS_VAL) dv[pos] = outv;
         }
     }
 }
@@ -236,14 +400,30 @@ void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b) {
     S.data.alloc(std::max<int64_t>(4, S.n_entries));
     if (M.has_values()) S.vals.alloc(std::max<int64_t>(4, S.n_entries));
     if (n_chunks > 0 && S.n_entries > 0) {
-        const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_chunks, 8), static_cast<int64_t>(c->num_sms) * 32));
+        const bool matched = c->fill_mode == 1;
         const int rb = 4 * b;
-#define SB_FILL(HV, NC)                                                                                            \
-    sell_fill_kernel<HV, NC><<<blocks, 256, 0, st>>>(M.ptr.p, M.idx.p, M.val.p, segptr.p, T, S.tile_cols, rb, n_chunks, \
-                                                     S.chunks_per_tile, S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p, \
-                                                     S.data.p, S.vals.p)
-        if (M.has_values()) { if (b == 8) SB_FILL(true, 4); else SB_FILL(true, 8); }
-        else                { if (b == 8) SB_FILL(false, 4); else SB_FILL(false, 8); }
+        // staging capacity (steps): segments average ~nnz_row/tiles; longer chunks take the slow path
+#define SB_FILL(HV, NC, MT, CAP)                                                                                      \
+    do {                                                                                                               \
+        const size_t fsm = static_cast<size_t>(kFillWarps) * CAP * kColPitch * 2 +                                     \
+                           (MT ? static_cast<size_t>(kFillWarps) * CAP * 32 : 0);                                      \
+        auto kern = sell_fill_kernel<HV, NC, MT, CAP>;                                                                 \
+        SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));       \
+        const int per_sm = std::max<int>(1, static_cast<int>((220u << 10) / fsm));                                     \
+        const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_chunks, kFillWarps),                          \
+                                                              static_cast<int64_t>(c->num_sms) * per_sm));             \
+        kern<<<blocks, kFillWarps * 32, fsm, st>>>(M.ptr.p, M.idx.p, M.val.p, segptr.p, T, S.tile_cols, rb, n_chunks, \
+                                                   S.chunks_per_tile, S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p,  \
+                                                   S.data.p, S.vals.p);                                                \
+    } while (0)
+        const bool hv = M.has_values();
+        if (b == 8) {
+            if (hv) { if (matched) SB_FILL(true, 4, true, 128); else SB_FILL(true, 4, false, 128); }
+            else    { if (matched) SB_FILL(false, 4, true, 128); else SB_FILL(false, 4, false, 128); }
+        } else {
+            if (hv) { if (matched) SB_FILL(true, 8, true, 256); else SB_FILL(true, 8, false, 256); }
+            else    { if (matched) SB_FILL(false, 8, true, 256); else SB_FILL(false, 8, false, 256); }
+        }
 #undef SB_FILL
         SB_LAUNCH_CHECK();
     }

@@ -36,7 +36,7 @@ def test_tiled_operator_matches_oracle_and_csr_path(engine, valued, block):
     got = {}
     engine.set_block(block)
     try:
-        for mode in ("csr", "tiled"):
+        for mode in ("csr", "tiled", "tiled+matched"):
             engine.set_spmm_mode(mode)
             engine.load_csr(X, binarized=not valued)
             engine.set_feature_weights(None)
@@ -44,13 +44,14 @@ def test_tiled_operator_matches_oracle_and_csr_path(engine, valued, block):
             np.testing.assert_allclose(idf, w, rtol=1e-5)
             np.testing.assert_allclose(degree, deg, rtol=1e-5)
             Y = engine.operator_apply(V)
-            assert engine.stats()["spmm_tiled"] == (1 if mode == "tiled" else 0)
+            assert engine.stats()["spmm_tiled"] == (0 if mode == "csr" else 1)
             err = np.abs(Y - want).max() / np.abs(want).max()
             assert err < 2e-5, (mode, err)
             got[mode] = Y
             # bitwise repeatable (no atomics anywhere on the path)
             np.testing.assert_array_equal(engine.operator_apply(V), Y)
         assert np.abs(got["csr"] - got["tiled"]).max() / np.abs(want).max() < 1e-5
+        assert np.abs(got["csr"] - got["tiled+matched"]).max() / np.abs(want).max() < 1e-5
     finally:
         engine.set_spmm_mode("auto")
         engine.set_block(8)
