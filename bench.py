@@ -248,14 +248,18 @@ def run_ours(args):
         step()
 
     # ---- timed region: K steps, device events on the library's stream, max over ranks
-    launches0 = eng.stats()["kernel_launches"]
+    st0 = eng.stats()
+    launches0 = st0["kernel_launches"]
     sync_all()
     sampler.mark_begin()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(ext_stream)
     t0 = time.perf_counter()
+    step_wall = []
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         evals, _ = step()
+        step_wall.append(round(1e3 * (time.perf_counter() - t_s), 2))
     ev1.record(ext_stream)
     ev1.synchronize()
     wall = time.perf_counter() - t0
@@ -356,10 +360,12 @@ def run_ours(args):
                        if nnz_local * 4 > (256 << 20) else "inputs fit L2; operator_time flushes L2 between iterations"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "timing": {"device_ms_total": total_ms, "wall_ms_total": wall_ms, "generate_s": t_gen,
-                       "last_step_call_ms": call_ms},
+                       "last_step_call_ms": call_ms, "step_wall_ms": step_wall,
+                       "pool_mallocs_in_timed_region": stats["pool_mallocs"] - st0["pool_mallocs"],
+                       "pool_ms_in_timed_region": stats["ms_pool"] - st0["ms_pool"]},
             "solver": {kk: stats[kk] for kk in ("n_ops", "n_restarts", "basis_cols", "max_residual", "ms_transpose",
                                                 "ms_prepare", "ms_format", "ms_eigsh", "ms_spmm", "ms_ortho", "ms_comm", "ms_host",
-                                                "spmm_tiled", "ms_prepare_wall")},
+                                                "spmm_tiled", "ms_prepare_wall", "ms_pool", "pool_mallocs")},
             "evals_head": [float(x) for x in evals[:4]],
         }
         print(json.dumps(line), flush=True)

@@ -59,7 +59,8 @@ typedef struct snapb200_stats {
     double ms_format;      /* building the shared-memory tiled (sliced-ELL) copies */
     int64_t spmm_tiled;    /* 1 if the last operator ran the tiled kernels     */
     double ms_prepare_wall; /* host wall clock of the whole prepare call        */
-    int64_t reserved[2];
+    double ms_pool;        /* host time spent in cudaMalloc/cudaFree by the caching allocator (cumulative) */
+    int64_t pool_mallocs;  /* driver allocations so far (cumulative; a steady state adds none)             */
 } snapb200_stats;
 
 /* Library / error plumbing. */
@@ -151,7 +152,7 @@ int  snapb200_get_stats(snapb200_ctx* ctx, snapb200_stats* out);
  * ~2x the format build time).  Takes effect at the next prepare. */
 int  snapb200_set_spmm_mode(snapb200_ctx* ctx, int mode);
 
-/* Default Lanczos block width b (4, 8 or 16; initially 8).  prepare() builds
+/* Default Lanczos block width b (4, 8 or 16; initially 4).  prepare() builds
  * the tiled copies for it and eigsh(block = 0) uses it. */
 int  snapb200_set_block(snapb200_ctx* ctx, int block);
 

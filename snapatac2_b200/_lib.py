@@ -35,11 +35,11 @@ class Stats(C.Structure):
         ("block", C.c_int64), ("nnz_local", C.c_int64), ("kernel_launches", C.c_int64),
         ("ms_format", C.c_double), ("spmm_tiled", C.c_int64),
         ("ms_prepare_wall", C.c_double),
-        ("reserved", C.c_int64 * 2),
+        ("ms_pool", C.c_double), ("pool_mallocs", C.c_int64),
     ]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_}
 
 
 _lib = None

@@ -393,6 +393,11 @@ int snapb200_eigsh(snapb200_ctx* c, int k, int64_t seed, double tol, int block, 
 int snapb200_get_stats(snapb200_ctx* c, snapb200_stats* out) {
     return guarded([&] {
         SB_CHECK(c && out, "get_stats: null argument");
+        long long mallocs = 0, reuses = 0, trims = 0;
+        double ms = 0.0;
+        pool_counters(&mallocs, &reuses, &trims, &ms);
+        c->stats.ms_pool = ms;
+        c->stats.pool_mallocs = mallocs;
         *out = c->stats;
     });
 }

@@ -13,6 +13,7 @@ void* pool_alloc(size_t bytes);
 void pool_free(void* p);
 void pool_trim();
 void pool_set_stream(cudaStream_t s);
+void pool_counters(long long* mallocs, long long* reuses, long long* trims, double* ms);
 
 // Owning device buffer (released to the pool with the context or on reassignment).
 template <typename T>
@@ -133,7 +134,10 @@ struct snapb200_ctx {
     snapb::Sell S2;  // tiled copy of X  (pass 2: gathers W rows by feature)
     snapb::Sell S1;  // tiled copy of Xt (pass 1: gathers r.*V rows by cell)
     int spmm_mode = 0;   // 0 = auto, 1 = CSR gather from L2, 2 = shared-memory tiled SELL
-    int block = 8;       // default Lanczos block width (prepare builds the tiled copies for it)
+    // default Lanczos block width (prepare builds the tiled copies for it).  4: a dense row is one
+    // 16-byte bank group, half the shared-memory traffic per entry of b = 8; the solver needs ~1.6x the
+    // operator applications but each costs half, and the SpMM runs at ~60% instead of ~35% of HBM peak.
+    int block = 4;
     int fill_mode = 0;   // tiled format entry order: 0 = per-lane class rotation, 1 = + group matching of the remainder
 
     // user feature weights (host copy, optional)

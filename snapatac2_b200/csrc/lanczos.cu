@@ -172,6 +172,7 @@ struct Ritz {
 template <int B>
 void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis, int max_ops, double* evals,
                 double* evecs) {
+    HostClock wall;
     const int64_t n = c->n_local, ng = c->n_global;
     cudaStream_t st = c->stream;
     SB_CHECK(k >= 1 && k < ng, "eigsh: k must satisfy 1 <= k < n_obs");
@@ -193,11 +194,13 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
     dG0.alloc(B * B);
     dG.alloc(B * B);
     dChol.alloc(chol_len);
-    PinBuf<double> hbuf;
-    hbuf.ensure(2 * static_cast<int64_t>(ld) * B + chol_len);
-    double* hH1 = hbuf.p;
-    double* hH2 = hbuf.p + static_cast<int64_t>(ld) * B;
-    double* hChol = hbuf.p + 2 * static_cast<int64_t>(ld) * B;
+    // pinned staging for the small per-step matrices lives in the context (cudaMallocHost /
+    // cudaFreeHost per call cost hundreds of milliseconds on a device with ~100 GB mapped)
+    c->pinned.ensure(static_cast<int64_t>(sizeof(double)) * (2 * static_cast<int64_t>(ld) * B + chol_len));
+    double* hbuf = reinterpret_cast<double*>(c->pinned.p);
+    double* hH1 = hbuf;
+    double* hH2 = hbuf + static_cast<int64_t>(ld) * B;
+    double* hChol = hbuf + 2 * static_cast<int64_t>(ld) * B;
     double* dH1 = dH.p;
     double* dH2 = dH.p + static_cast<int64_t>(ld) * B;
 
@@ -208,7 +211,6 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
     cudaEvent_t evs[6];
     for (auto& e : evs) SB_CUDA(cudaEventCreate(&e));
     double ms_spmm = 0.0, ms_comm = 0.0, ms_ortho = 0.0, ms_host = 0.0;
-    HostClock wall;
 
     // orthogonalise Z against Q[:, 0:nb] twice; optionally keep H1/H2
     auto orthogonalise = [&](int nb) {
@@ -422,7 +424,7 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
 void eigsh(snapb200_ctx* c, int k, int64_t seed, double tol, int block, int max_basis, int max_ops, double* evals,
            double* evecs) {
     SB_CHECK(c->prepared, "eigsh: call prepare first");
-    if (block <= 0) block = 8;
+    if (block <= 0) block = c->block;
     switch (block) {
         case 4: eigsh_impl<4>(c, k, seed, tol, max_basis, max_ops, evals, evecs); break;
         case 8: eigsh_impl<8>(c, k, seed, tol, max_basis, max_ops, evals, evecs); break;

@@ -10,6 +10,8 @@
 // block is returned to the driver and the allocation retried.
 #include "common.cuh"
 
+#include <atomic>
+#include <chrono>
 #include <map>
 #include <mutex>
 #include <unordered_map>
@@ -32,6 +34,15 @@ Pool& pool() {
     return *p;
 }
 thread_local cudaStream_t t_stream = nullptr;
+// diagnostics: driver allocations, trims and the host time spent in them
+std::atomic<long long> g_mallocs{0}, g_trims{0}, g_reuses{0};
+std::atomic<long long> g_ns{0};
+struct ScopedNs {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    ~ScopedNs() {
+        g_ns += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
 
 size_t round_size(size_t b) {
     const size_t g = b < (1u << 20) ? 512 : (2u << 20);
@@ -64,14 +75,18 @@ void* pool_alloc(size_t bytes) {
         bins.erase(it);
         if (blk.stream != t_stream && blk.stream != nullptr) cudaStreamSynchronize(blk.stream);
         P.live[blk.p] = sz;
+        ++g_reuses;
         return blk.p;
     }
+    ScopedNs timer;
+    ++g_mallocs;
     void* p = nullptr;
     cudaError_t e = cudaMalloc(&p, bytes);
     if (e == cudaErrorMemoryAllocation) {
         cudaGetLastError();
         cudaDeviceSynchronize();
         trim_locked(P, dev);
+        ++g_trims;
         e = cudaMalloc(&p, bytes);
     }
     if (e != cudaSuccess) {
@@ -98,6 +113,13 @@ void pool_free(void* p) {
     int dev = 0;
     cudaGetDevice(&dev);
     P.parked[dev].emplace(sz, Parked{p, t_stream});
+}
+
+void pool_counters(long long* mallocs, long long* reuses, long long* trims, double* ms) {
+    *mallocs = g_mallocs.load();
+    *reuses = g_reuses.load();
+    *trims = g_trims.load();
+    *ms = static_cast<double>(g_ns.load()) * 1e-6;
 }
 
 // Return every parked block of the current device to the driver.

@@ -109,7 +109,11 @@ __device__ __forceinline__ int64_t find_in_row(const int32_t* __restrict__ idx, 
     return s;
 }
 
-__global__ void bitmap_emit_kernel(const uint32_t* __restrict__ bm, int64_t m, int planes, int64_t r0,
+// One thread per feature walks the slab's planes in row order (eight coalesced word loads in
+// flight) and appends the set bits to the feature's list; consumed words are cleared in place so
+// the slab needs no separate memset.  (A 32 x 32 feature x plane CTA tiling with a shared-memory
+// prefix was tried and was 3x slower: profiles/README.md.)
+__global__ void bitmap_emit_kernel(uint32_t* __restrict__ bm, int64_t m, int planes, int64_t r0,
                                    int64_t* __restrict__ cursor, int32_t* __restrict__ tidx,
                                    const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
                                    const float* __restrict__ val, float* __restrict__ tval) {
@@ -124,6 +128,7 @@ __global__ void bitmap_emit_kernel(const uint32_t* __restrict__ bm, int64_t m, i
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             uint32_t word = words[u];
+            if (word) bm[static_cast<int64_t>(k0 + u) * m + j] = 0u;
             while (word) {
                 int bit = __ffs(word) - 1;
                 word &= word - 1;
@@ -361,9 +366,10 @@ static void build_transpose_impl(snapb200_ctx* c, DevBuf<int32_t>& cnt) {
     const int planes = static_cast<int>(S / 32);
     DevBuf<uint32_t> bm;
     bm.alloc(static_cast<int64_t>(planes) * m);
+    // cleared once; the emit kernel zeroes every word it consumes
+    SB_CUDA(cudaMemsetAsync(bm.p, 0, sizeof(uint32_t) * static_cast<size_t>(planes) * m, c->stream));
     for (int64_t r0 = 0; r0 < n; r0 += S) {
         int64_t r1 = std::min<int64_t>(n, r0 + S);
-        SB_CUDA(cudaMemsetAsync(bm.p, 0, sizeof(uint32_t) * static_cast<size_t>(planes) * m, c->stream));
         int g = grid_for_rows(c, (r1 - r0) * 8);   // 8 warps per row (kSetSplit)
         bitmap_set_kernel<<<g, 256, 0, c->stream>>>(X.ptr.p, X.idx.p, r0, r1, m, bm.p);
         SB_LAUNCH_CHECK();

@@ -154,21 +154,40 @@ template <bool HAS_VAL, int NC>
 __device__ void fill_lane_simple(const int32_t* __restrict__ idx, const float* __restrict__ val, int64_t s, int64_t e,
                                  int o, int col0, int row_bytes, int steps, int32_t* __restrict__ d,
                                  float* __restrict__ dv) {
+    // eight consecutive entries (one 32-byte sector) are loaded per iteration so that a lane exposes
+    // one memory latency per sector instead of one per entry
     Packed<NC> cnt;
     cnt.clear();
-    for (int64_t p = s; p < e; ++p) cnt.add(idx[p] & (NC - 1), 1);
+    for (int64_t p = s; p < e; p += 8) {
+        int jj[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) jj[u] = (p + u < e) ? idx[p + u] : -1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (jj[u] >= 0) cnt.add(jj[u] & (NC - 1), 1);
+    }
     const int mmin = cnt.min_all();
     cnt.clear();
     int left = 0;
-    for (int64_t p = s; p < e; ++p) {
-        const int j = idx[p];
-        const int cl = j & (NC - 1);
-        const int q = cnt.get(cl);
-        cnt.add(cl, 1);
-        const int k = (q < mmin) ? NC * q + ((cl - o) & (NC - 1)) : NC * mmin + left++;
-        const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
-        d[pos] = (j - col0) * row_bytes;
-        if (HAS_VAL) dv[pos] = val[p];
+    for (int64_t p = s; p < e; p += 8) {
+        int jj[8];
+        float vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            jj[u] = (p + u < e) ? idx[p + u] : -1;
+            vv[u] = (HAS_VAL && p + u < e) ? val[p + u] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            if (jj[u] < 0) continue;
+            const int cl = jj[u] & (NC - 1);
+            const int q = cnt.get(cl);
+            cnt.add(cl, 1);
+            const int k = (q < mmin) ? NC * q + ((cl - o) & (NC - 1)) : NC * mmin + left++;
+            const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
+            d[pos] = (jj[u] - col0) * row_bytes;
+            if (HAS_VAL) dv[pos] = vv[u];
+        }
     }
     for (int k = static_cast<int>(e - s); k < steps; ++k) {
         const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
@@ -224,7 +243,7 @@ sell_fill_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
         }
         const int col0 = t * tile_cols;
         const int len = static_cast<int>(e - s);
-        if (steps > CAP) {   // warp-uniform; rare (very long segments): per-lane walks over global memory
+        if (!MATCHED || steps > CAP) {   // warp-uniform: simple order, or a chunk too long to stage
             fill_lane_simple<HAS_VAL, NC>(idx, val, s, e, o, col0, row_bytes, steps, d, dv);
             continue;
         }
@@ -254,27 +273,6 @@ sell_fill_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
         cnt.clear();
         for (int q = 0; q < len; ++q) cnt.add(cols[q * kColPitch + lane] & (NC - 1), 1);
 
-        if (!MATCHED) {
-            const int mmin = cnt.min_all();
-            cnt.clear();
-            int left = 0;
-            for (int q = 0; q < len; ++q) {
-                const int jl = cols[q * kColPitch + lane];
-                const int cl = jl & (NC - 1);
-                const int r = cnt.get(cl);
-                cnt.add(cl, 1);
-                const int k = (r < mmin) ? NC * r + ((cl - o) & (NC - 1)) : NC * mmin + left++;
-                const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
-                d[pos] = jl * row_bytes;
-                if (HAS_VAL) dv[pos] = val[s + q];
-            }
-            for (int k = len; k < steps; ++k) {
-                const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
-                d[pos] = -1;
-                if (HAS_VAL) dv[pos] = 0.f;
-            }
-            continue;
-        }
         // ---- matched: bucket the lane's positions by class
         Packed<NC> ofs, hd;
         ofs.clear();
@@ -405,11 +403,10 @@ void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b) {
         // staging capacity (steps): segments average ~nnz_row/tiles; longer chunks take the slow path
 #define SB_FILL(HV, NC, MT, CAP)                                                                                      \
     do {                                                                                                               \
-        const size_t fsm = static_cast<size_t>(kFillWarps) * CAP * kColPitch * 2 +                                     \
-                           (MT ? static_cast<size_t>(kFillWarps) * CAP * 32 : 0);                                      \
+        const size_t fsm = MT ? static_cast<size_t>(kFillWarps) * CAP * (kColPitch * 2 + 32) : 0;                      \
         auto kern = sell_fill_kernel<HV, NC, MT, CAP>;                                                                 \
         SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));       \
-        const int per_sm = std::max<int>(1, static_cast<int>((220u << 10) / fsm));                                     \
+        const int per_sm = MT ? std::max<int>(1, static_cast<int>((220u << 10) / fsm)) : 8;                            \
         const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_chunks, kFillWarps),                          \
                                                               static_cast<int64_t>(c->num_sms) * per_sm));             \
         kern<<<blocks, kFillWarps * 32, fsm, st>>>(M.ptr.p, M.idx.p, M.val.p, segptr.p, T, S.tile_cols, rb, n_chunks, \

@@ -130,7 +130,7 @@ def spectral(
 
     Extra keyword-only knobs: ``engine`` (reuse a context), ``tol`` (relative
     residual, default 1e-5; the reference asks ARPACK for machine precision),
-    ``block`` (Lanczos block width 4/8/16, default 8).
+    ``block`` (Lanczos block width 4/8/16, default 4).
     """
     np.random.seed(random_state)                                    # :223
 

@@ -54,7 +54,7 @@ def test_tiled_operator_matches_oracle_and_csr_path(engine, valued, block):
         assert np.abs(got["csr"] - got["tiled+matched"]).max() / np.abs(want).max() < 1e-5
     finally:
         engine.set_spmm_mode("auto")
-        engine.set_block(8)
+        engine.set_block(4)
 
 
 @pytest.mark.parametrize("block", [8, 4])
@@ -77,4 +77,4 @@ def test_tiled_eigsh_parity_config1(engine, block):
         assert eigvec_agreement(ev_o, evec_o, evecs).min() >= 0.999
     finally:
         engine.set_spmm_mode("auto")
-        engine.set_block(8)
+        engine.set_block(4)
