@@ -117,10 +117,12 @@ int  snapb200_set_feature_weights(snapb200_ctx* ctx, const double* w, int64_t m)
  * entries, degree_out n_local (degree = X c - 1, i.e. 1/dinv). */
 int  snapb200_prepare(snapb200_ctx* ctx, double* idf_out, double* degree_out);
 
-/* Multi-view support (embedding.rs:417-442): Frobenius norm of the
- * off-diagonal cosine similarity over the given local rows, and a uniform
- * scale applied to this view's normalised rows before hstack. */
-int  snapb200_view_frobenius(snapb200_ctx* ctx, const int64_t* rows, int64_t n_rows, double* out);
+/* Multi-view support (multi_spectral_embedding, embedding.rs:398-416): the
+ * per-view statistics of the loaded (and column-selected) view -- its IDF
+ * weights (idf_out, m entries) and the L2 norms of its IDF-weighted rows
+ * (rho_out, n_local entries).  The caller scales and concatenates the views
+ * (embedding.rs:428-443) and runs the ordinary load/prepare/eigsh on the result. */
+int  snapb200_view_norms(snapb200_ctx* ctx, double* idf_out, double* rho_out);
 
 /* a6 alone: Y = X~ (X~^T V) - dinv .* V on b vectors (embedding.rs:162-163).
  * V and Y are host, row-major n_local x b, b in {4, 8, 16}. */

@@ -328,8 +328,8 @@ int snapb200_prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     return guarded([&] { bind(c); prepare(c, idf_out, degree_out); });
 }
 
-int snapb200_view_frobenius(snapb200_ctx* c, const int64_t* rows, int64_t n_rows, double* out) {
-    return guarded([&] { bind(c); view_frobenius(c, rows, n_rows, out); });
+int snapb200_view_norms(snapb200_ctx* c, double* idf_out, double* rho_out) {
+    return guarded([&] { bind(c); view_norms(c, idf_out, rho_out); });
 }
 
 int snapb200_operator_apply(snapb200_ctx* c, const float* V, float* Y, int b) {

@@ -194,7 +194,7 @@ void flush_l2(snapb200_ctx* c);
 void select_features(snapb200_ctx* c, const uint8_t* keep_host, int64_t m);
 void build_transpose(snapb200_ctx* c);
 void prepare(snapb200_ctx* c, double* idf_out, double* degree_out);
-void view_frobenius(snapb200_ctx* c, const int64_t* rows, int64_t n_rows, double* out);
+void view_norms(snapb200_ctx* c, double* idf_out, double* rho_out);
 
 // ---- spmm.cu
 // Y[n x b] (leading dim ldy) = X~ X~^T V - dinv .* V, V with leading dim ldv.

@@ -517,8 +517,42 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     c->prepared = true;
 }
 
-void view_frobenius(snapb200_ctx*, const int64_t*, int64_t, double*) {
-    throw Error("view_frobenius: multi-view support is not built yet");
+// Per-view statistics for multi_spectral (embedding.rs:413-416): IDF weights of the loaded
+// (and column-selected) view and the L2 norms of its IDF-weighted rows.  No transposition.
+void view_norms(snapb200_ctx* c, double* idf_out, double* rho_out) {
+    SB_CHECK(c->loaded, "view_norms: no matrix loaded");
+    Csr& X = c->X;
+    const int64_t m = c->m, n = c->n_local;
+    cudaStream_t st = c->stream;
+    DevBuf<int32_t> cnt;
+    DevBuf<int64_t> df, mm;
+    DevBuf<double> w, rho;
+    cnt.alloc(m);
+    df.alloc(m);
+    mm.alloc(2);
+    w.alloc(m);
+    rho.alloc(std::max<int64_t>(1, n));
+    SB_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int32_t) * m, st));
+    if (X.nnz > 0) {
+        int blocks = static_cast<int>(std::min<int64_t>(ceil_div(X.nnz, 256), static_cast<int64_t>(c->num_sms) * 32));
+        col_count_kernel<<<blocks, 256, 0, st>>>(X.idx.p, X.nnz, cnt.p);
+        SB_LAUNCH_CHECK();
+    }
+    i32_to_i64_kernel<<<grid1d(m), 256, 0, st>>>(cnt.p, df.p, m);
+    SB_LAUNCH_CHECK();
+    allreduce_i64(c, df.p, m);
+    df_minmax_kernel<<<1, 256, 0, st>>>(df.p, m, mm.p);
+    SB_LAUNCH_CHECK();
+    idf_kernel<<<grid1d(m), 256, 0, st>>>(df.p, mm.p, m, static_cast<double>(c->n_global), w.p);
+    SB_LAUNCH_CHECK();
+    if (n > 0) {
+        spmv_f64_kernel<0><<<grid_for_rows(c, n), 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, w.p, nullptr, 0.0, n, rho.p);
+        SB_LAUNCH_CHECK();
+    }
+    count_launch(c, 5);
+    if (idf_out) SB_CUDA(cudaMemcpyAsync(idf_out, w.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+    if (rho_out && n > 0) SB_CUDA(cudaMemcpyAsync(rho_out, rho.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
 }
 
 }  // namespace snapb

@@ -147,6 +147,13 @@ class Engine:
         _lib.check(self._lib.snapb200_prepare(self._ctx, _lib.ptr(idf), _lib.ptr(deg)))
         return idf, deg
 
+    def view_norms(self):
+        """IDF weights and IDF-weighted row norms of the loaded view (multi_spectral)."""
+        idf = np.empty(self.m, dtype=np.float64)
+        rho = np.empty(self.n_local, dtype=np.float64)
+        _lib.check(self._lib.snapb200_view_norms(self._ctx, _lib.ptr(idf), _lib.ptr(rho)))
+        return idf, rho
+
     def operator_apply(self, V):
         V = np.ascontiguousarray(V, dtype=np.float32)
         assert V.ndim == 2 and V.shape[0] == self.n_local

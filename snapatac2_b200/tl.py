@@ -184,11 +184,85 @@ def spectral(
     return evals, evecs
 
 
-def multi_spectral(adatas, n_comps: int = 30, features="selected", weights=None,
-                   random_state: int = 0, weighted_by_sd: bool = True):
-    """``snap.tl.multi_spectral`` (tools/_embedding.py:483-540).
+def _frobenius_offdiag(xhat: sp.csr_matrix) -> float:
+    """``sqrt(sum((X X^T)^2) - n)`` on (at most 2000) unit-norm rows -- the view
+    normaliser of embedding.rs:454-471.  A 2000 x 2000 Gram: host side."""
+    s = xhat @ xhat.T
+    return float(np.sqrt(float(s.multiply(s).sum()) - xhat.shape[0]))
 
-    Scope row (f)-2 of SURVEY.md section 8; the device-side view builder is not
-    in this round's build.
+
+def multi_spectral_embedding(engine: Engine, xs, selected_features, weights, n_components, random_state,
+                             *, sample_rows=None, tol=0.0, block=0, return_parts=False):
+    """Counterpart of ``internal.multi_spectral_embedding`` (embedding.rs:388-452).
+
+    Per view the device computes the IDF weights and the norms of the
+    IDF-weighted rows (``snapb200_view_norms``; embedding.rs:413-416).  The
+    Frobenius normaliser is taken over all rows when ``n <= 2000`` and over
+    2000 sampled rows otherwise (:417-421); the reference samples with Rust's
+    ``StdRng(2023)``, which cannot be reproduced outside Rust, so the sample is
+    ``sample_rows`` if given, else ``numpy.random.RandomState(2023)`` -- a
+    documented deviation.  The views are scaled by ``sqrt((w_i/norm_i)/sum)``
+    (:428-442), concatenated column-wise (:443) -- on the host -- and handed to
+    the ordinary load/prepare/eigsh path with the concatenated IDF weights as
+    feature weights and ``c_v / rho_v,i`` folded into the stored values, so the
+    stacked rows already have unit norm exactly as in ``spectral_mf`` (:447).
     """
-    raise NotImplementedError("multi_spectral: the multi-view builder is not built yet (SURVEY.md 8f, rank 2)")
+    if dist.world()[1] > 1:
+        raise NotImplementedError("multi_spectral is single-GPU in this build")
+    views, idfs, norms = [], [], []
+    for X, sel in zip(xs, selected_features):
+        if not sp.issparse(X) or X.format != "csr":
+            X = sp.csr_matrix(X)
+        mask, _ = _feature_mask(sel, X.shape[1], None)
+        engine.load_csr(X)
+        if mask is not None:
+            engine.select_features(mask)
+            X = X[:, mask]
+        idf, rho = engine.view_norms()
+        Xs = sp.csr_matrix(X, dtype=np.float64)
+        n = Xs.shape[0]
+        if n <= 2000:
+            rows = np.arange(n)
+        elif sample_rows is not None:
+            rows = np.asarray(sample_rows)
+        else:
+            rows = np.sort(np.random.RandomState(2023).choice(n, 2000, replace=False))
+        xhat_s = sp.diags(1.0 / rho[rows]) @ (Xs[rows] @ sp.diags(idf))
+        norms.append(_frobenius_offdiag(sp.csr_matrix(xhat_s)))
+        views.append((Xs, rho))
+        idfs.append(idf)
+    ws = [w / nrm for w, nrm in zip(weights, norms)]
+    w_sum = float(sum(ws))
+    scaled = [sp.diags(np.sqrt(w / w_sum) / rho) @ Xs for (Xs, rho), w in zip(views, ws)]
+    stacked = sp.csr_matrix(sp.hstack(scaled, format="csr"))
+    stacked.sort_indices()
+    fw = np.concatenate(idfs)
+    out = spectral_embedding(engine, stacked, None, n_components, random_state, fw,
+                             tol=tol, block=block, return_parts=return_parts)
+    if return_parts:
+        return out + (norms,)
+    return out
+
+
+def multi_spectral(adatas, n_comps: int = 30, features="selected", weights=None,
+                   random_state: int = 0, weighted_by_sd: bool = True, *,
+                   engine: Engine | None = None, sample_rows=None):
+    """Laplacian eigenmaps on several modalities at once -- same call as
+    ``snap.tl.multi_spectral`` (tools/_embedding.py:483-540); returns
+    ``(evals, evecs)`` and does not write into the AnnData objects."""
+    np.random.seed(random_state)                                            # :523
+    if features is None or isinstance(features, str):                       # :525-528
+        features = [features] * len(adatas)
+    if all(isinstance(f, str) for f in features):
+        features = [_resolve_features(a, f) for a, f in zip(adatas, features)]
+    if weights is None:                                                     # :530-531
+        weights = [1.0 for _ in adatas]
+    n_comps = min(min(a.n_obs for a in adatas) - 1, n_comps)
+    eng = engine if engine is not None else default_engine()
+    evals, evecs = multi_spectral_embedding(eng, [_get_csr(a) for a in adatas], features, weights,
+                                            n_comps, random_state, sample_rows=sample_rows)   # :533
+    if weighted_by_sd:                                                      # :535-538
+        idx = [i for i in range(evals.shape[0]) if evals[i] > 0]
+        evals = evals[idx]
+        evecs = evecs[:, idx] * np.sqrt(evals)
+    return evals, evecs

@@ -172,3 +172,38 @@ def test_int64_indices_and_count_dtypes(engine):
     idf, deg = engine.prepare()
     np.testing.assert_allclose(idf, z["idf"], rtol=TOL_VEC)
     np.testing.assert_allclose(deg, z["degree"], rtol=TOL_VEC)
+
+
+def _two_views(n, seed):
+    s1 = synth.make_spec(n, 6000, 250, n_clusters=10, seed=seed)
+    s2 = synth.make_spec(n, 900, 60, n_clusters=10, seed=seed)          # same planted labels (keyed by seed,row)
+    atac = synth.generate_csr(s1, dtype=np.float64)
+    rna = synth.generate_csr(s2, dtype=np.float64)
+    rng = np.random.default_rng(seed)
+    rna.data = 1.0 + rng.poisson(0.5, size=rna.nnz)                      # integer counts (values path)
+    return atac, rna
+
+
+def test_multi_spectral_matches_oracle(engine):
+    # embedding.rs:388-452; n <= 2000 so the Frobenius normaliser uses every row (no RNG involved)
+    atac, rna = _two_views(1500, 4)
+    ev_o, evec_o = oracle.multi_spectral_embedding([atac, rna], [None, None], [1.0, 1.0], 8, 0)
+    evals, evecs = tl.multi_spectral_embedding(engine, [atac, rna], [None, None], [1.0, 1.0], 8, 0)
+    _check_against(ev_o, evec_o, evals, evecs)
+    # wrapper: weights, weighted_by_sd, no write into the AnnData objects
+    a1, a2 = MiniAnnData(atac), MiniAnnData(rna)
+    ev_w, emb_w = tl.multi_spectral([a1, a2], n_comps=6, features=None, weights=[2.0, 1.0], engine=engine)
+    ev_r, emb_r = oracle.multi_spectral([a1, a2], n_comps=6, features=None, weights=[2.0, 1.0])
+    np.testing.assert_allclose(ev_w, ev_r, rtol=TOL_EVAL)
+    cos = np.abs(np.sum(emb_w * emb_r, axis=0)) / (np.linalg.norm(emb_w, axis=0) * np.linalg.norm(emb_r, axis=0))
+    assert cos.min() > MIN_COS and not a1.obsm and not a1.uns
+
+
+def test_multi_spectral_sampled_normaliser(engine):
+    # n > 2000: the 2000-row sample is passed explicitly to both sides (the reference's Rust RNG
+    # cannot be reproduced outside Rust -- SURVEY.md H8)
+    atac, rna = _two_views(2600, 9)
+    rows = np.sort(np.random.default_rng(1).choice(2600, 2000, replace=False))
+    ev_o, evec_o = oracle.multi_spectral_embedding([atac, rna], [None, None], [1.0, 1.0], 6, 0, sample_rows=rows)
+    evals, evecs = tl.multi_spectral_embedding(engine, [atac, rna], [None, None], [1.0, 1.0], 6, 0, sample_rows=rows)
+    _check_against(ev_o, evec_o, evals, evecs)
