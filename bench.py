@@ -383,7 +383,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", choices=sorted(CONFIGS), default=os.environ.get("SNAPB200_BENCH_CONFIG", "c3"))
     ap.add_argument("--block", type=int, default=0)
-    ap.add_argument("--spmm", choices=["auto", "csr", "tiled", "auto+matched", "tiled+matched"], default="auto")
+    ap.add_argument("--spmm", choices=["auto", "csr", "tiled", "auto+matched", "tiled+matched", "auto+plain", "tiled+plain"], default="auto")
     ap.add_argument("--tol", type=float, default=0.0)
     ap.add_argument("--op-iters", type=int, default=5)
     ap.add_argument("--e2e-steps", type=int, default=2)

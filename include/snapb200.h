@@ -148,10 +148,11 @@ int  snapb200_get_stats(snapb200_ctx* ctx, snapb200_stats* out);
 
 /* SpMM kernel selection: 0 = automatic (tiled for >= 2^25 stored entries and
  * b = 4 or 8), 1 = CSR gather out of L2, 2 = shared-memory tiled sliced-ELL.
- * Adding 8 selects the slower-to-build tiled entry order in which the lanes of
- * a quarter warp are additionally matched to free bank groups once some lane
- * runs out of its rotation class (fewer shared-memory bank conflicts per pass,
- * ~2x the format build time).  Takes effect at the next prepare. */
+ * The tiled entry order defaults to a padded class rotation (the lanes of a
+ * quarter warp read distinct shared-memory bank groups; ~11% padding slots).
+ * Adding 8 selects the group-matched order (no padding, ~2x slower format
+ * build), adding 16 the plain rotation without padding (most bank conflicts).
+ * Takes effect at the next prepare. */
 int  snapb200_set_spmm_mode(snapb200_ctx* ctx, int mode);
 
 /* Default Lanczos block width b (4, 8 or 16; initially 4).  prepare() builds

@@ -405,7 +405,7 @@ int snapb200_get_stats(snapb200_ctx* c, snapb200_stats* out) {
 int snapb200_set_spmm_mode(snapb200_ctx* c, int mode) {
     return guarded([&] {
         SB_CHECK(c != nullptr, "null context");
-        SB_CHECK((mode & 7) <= 2 && (mode >> 3) <= 1, "set_spmm_mode: bad mode");
+        SB_CHECK((mode & 7) <= 2 && (mode >> 3) <= 2, "set_spmm_mode: bad mode");
         c->spmm_mode = mode & 7;
         c->fill_mode = mode >> 3;
         c->prepared = false;

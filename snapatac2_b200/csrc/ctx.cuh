@@ -138,7 +138,9 @@ struct snapb200_ctx {
     // 16-byte bank group, half the shared-memory traffic per entry of b = 8; the solver needs ~1.6x the
     // operator applications but each costs half, and the SpMM runs at ~60% instead of ~35% of HBM peak.
     int block = 4;
-    int fill_mode = 0;   // tiled format entry order: 0 = per-lane class rotation, 1 = + group matching of the remainder
+    // tiled format entry order: 0 = padded class rotation (default), 1 = group-matched (no padding,
+    // slow build), 2 = plain rotation without padding (first version, most bank conflicts)
+    int fill_mode = 0;
 
     // user feature weights (host copy, optional)
     std::vector<double> user_weights;

@@ -31,7 +31,22 @@ namespace snapb {
 namespace {
 
 constexpr int kPlanThreads = 256;
-constexpr uint32_t kLenBias = 16383;   // tile_cols <= 12288 < 2^14
+constexpr uint32_t kLenBias = 32767;   // padded segment length <= 2 * tile_cols = 24576 < 2^15
+
+// Padded class rotation.  A lane with `len` entries consumes its classes in rotation for R rounds
+// (slot NC*q + ((class - o) mod NC) holds the q-th entry of a class, -1 if the class has fewer than
+// q+1 entries); entries beyond R per class go to a tail after slot NC*R in column order, and if the
+// tail is full into leftover holes of the rotation region.  R slightly below len/NC keeps ~90% of
+// the entries in the conflict-free rotation; the lane owns len + a(len) slots (~11% padding for
+// len ~ 100), a function of len alone so that the chunk plan needs no per-class statistics.
+__host__ __device__ __forceinline__ int rotation_depth(int len, int nc) {
+    const int r = (len + nc - 1) / nc - 1;
+    return r > 0 ? r : 0;
+}
+__host__ __device__ __forceinline__ int padded_slots(int len, int nc) {
+    if (rotation_depth(len, nc) == 0) return len;
+    return len + static_cast<int>(0.45f * sqrtf(static_cast<float>(nc * len))) + 1;
+}
 
 // segptr[row*(T+1) + t] = number of entries of `row` with column < t*tile_cols
 __global__ void seg_bounds_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t nrows,
@@ -56,7 +71,7 @@ __global__ void seg_bounds_kernel(const int64_t* __restrict__ ptr, const int32_t
 __global__ void __launch_bounds__(kPlanThreads)
 sell_plan_kernel(const int64_t* __restrict__ window_start, const int64_t* __restrict__ window_chunk0,
                  const int32_t* __restrict__ segptr, int n_tiles, int n_windows, int64_t chunks_per_tile,
-                 int32_t* __restrict__ chunk_rows, int32_t* __restrict__ chunk_len4) {
+                 int pad_nc, int32_t* __restrict__ chunk_rows, int32_t* __restrict__ chunk_len4) {
     __shared__ uint32_t keys[kSellWindowRows];
     const int t = blockIdx.x / n_windows, w = blockIdx.x % n_windows;
     const int64_t r0 = window_start[w];
@@ -68,7 +83,8 @@ sell_plan_kernel(const int64_t* __restrict__ window_start, const int64_t* __rest
         uint32_t key = 0xFFFFFFFFu;
         if (i < nr) {
             const int32_t* sp = segptr + (r0 + i) * (n_tiles + 1) + t;
-            const int len = sp[1] - sp[0];
+            int len = sp[1] - sp[0];
+            if (pad_nc) len = padded_slots(len, pad_nc);   // slots, not entries
             key = ((kLenBias - static_cast<uint32_t>(len)) << 13) | static_cast<uint32_t>(i);
         }
         keys[i] = key;
@@ -150,7 +166,7 @@ __device__ __forceinline__ unsigned rotl_nc(unsigned x, int r) {
 
 // Simple per-lane layout (used for chunks longer than the staging capacity):
 // class rotation while every class has entries, the rest in column order.
-template <bool HAS_VAL, int NC>
+template <bool HAS_VAL, int NC, bool PAD>
 __device__ void fill_lane_simple(const int32_t* __restrict__ idx, const float* __restrict__ val, int64_t s, int64_t e,
                                  int o, int col0, int row_bytes, int steps, int32_t* __restrict__ d,
                                  float* __restrict__ dv) {
@@ -166,9 +182,26 @@ __device__ void fill_lane_simple(const int32_t* __restrict__ idx, const float* _
         for (int u = 0; u < 8; ++u)
             if (jj[u] >= 0) cnt.add(jj[u] & (NC - 1), 1);
     }
-    const int mmin = cnt.min_all();
+    // rotation depth: padded rotation (holes written as -1) or plain (no holes: depth = min class count)
+    const int len = static_cast<int>(e - s);
+    const int R = PAD ? rotation_depth(len, NC) : cnt.min_all();
+    const int tail_cap = PAD ? padded_slots(len, NC) - NC * R : len;
+    const Packed<NC> tot = cnt;   // final class counts (hole enumeration)
+    if (PAD) {   // holes of the rotation region: classes with fewer than R entries
+#pragma unroll
+        for (int cl = 0; cl < NC; ++cl) {
+            const int x = (cl - o) & (NC - 1);
+            for (int q = tot.get(cl); q < R; ++q) {
+                const int k = NC * q + x;
+                const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
+                d[pos] = -1;
+                if (HAS_VAL) dv[pos] = 0.f;
+            }
+        }
+    }
     cnt.clear();
     int left = 0;
+    int hole_c = 0, hole_q = PAD ? tot.get(0) : 0;   // next hole (only used when the tail overflows)
     for (int64_t p = s; p < e; p += 8) {
         int jj[8];
         float vv[8];
@@ -183,48 +216,38 @@ __device__ void fill_lane_simple(const int32_t* __restrict__ idx, const float* _
             const int cl = jj[u] & (NC - 1);
             const int q = cnt.get(cl);
             cnt.add(cl, 1);
-            const int k = (q < mmin) ? NC * q + ((cl - o) & (NC - 1)) : NC * mmin + left++;
+            int k;
+            if (q < R) {
+                k = NC * q + ((cl - o) & (NC - 1));
+            } else if (left < tail_cap) {
+                k = NC * R + left++;
+            } else {   // tail full (rare): use a leftover hole of the rotation region
+                while (hole_q >= R) { ++hole_c; hole_q = tot.get(hole_c); }
+                k = NC * hole_q + ((hole_c - o) & (NC - 1));
+                ++hole_q;
+            }
             const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
             d[pos] = (jj[u] - col0) * row_bytes;
             if (HAS_VAL) dv[pos] = vv[u];
         }
     }
-    for (int k = static_cast<int>(e - s); k < steps; ++k) {
+    // everything after the lane's last tail slot up to the chunk length
+    for (int k = (len > 0 ? NC * R + left : 0); k < steps; ++k) {
         const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
         d[pos] = -1;
         if (HAS_VAL) dv[pos] = 0.f;
     }
 }
 
-// One warp per chunk.
-//  1. The 32 row segments of the chunk are loaded cooperatively (coalesced,
-//     four segments in flight) into shared memory as 16-bit tile-local columns
-//     -- per-lane walks over global memory were latency bound.
-//  2. Every lane counts its entries per bank-group class (walks over shared
-//     memory) and either
-//     simple:  places them by class rotation while all classes have entries,
-//              the remainder in column order; or
-//     matched: buckets them by class and lays the chunk out step by step: at
-//              step k lane l takes an entry of its rotation class
-//              (k + o(l)) mod NC when it has one; lanes that do not are
-//              matched, inside their group, to the classes left free by the
-//              other members of the group (greedy, lowest lane first); a lane
-//              with slack idles rather than take a conflicting class.
-constexpr int kFillWarps = 8;
-constexpr int kColPitch = 33;   // uint16 columns staged as [position][lane], padded against bank conflicts
-
-template <bool HAS_VAL, int NC, bool MATCHED, int CAP>
-__global__ void __launch_bounds__(kFillWarps * 32)
-sell_fill_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
-                 const int32_t* __restrict__ segptr, int n_tiles, int tile_cols, int row_bytes, int64_t n_chunks,
-                 int64_t chunks_per_tile, const int32_t* __restrict__ chunk_rows,
-                 const int32_t* __restrict__ chunk_len4, const int64_t* __restrict__ chunk_off,
-                 int32_t* __restrict__ data, float* __restrict__ vals) {
-    extern __shared__ __align__(16) unsigned char fill_smem[];
-    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-    const unsigned full = 0xffffffffu;
-    uint16_t* cols = reinterpret_cast<uint16_t*>(fill_smem) + static_cast<size_t>(wic) * CAP * kColPitch;
-    uint8_t* bkt = fill_smem + static_cast<size_t>(kFillWarps) * CAP * kColPitch * 2 + static_cast<size_t>(wic) * CAP * 32;
+// ---- simple order: one warp per chunk, every lane lays out its own segment ----
+template <bool HAS_VAL, int NC, bool PAD>
+__global__ void __launch_bounds__(256)
+sell_fill_simple_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
+                        const int32_t* __restrict__ segptr, int n_tiles, int tile_cols, int row_bytes, int64_t n_chunks,
+                        int64_t chunks_per_tile, const int32_t* __restrict__ chunk_rows,
+                        const int32_t* __restrict__ chunk_len4, const int64_t* __restrict__ chunk_off,
+                        int32_t* __restrict__ data, float* __restrict__ vals) {
+    const int lane = threadIdx.x & 31;
     const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
     const int o = group_member<NC>(lane);
@@ -241,10 +264,78 @@ sell_fill_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
             s = ptr[row] + sp[0];
             e = ptr[row] + sp[1];
         }
+        fill_lane_simple<HAS_VAL, NC, PAD>(idx, val, s, e, o, t * tile_cols, row_bytes, steps, d, dv);
+    }
+}
+
+// ---- matched order --------------------------------------------------------
+// One warp per chunk.
+//  1. The 32 row segments of the chunk are loaded cooperatively (coalesced,
+//     four segments in flight) into shared memory as 16-bit tile-local columns.
+//  2. Every lane buckets its entries by bank-group class (walks over shared
+//     memory).  Per-lane state is kept in ROTATED class order (slot x holds
+//     class (x + o) mod NC), so that the class a lane wants at step k, slot
+//     k mod NC, is a compile-time register index once the step loop is
+//     unrolled by NC.
+//  3. Regular rounds: while every lane of the warp still has an entry of
+//     every class, a round of NC steps is a plain rotation -- conflict free by
+//     construction, no cross-lane traffic.
+//  4. Tail: step by step, a lane takes an entry of its rotation class when it
+//     has one; the others are matched, inside their group, to the classes the
+//     group's primaries leave free (parallel proposals, lowest lane wins, a
+//     few rounds); a lane with slack idles rather than take a conflicting
+//     class, a lane without slack accepts the conflict.
+constexpr int kFillWarps = 8;
+constexpr int kColPitch = 33;   // uint16 columns staged as [position][lane], padded against bank conflicts
+
+template <int NC>
+__device__ __forceinline__ int slot_get(const int (&a)[NC], int xi) {
+    int v = a[0];
+#pragma unroll
+    for (int x = 1; x < NC; ++x)
+        if (x == xi) v = a[x];
+    return v;
+}
+template <int NC>
+__device__ __forceinline__ void slot_inc(int (&a)[NC], int xi) {
+#pragma unroll
+    for (int x = 0; x < NC; ++x)
+        if (x == xi) ++a[x];
+}
+
+template <bool HAS_VAL, int NC, int CAP>
+__global__ void __launch_bounds__(kFillWarps * 32)
+sell_fill_matched_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
+                         const int32_t* __restrict__ segptr, int n_tiles, int tile_cols, int row_bytes,
+                         int64_t n_chunks, int64_t chunks_per_tile, const int32_t* __restrict__ chunk_rows,
+                         const int32_t* __restrict__ chunk_len4, const int64_t* __restrict__ chunk_off,
+                         int32_t* __restrict__ data, float* __restrict__ vals) {
+    extern __shared__ __align__(16) unsigned char fill_smem[];
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    const unsigned full = 0xffffffffu;
+    uint16_t* cols = reinterpret_cast<uint16_t*>(fill_smem) + static_cast<size_t>(wic) * CAP * kColPitch;
+    uint8_t* bkt = fill_smem + static_cast<size_t>(kFillWarps) * CAP * kColPitch * 2 + static_cast<size_t>(wic) * CAP * 32;
+    const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    const int o = group_member<NC>(lane);
+    const unsigned gmask = (NC == 8) ? (0xFFu << (lane & ~7)) : (0x55u << ((lane & ~7) + (lane & 1)));
+    for (int64_t c = warp; c < n_chunks; c += nwarps) {
+        const int steps = chunk_len4[c] * 4;
+        if (steps == 0) continue;
+        const int row = chunk_rows[c * 32 + lane];
+        const int t = static_cast<int>(c / chunks_per_tile);
+        int32_t* d = data + chunk_off[c] * 128 + lane * 4;
+        float* dv = HAS_VAL ? vals + chunk_off[c] * 128 + lane * 4 : nullptr;
+        int64_t s = 0, e = 0;
+        if (row >= 0) {
+            const int32_t* sp = segptr + static_cast<int64_t>(row) * (n_tiles + 1) + t;
+            s = ptr[row] + sp[0];
+            e = ptr[row] + sp[1];
+        }
         const int col0 = t * tile_cols;
         const int len = static_cast<int>(e - s);
-        if (!MATCHED || steps > CAP) {   // warp-uniform: simple order, or a chunk too long to stage
-            fill_lane_simple<HAS_VAL, NC>(idx, val, s, e, o, col0, row_bytes, steps, d, dv);
+        if (steps > CAP) {   // warp-uniform; rare (very long segments): simple order straight from global memory
+            fill_lane_simple<HAS_VAL, NC, false>(idx, val, s, e, o, col0, row_bytes, steps, d, dv);
             continue;
         }
         // ---- 1. cooperative staging of the chunk's columns
@@ -268,75 +359,122 @@ sell_fill_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
             }
         }
         __syncwarp();
-        // ---- 2. per-lane class counts (walk over shared memory)
-        Packed<NC> cnt;
-        cnt.clear();
-        for (int q = 0; q < len; ++q) cnt.add(cols[q * kColPitch + lane] & (NC - 1), 1);
-
-        // ---- matched: bucket the lane's positions by class
-        Packed<NC> ofs, hd;
-        ofs.clear();
-        unsigned avail = 0;
+        // ---- 2. bucket by class; state in rotated slot order (slot x <-> class (x + o) mod NC)
+        int cnt[NC], head[NC];
+#pragma unroll
+        for (int x = 0; x < NC; ++x) cnt[x] = 0;
+        for (int q = 0; q < len; ++q) slot_inc<NC>(cnt, (static_cast<int>(cols[q * kColPitch + lane]) - o) & (NC - 1));
+        int mmin = cnt[0];
         {
             int run = 0;
 #pragma unroll
-            for (int cl = 0; cl < NC; ++cl) {
-                const int n_cl = cnt.get(cl);
-                ofs.add(cl, run);
-                run += n_cl;
-                if (n_cl > 0) avail |= 1u << cl;
+            for (int x = 0; x < NC; ++x) {
+                head[x] = run;          // bucket start of slot x
+                run += cnt[x];
+                mmin = min(mmin, cnt[x]);
             }
         }
-        hd.clear();
-        for (int q = 0; q < len; ++q) {
-            const int cl = cols[q * kColPitch + lane] & (NC - 1);
-            bkt[(ofs.get(cl) + hd.get(cl)) * 32 + lane] = static_cast<uint8_t>(q);
-            hd.add(cl, 1);
+        {
+            int fillp[NC];
+#pragma unroll
+            for (int x = 0; x < NC; ++x) fillp[x] = head[x];
+            for (int q = 0; q < len; ++q) {
+                const int xi = (static_cast<int>(cols[q * kColPitch + lane]) - o) & (NC - 1);
+                bkt[slot_get<NC>(fillp, xi) * 32 + lane] = static_cast<uint8_t>(q);
+                slot_inc<NC>(fillp, xi);
+            }
         }
-        hd.clear();
+        int endp[NC];
+#pragma unroll
+        for (int x = 0; x < NC; ++x) endp[x] = head[x] + cnt[x];
+        // ---- 3. regular rounds (every lane that has entries still has one of every class)
+        const int rreg = __reduce_min_sync(full, len > 0 ? mmin : 0x7fffffff);
+        const int n_reg = (rreg == 0x7fffffff) ? 0 : rreg;
+        for (int r = 0; r < n_reg; ++r) {
+#pragma unroll
+            for (int x = 0; x < NC; ++x) {
+                const int k = NC * r + x;
+                int out = -1;
+                float outv = 0.f;
+                if (len > 0) {
+                    const int rel = bkt[(head[x] + r) * 32 + lane];
+                    out = static_cast<int>(cols[rel * kColPitch + lane]) * row_bytes;
+                    if (HAS_VAL) outv = val[s + rel];
+                }
+                const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
+                d[pos] = out;
+                if (HAS_VAL) dv[pos] = outv;
+            }
+        }
         int total = len;
-        // ---- step by step layout
-        for (int k = 0; k < steps; ++k) {
-            const int dcls = (k + o) & (NC - 1);
-            const bool has = total > 0;
-            const bool primary = has && ((avail >> dcls) & 1u);
-            int cls = primary ? dcls : -1;
-            const unsigned np = __ballot_sync(full, !primary);
-            const unsigned holes = __ballot_sync(full, has && !primary);
-            if (holes) {
-                unsigned freec = rotl_nc<NC>(group_bits<NC>(np, lane), k & (NC - 1));
-                unsigned pend = group_bits<NC>(holes, lane);
-                while (__any_sync(full, pend != 0)) {
-                    const int mem = pend ? (__ffs(pend) - 1) : 0;
-                    const int src = group_lane<NC>(lane, mem);
-                    int chosen_free = -1;
-                    if (pend && lane == src) {
-                        const unsigned usable = freec & avail;
-                        if (usable) { cls = __ffs(usable) - 1; chosen_free = cls; }
-                        else if (total >= steps - k) cls = __ffs(avail) - 1;   // no slack left: accept a conflict
-                        // otherwise idle this step (the lane is shorter than the chunk, it can wait)
-                    }
-                    const int cf = __shfl_sync(full, chosen_free, src);
-                    if (pend) {
-                        if (cf >= 0) freec &= ~(1u << cf);
-                        pend &= pend - 1;
+        unsigned avail = 0;   // bit x: slot x still has entries
+        if (len > 0) {
+            total = len - NC * n_reg;
+#pragma unroll
+            for (int x = 0; x < NC; ++x) {
+                head[x] += n_reg;
+                if (head[x] < endp[x]) avail |= 1u << x;
+            }
+        }
+        // ---- 4. matched tail; k0 is a multiple of NC so slot (k mod NC) is the compile-time x
+        for (int k0 = NC * n_reg; k0 < steps; k0 += NC) {
+#pragma unroll
+            for (int x = 0; x < NC; ++x) {
+                const int k = k0 + x;
+                if (k >= steps) break;   // warp-uniform
+                const bool has = total > 0;
+                const bool primary = has && ((avail >> x) & 1u);
+                int slot = primary ? x : -1;
+                const unsigned np = __ballot_sync(full, !primary);
+                const unsigned holes = __ballot_sync(full, has && !primary);
+                if (holes) {
+                    // classes of the group not used by a primary this step.  Member i wants class
+                    // (k + i) mod NC; in MY slot numbering class c is slot (c - o) mod NC, so the free
+                    // slots are the group's non-primary member bits rotated by (member - o) = 0: bit i of
+                    // group_bits(np) frees class (k + i), i.e. my slot (x + i - o) mod NC.
+                    const unsigned gb = group_bits<NC>(np, lane);
+                    unsigned freeslots = rotl_nc<NC>(gb, (x - o) & (NC - 1));
+                    bool pending = has && !primary;
+                    while (__any_sync(full, pending)) {
+                        int want = -1;
+                        if (pending) {
+                            const unsigned usable = freeslots & avail;
+                            if (usable) {
+                                want = __ffs(usable) - 1;
+                            } else {
+                                if (total >= steps - k) slot = __ffs(avail) - 1;   // no slack: accept a conflict
+                                pending = false;                                     // else idle this step
+                            }
+                        }
+                        // the class behind my slot `want`, as a group-wide key: lowest lane per class wins
+                        const int want_cls = (want + o) & (NC - 1);
+                        const unsigned key = (want >= 0) ? static_cast<unsigned>((lane >> 3) * 64 + (NC == 4 ? (lane & 1) * 16 : 0) + want_cls)
+                                                         : (0x1000u + static_cast<unsigned>(lane));
+                        const unsigned same = __match_any_sync(full, key);
+                        const bool win = pending && want >= 0 && (lane == __ffs(same) - 1);
+                        if (win) { slot = want; pending = false; }
+                        const unsigned wcls = win ? (1u << want_cls) : 0u;
+                        const unsigned taken_cls = __reduce_or_sync(gmask, wcls);
+                        // back to my slot numbering: class c -> slot (c - o) mod NC  (rotate right by o)
+                        freeslots &= ~rotl_nc<NC>(taken_cls, (NC - o) & (NC - 1));
                     }
                 }
+                int out = -1;
+                float outv = 0.f;
+                if (slot >= 0) {
+                    const int h = (slot == x) ? head[x] : slot_get<NC>(head, slot);
+                    const int rel = bkt[h * 32 + lane];
+                    if (slot == x) ++head[x]; else slot_inc<NC>(head, slot);
+                    const int en = (slot == x) ? endp[x] : slot_get<NC>(endp, slot);
+                    if (h + 1 == en) avail &= ~(1u << slot);
+                    --total;
+                    out = static_cast<int>(cols[rel * kColPitch + lane]) * row_bytes;
+                    if (HAS_VAL) outv = val[s + rel];
+                }
+                const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
+                d[pos] = out;
+                if (HAS_VAL) dv[pos] = outv;
             }
-            int out = -1;
-            float outv = 0.f;
-            if (cls >= 0) {
-                const int h = hd.get(cls);
-                const int rel = bkt[(ofs.get(cls) + h) * 32 + lane];
-                hd.add(cls, 1);
-                if (h + 1 == cnt.get(cls)) avail &= ~(1u << cls);
-                --total;
-                out = static_cast<int>(cols[rel * kColPitch + lane]) * row_bytes;
-                if (HAS_VAL) outv = val[s + rel];
-            }
-            const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
-            d[pos] = out;
-            if (HAS_VAL) dv[pos] = outv;
         }
     }
 }
@@ -371,6 +509,8 @@ void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b) {
     const int64_t n_chunks = S.n_chunks;
 
     // ---- per-row tile boundaries
+    const int pad_mode = (c->fill_mode == 0) ? 1 : 0;   // 0: padded rotation (default), 1: matched, 2: plain
+    const int nc = (b == 8) ? 4 : 8;
     DevBuf<int32_t> segptr;
     const int64_t nseg = R * (T + 1);
     segptr.alloc(std::max<int64_t>(1, nseg));
@@ -385,7 +525,8 @@ void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b) {
     S.chunk_off.alloc(n_chunks + 1);
     if (n_chunks > 0) {
         sell_plan_kernel<<<static_cast<unsigned>(static_cast<int64_t>(T) * nw), kPlanThreads, 0, st>>>(
-            S.window_start.p, S.window_chunk0.p, segptr.p, T, nw, S.chunks_per_tile, S.chunk_rows.p, S.chunk_len4.p);
+            S.window_start.p, S.window_chunk0.p, segptr.p, T, nw, S.chunks_per_tile, pad_mode ? nc : 0, S.chunk_rows.p,
+            S.chunk_len4.p);
         SB_LAUNCH_CHECK();
     }
     exclusive_scan_i32_to_i64(c, S.chunk_len4.p, S.chunk_off.p, n_chunks);
@@ -400,27 +541,30 @@ void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b) {
     if (n_chunks > 0 && S.n_entries > 0) {
         const bool matched = c->fill_mode == 1;
         const int rb = 4 * b;
-        // staging capacity (steps): segments average ~nnz_row/tiles; longer chunks take the slow path
-#define SB_FILL(HV, NC, MT, CAP)                                                                                      \
+#define SB_FILL_ARGS                                                                                                   \
+    M.ptr.p, M.idx.p, M.val.p, segptr.p, T, S.tile_cols, rb, n_chunks, S.chunks_per_tile, S.chunk_rows.p,             \
+        S.chunk_len4.p, S.chunk_off.p, S.data.p, S.vals.p
+#define SB_FILL(HV, NC, CAP)                                                                                           \
     do {                                                                                                               \
-        const size_t fsm = MT ? static_cast<size_t>(kFillWarps) * CAP * (kColPitch * 2 + 32) : 0;                      \
-        auto kern = sell_fill_kernel<HV, NC, MT, CAP>;                                                                 \
-        SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));       \
-        const int per_sm = MT ? std::max<int>(1, static_cast<int>((220u << 10) / fsm)) : 8;                            \
-        const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_chunks, kFillWarps),                          \
-                                                              static_cast<int64_t>(c->num_sms) * per_sm));             \
-        kern<<<blocks, kFillWarps * 32, fsm, st>>>(M.ptr.p, M.idx.p, M.val.p, segptr.p, T, S.tile_cols, rb, n_chunks, \
-                                                   S.chunks_per_tile, S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p,  \
-                                                   S.data.p, S.vals.p);                                                \
+        if (matched) {                                                                                                 \
+            const size_t fsm = static_cast<size_t>(kFillWarps) * CAP * (kColPitch * 2 + 32);                           \
+            auto kern = sell_fill_matched_kernel<HV, NC, CAP>;                                                         \
+            SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));   \
+            const int per_sm = std::max<int>(1, static_cast<int>((220u << 10) / fsm));                                 \
+            const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_chunks, kFillWarps),                      \
+                                                                  static_cast<int64_t>(c->num_sms) * per_sm));         \
+            kern<<<blocks, kFillWarps * 32, fsm, st>>>(SB_FILL_ARGS);                                                  \
+        } else {                                                                                                       \
+            const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_chunks, 8),                               \
+                                                                  static_cast<int64_t>(c->num_sms) * 8));              \
+            if (pad_mode) sell_fill_simple_kernel<HV, NC, true><<<blocks, 256, 0, st>>>(SB_FILL_ARGS);                 \
+            else          sell_fill_simple_kernel<HV, NC, false><<<blocks, 256, 0, st>>>(SB_FILL_ARGS);                \
+        }                                                                                                              \
     } while (0)
         const bool hv = M.has_values();
-        if (b == 8) {
-            if (hv) { if (matched) SB_FILL(true, 4, true, 128); else SB_FILL(true, 4, false, 128); }
-            else    { if (matched) SB_FILL(false, 4, true, 128); else SB_FILL(false, 4, false, 128); }
-        } else {
-            if (hv) { if (matched) SB_FILL(true, 8, true, 256); else SB_FILL(true, 8, false, 256); }
-            else    { if (matched) SB_FILL(false, 8, true, 256); else SB_FILL(false, 8, false, 256); }
-        }
+        if (b == 8) { if (hv) SB_FILL(true, 4, 128); else SB_FILL(false, 4, 128); }
+        else        { if (hv) SB_FILL(true, 8, 256); else SB_FILL(false, 8, 256); }
+#undef SB_FILL_ARGS
 #undef SB_FILL
         SB_LAUNCH_CHECK();
     }
