@@ -236,6 +236,9 @@ int snapb200_create(int device, snapb200_ctx** out) {
         c->device = device;
         c->num_sms = prop.multiProcessorCount;
         SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        SB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+        SB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        SB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         SB_CUDA(cudaEventCreate(&c->ev0));
         SB_CUDA(cudaEventCreate(&c->ev1));
         *out = c;
@@ -247,12 +250,16 @@ int snapb200_destroy(snapb200_ctx* c) {
         if (!c) return;
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
+        if (c->stream2) cudaStreamSynchronize(c->stream2);
         comm_destroy(c);
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
-        cudaStream_t st = c->stream;
+        if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+        if (c->ev_join) cudaEventDestroy(c->ev_join);
+        cudaStream_t st = c->stream, st2 = c->stream2;
         delete c;
         if (st) cudaStreamDestroy(st);
+        if (st2) cudaStreamDestroy(st2);
     });
 }
 

@@ -118,7 +118,9 @@ struct Comm;  // NCCL wrapper (comm.cu)
 // The public opaque type.
 struct snapb200_ctx {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;    // the context's stream: every call is ordered on it
+    cudaStream_t stream2 = nullptr;   // helper stream: independent prepare phases overlap with the transpose
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int num_sms = snapb::kNumSMsB200;
 
     // multi-GPU

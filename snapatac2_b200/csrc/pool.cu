@@ -3,10 +3,10 @@
 // cudaFree synchronises the whole device and cudaMalloc of multi-GB blocks is
 // slow; a spectral() call allocates and releases dozens of temporaries (and
 // bench.py repeats the call), so freed blocks are parked here and handed out
-// again.  Reuse is stream ordered: all work of a context runs on one stream,
-// so a block freed while kernels still read it can be given to the next user
-// on the same stream safely; if a block migrates to a different stream, the
-// previous owner's stream is drained first.  On out-of-memory every parked
+// again.  Reuse is stream ordered: a block freed while kernels still read it
+// can be given to the next user on the same stream safely; every parked block
+// carries an event recorded on its last stream, and a user on a different
+// stream is ordered after that event (cudaStreamWaitEvent, no host stall).  On out-of-memory every parked
 // block is returned to the driver and the allocation retried.
 #include "common.cuh"
 
@@ -22,7 +22,8 @@ namespace {
 
 struct Parked {
     void* p;
-    cudaStream_t stream;
+    cudaStream_t stream;   // stream the block was last used on
+    cudaEvent_t ev;        // recorded on `stream` when the block was parked
 };
 struct Pool {
     std::mutex mu;
@@ -52,7 +53,10 @@ size_t round_size(size_t b) {
 void trim_locked(Pool& P, int dev) {
     auto it = P.parked.find(dev);
     if (it == P.parked.end()) return;
-    for (auto& kv : it->second) cudaFree(kv.second.p);
+    for (auto& kv : it->second) {
+        if (kv.second.ev) cudaEventDestroy(kv.second.ev);
+        cudaFree(kv.second.p);
+    }
     it->second.clear();
 }
 
@@ -73,7 +77,14 @@ void* pool_alloc(size_t bytes) {
         Parked blk = it->second;
         const size_t sz = it->first;
         bins.erase(it);
-        if (blk.stream != t_stream && blk.stream != nullptr) cudaStreamSynchronize(blk.stream);
+        if (blk.ev) {
+            // a block parked by another stream may still be read there: order the new user after it
+            if (blk.stream != t_stream) {
+                if (t_stream) cudaStreamWaitEvent(t_stream, blk.ev, 0);
+                else cudaEventSynchronize(blk.ev);
+            }
+            cudaEventDestroy(blk.ev);
+        }
         P.live[blk.p] = sz;
         ++g_reuses;
         return blk.p;
@@ -112,7 +123,9 @@ void pool_free(void* p) {
     P.live.erase(it);
     int dev = 0;
     cudaGetDevice(&dev);
-    P.parked[dev].emplace(sz, Parked{p, t_stream});
+    cudaEvent_t ev = nullptr;
+    if (t_stream && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(ev, t_stream);
+    P.parked[dev].emplace(sz, Parked{p, t_stream, ev});
 }
 
 void pool_counters(long long* mallocs, long long* reuses, long long* trims, double* ms) {

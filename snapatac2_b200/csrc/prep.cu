@@ -334,7 +334,15 @@ void select_features(snapb200_ctx* c, const uint8_t* keep_host, int64_t m) {
 
 // --------------------------------------------------------------------------
 // Builds c->Xt and leaves the local column counts in `cnt_out` (m int32).
-static void build_transpose_impl(snapb200_ctx* c, DevBuf<int32_t>& cnt) {
+// Temporaries of the transpose that must outlive its (asynchronous) slab loop.
+struct TransposeState {
+    DevBuf<int64_t> cursor;
+    DevBuf<uint32_t> bm;
+    int64_t S = 0;
+};
+
+// Part 1: local column counts (left in `cnt`), row pointers of Xt, output allocation.
+static void transpose_begin(snapb200_ctx* c, DevBuf<int32_t>& cnt, TransposeState& ts) {
     Csr& X = c->X;
     Csr& T = c->Xt;
     const int64_t m = c->m, n = X.nrows, nnz = X.nnz;
@@ -353,38 +361,45 @@ static void build_transpose_impl(snapb200_ctx* c, DevBuf<int32_t>& cnt) {
     exclusive_scan_i32_to_i64(c, cnt.p, T.ptr.p, m);
     T.idx.alloc(std::max<int64_t>(1, nnz));
     if (X.has_values()) T.val.alloc(std::max<int64_t>(1, nnz)); else T.val.release();
+    ts.S = 0;
     if (nnz == 0 || n == 0) return;
-
-    DevBuf<int64_t> cursor;
-    cursor.alloc(m);
-    SB_CUDA(cudaMemcpyAsync(cursor.p, T.ptr.p, sizeof(int64_t) * m, cudaMemcpyDeviceToDevice, c->stream));
-
-    // slab height: bitmap of m x S bits kept around 64 MB
+    ts.cursor.alloc(m);
+    SB_CUDA(cudaMemcpyAsync(ts.cursor.p, T.ptr.p, sizeof(int64_t) * m, cudaMemcpyDeviceToDevice, c->stream));
+    // slab height: bitmap of m x S bits kept around 64 MB (L2 resident)
     int64_t S = ((512ll << 20) / std::max<int64_t>(m, 1)) / 32 * 32;
     S = std::max<int64_t>(32, std::min<int64_t>(S, 8192));
     S = std::min<int64_t>(S, ceil_div(n, 32) * 32);
-    const int planes = static_cast<int>(S / 32);
-    DevBuf<uint32_t> bm;
-    bm.alloc(static_cast<int64_t>(planes) * m);
+    ts.S = S;
+    ts.bm.alloc((S / 32) * m);
     // cleared once; the emit kernel zeroes every word it consumes
-    SB_CUDA(cudaMemsetAsync(bm.p, 0, sizeof(uint32_t) * static_cast<size_t>(planes) * m, c->stream));
+    SB_CUDA(cudaMemsetAsync(ts.bm.p, 0, sizeof(uint32_t) * static_cast<size_t>(S / 32) * m, c->stream));
+}
+
+// Part 2: the slab loop, enqueued on the context's stream without waiting for it.
+static void transpose_enqueue(snapb200_ctx* c, TransposeState& ts) {
+    if (ts.S == 0) return;
+    Csr& X = c->X;
+    Csr& T = c->Xt;
+    const int64_t m = c->m, n = X.nrows, S = ts.S;
     for (int64_t r0 = 0; r0 < n; r0 += S) {
         int64_t r1 = std::min<int64_t>(n, r0 + S);
         int g = grid_for_rows(c, (r1 - r0) * 8);   // 8 warps per row (kSetSplit)
-        bitmap_set_kernel<<<g, 256, 0, c->stream>>>(X.ptr.p, X.idx.p, r0, r1, m, bm.p);
+        bitmap_set_kernel<<<g, 256, 0, c->stream>>>(X.ptr.p, X.idx.p, r0, r1, m, ts.bm.p);
         SB_LAUNCH_CHECK();
         int pl = static_cast<int>(ceil_div(r1 - r0, 32));
-        bitmap_emit_kernel<<<grid1d(m), 256, 0, c->stream>>>(bm.p, m, pl, r0, cursor.p, T.idx.p, X.ptr.p, X.idx.p,
-                                                            X.val.p, T.val.p);
+        bitmap_emit_kernel<<<grid1d(m), 256, 0, c->stream>>>(ts.bm.p, m, pl, r0, ts.cursor.p, T.idx.p, X.ptr.p,
+                                                            X.idx.p, X.val.p, T.val.p);
         SB_LAUNCH_CHECK();
         count_launch(c, 2);
     }
-    SB_CUDA(cudaStreamSynchronize(c->stream));
 }
 
 void build_transpose(snapb200_ctx* c) {
     DevBuf<int32_t> cnt;
-    build_transpose_impl(c, cnt);
+    TransposeState ts;
+    transpose_begin(c, cnt, ts);
+    transpose_enqueue(c, ts);
+    SB_CUDA(cudaStreamSynchronize(c->stream));
 }
 
 // --------------------------------------------------------------------------
@@ -396,50 +411,82 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     cudaStream_t st = c->stream;
     const auto wall0 = std::chrono::steady_clock::now();
 
-    // ---- feature-major copy + local document frequencies
+    // ---- local document frequencies, row pointers of the feature-major copy (main stream)
     SB_CUDA(cudaEventRecord(c->ev0, st));
     DevBuf<int32_t> cnt;
-    build_transpose_impl(c, cnt);
-    c->stats.ms_transpose = elapsed_ms(c);
-
-    SB_CUDA(cudaEventRecord(c->ev0, st));
-    // ---- weights
+    TransposeState ts;
+    transpose_begin(c, cnt, ts);
     c->w.alloc(m);
+    DevBuf<int64_t> df, mm;
     if (!c->user_weights.empty()) {
         SB_CHECK(static_cast<int64_t>(c->user_weights.size()) == m,
                  "feature_weights length must equal the number of selected features");
         SB_CUDA(cudaMemcpyAsync(c->w.p, c->user_weights.data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
     } else {
-        DevBuf<int64_t> df, mm;
         df.alloc(m);
         mm.alloc(2);
         i32_to_i64_kernel<<<grid1d(m), 256, 0, st>>>(cnt.p, df.p, m);
         SB_LAUNCH_CHECK();
-        allreduce_i64(c, df.p, m);
-        df_minmax_kernel<<<1, 256, 0, st>>>(df.p, m, mm.p);
-        SB_LAUNCH_CHECK();
-        idf_kernel<<<grid1d(m), 256, 0, st>>>(df.p, mm.p, m, static_cast<double>(c->n_global), c->w.p);
-        SB_LAUNCH_CHECK();
-        count_launch(c, 3);
-        SB_CUDA(cudaStreamSynchronize(st));
+        allreduce_i64(c, df.p, m);   // every NCCL call stays on the main stream
+        count_launch(c);
     }
-    cnt.release();
-
-    // ---- row norms rho_i = || w .* x_i ||                       (:315-326)
     c->rho.alloc(std::max<int64_t>(1, n));
     c->degree.alloc(std::max<int64_t>(1, n));
     c->csum.alloc(m);
     DevBuf<double> rinv, wc;
     rinv.alloc(std::max<int64_t>(1, n));
     wc.alloc(m);
-    if (n > 0) {
-        spmv_f64_kernel<0><<<grid_for_rows(c, n), 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, c->w.p, nullptr, 0.0, n,
-                                                               c->rho.p);
-        SB_LAUNCH_CHECK();
-        recip_kernel<<<grid1d(n), 256, 0, st>>>(c->rho.p, rinv.p, n);
-        SB_LAUNCH_CHECK();
-        count_launch(c, 2);
+    c->S1.clear();
+    c->S2.clear();
+    c->stats.ms_format = 0.0;
+    SB_CUDA(cudaEventRecord(c->ev_fork, st));
+
+    // ---- main stream: the transpose slab loop (~2 launches per 1024 rows), enqueued asynchronously
+    transpose_enqueue(c, ts);
+    SB_CUDA(cudaEventRecord(c->ev1, st));   // end of the transpose on the main stream's timeline
+
+    // ---- helper stream, concurrently: IDF weights, row norms, the cell-major tiled copy.  These
+    //      need X and the document frequencies only; they overlap with the atomics-bound transpose.
+    const auto wall_fork = std::chrono::steady_clock::now();
+    {
+        cudaStream_t aux = c->stream2;
+        SB_CUDA(cudaStreamWaitEvent(aux, c->ev_fork, 0));
+        c->stream = aux;
+        pool_set_stream(aux);
+        try {
+            if (c->user_weights.empty()) {
+                df_minmax_kernel<<<1, 256, 0, aux>>>(df.p, m, mm.p);
+                SB_LAUNCH_CHECK();
+                idf_kernel<<<grid1d(m), 256, 0, aux>>>(df.p, mm.p, m, static_cast<double>(c->n_global), c->w.p);
+                SB_LAUNCH_CHECK();
+                count_launch(c, 2);
+            }
+            // row norms rho_i = || w .* x_i ||                       (:315-326)
+            if (n > 0) {
+                spmv_f64_kernel<0><<<grid_for_rows(c, n), 256, 0, aux>>>(X.ptr.p, X.idx.p, X.val.p, c->w.p, nullptr, 0.0,
+                                                                        n, c->rho.p);
+                SB_LAUNCH_CHECK();
+                recip_kernel<<<grid1d(n), 256, 0, aux>>>(c->rho.p, rinv.p, n);
+                SB_LAUNCH_CHECK();
+                count_launch(c, 2);
+            }
+            if (use_tiled(c, c->block)) sell_build(c, c->X, c->S2, c->block);
+            SB_CUDA(cudaEventRecord(c->ev_join, aux));
+        } catch (...) {
+            c->stream = st;
+            pool_set_stream(st);
+            cudaStreamSynchronize(aux);
+            cudaStreamSynchronize(st);
+            throw;
+        }
+        c->stream = st;
+        pool_set_stream(st);
+        SB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
     }
+    const double ms_aux_host =
+        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall_fork).count();
+    cnt.release();
+
     // ---- column sums c_j = w_j sum_i x_ij / rho_i               (:139-144)
     spmv_f64_kernel<1><<<grid_for_rows(c, m), 256, 0, st>>>(c->Xt.ptr.p, c->Xt.idx.p, c->Xt.val.p, rinv.p, c->w.p,
                                                            0.0, m, c->csum.p);
@@ -505,15 +552,22 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     SB_LAUNCH_CHECK();
     count_launch(c, 2);
     SB_CUDA(cudaStreamSynchronize(st));
-    c->stats.ms_prepare = elapsed_ms(c);
-
-    // ---- shared-memory tiled copies for the SpMM (large problems, b = 8)
-    c->S1.clear();
-    c->S2.clear();
-    c->stats.ms_format = 0.0;
-    if (use_tiled(c, c->block)) ensure_tiled(c, c->block);
+    // ---- feature-major tiled copy (needs Xt)
+    const auto wall_s1 = std::chrono::steady_clock::now();
+    if (use_tiled(c, c->block)) {
+        sell_build(c, c->Xt, c->S1, c->block);
+        SB_CUDA(cudaStreamSynchronize(st));
+    }
+    const double ms_s1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall_s1).count();
+    {
+        float ms_t = 0.f;
+        cudaEventElapsedTime(&ms_t, c->ev0, c->ev1);   // counts + slab loop as seen on the main stream
+        c->stats.ms_transpose = ms_t;
+    }
+    c->stats.ms_format = ms_aux_host + ms_s1;   // host view: helper-stream phase (overlaps the transpose) + S1 build
     c->stats.ms_prepare_wall =
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    c->stats.ms_prepare = c->stats.ms_prepare_wall - c->stats.ms_transpose - ms_s1;   // the rest (overlap aside)
     c->prepared = true;
 }
 
