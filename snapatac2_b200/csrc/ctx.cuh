@@ -213,6 +213,10 @@ void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b);
 // through the tiled copy (b = S.b); `in` and `out` are packed (leading dimension b).
 void sell_spmm(snapb200_ctx* c, const Sell& S, const float* in, float* out, const float* scale,
                const float* subscale, const float* sub, int64_t lds);
+// fp64 SpMV through the tiled copy (prepare): mode 0: out[row] = sqrt(sum_j v_ij^2 x[j]);
+// mode 1: out[row] = scale[row] * sum_j v_ij x[j] + shift  (v = 1 without values, scale may be null)
+void sell_spmv64(snapb200_ctx* c, const Sell& S, const double* x, int mode, const double* scale, double shift,
+                 double* out);
 bool use_tiled(const snapb200_ctx* c, int b);
 // (re)build S1/S2 for block width b if they are missing or sized for another width
 void ensure_tiled(snapb200_ctx* c, int b);

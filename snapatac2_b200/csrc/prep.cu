@@ -228,6 +228,10 @@ __global__ void recip_kernel(const double* __restrict__ in, double* __restrict__
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = 1.0 / in[i];
 }
+__global__ void sqr_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t n) {
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] * in[i];
+}
 __global__ void mul_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int64_t n) {
     int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] * b[i];
@@ -434,8 +438,9 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     c->degree.alloc(std::max<int64_t>(1, n));
     c->csum.alloc(m);
     DevBuf<double> rinv, wc;
-    rinv.alloc(std::max<int64_t>(1, n));
-    wc.alloc(m);
+    rinv.alloc(n + 2);   // (+2: the tiled fp64 SpMV stages whole 16-byte units)
+    wc.alloc(m + 2);
+    const bool tiled = use_tiled(c, c->block);
     c->S1.clear();
     c->S2.clear();
     c->stats.ms_format = 0.0;
@@ -461,16 +466,26 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
                 SB_LAUNCH_CHECK();
                 count_launch(c, 2);
             }
-            // row norms rho_i = || w .* x_i ||                       (:315-326)
-            if (n > 0) {
+            // cell-major tiled copy, then row norms rho_i = || w .* x_i ||   (:315-326)
+            if (tiled) {
+                sell_build(c, c->X, c->S2, c->block);
+                if (n > 0) {
+                    sqr_kernel<<<grid1d(m), 256, 0, aux>>>(c->w.p, wc.p, m);   // wc is free until the degrees
+                    SB_LAUNCH_CHECK();
+                    sell_spmv64(c, c->S2, wc.p, 0, nullptr, 0.0, c->rho.p);
+                    count_launch(c);
+                }
+            } else if (n > 0) {
                 spmv_f64_kernel<0><<<grid_for_rows(c, n), 256, 0, aux>>>(X.ptr.p, X.idx.p, X.val.p, c->w.p, nullptr, 0.0,
                                                                         n, c->rho.p);
                 SB_LAUNCH_CHECK();
+                count_launch(c);
+            }
+            if (n > 0) {
                 recip_kernel<<<grid1d(n), 256, 0, aux>>>(c->rho.p, rinv.p, n);
                 SB_LAUNCH_CHECK();
-                count_launch(c, 2);
+                count_launch(c);
             }
-            if (use_tiled(c, c->block)) sell_build(c, c->X, c->S2, c->block);
             SB_CUDA(cudaEventRecord(c->ev_join, aux));
         } catch (...) {
             c->stream = st;
@@ -487,20 +502,36 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall_fork).count();
     cnt.release();
 
+    // ---- feature-major tiled copy (needs Xt)
+    const auto wall_s1 = std::chrono::steady_clock::now();
+    if (tiled) {
+        sell_build(c, c->Xt, c->S1, c->block);
+        SB_CUDA(cudaStreamSynchronize(st));
+    }
+    const double ms_s1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall_s1).count();
     // ---- column sums c_j = w_j sum_i x_ij / rho_i               (:139-144)
-    spmv_f64_kernel<1><<<grid_for_rows(c, m), 256, 0, st>>>(c->Xt.ptr.p, c->Xt.idx.p, c->Xt.val.p, rinv.p, c->w.p,
-                                                           0.0, m, c->csum.p);
-    SB_LAUNCH_CHECK();
+    if (tiled) {
+        sell_spmv64(c, c->S1, rinv.p, 1, c->w.p, 0.0, c->csum.p);
+    } else {
+        spmv_f64_kernel<1><<<grid_for_rows(c, m), 256, 0, st>>>(c->Xt.ptr.p, c->Xt.idx.p, c->Xt.val.p, rinv.p, c->w.p,
+                                                               0.0, m, c->csum.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
     allreduce_f64(c, c->csum.p, m);
     mul_kernel<<<grid1d(m), 256, 0, st>>>(c->w.p, c->csum.p, wc.p, m);
     SB_LAUNCH_CHECK();
-    count_launch(c, 2);
+    count_launch(c);
     // ---- degrees d_i = (1/rho_i) sum_j x_ij w_j c_j - 1         (:145-146)
     if (n > 0) {
-        spmv_f64_kernel<1><<<grid_for_rows(c, n), 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, wc.p, rinv.p, -1.0, n,
-                                                               c->degree.p);
-        SB_LAUNCH_CHECK();
-        count_launch(c);
+        if (tiled) {
+            sell_spmv64(c, c->S2, wc.p, 1, rinv.p, -1.0, c->degree.p);
+        } else {
+            spmv_f64_kernel<1><<<grid_for_rows(c, n), 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, wc.p, rinv.p, -1.0, n,
+                                                                   c->degree.p);
+            SB_LAUNCH_CHECK();
+            count_launch(c);
+        }
     }
     // ---- global sum of degrees, degenerate-row check
     const int nb = 256;
@@ -552,13 +583,6 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     SB_LAUNCH_CHECK();
     count_launch(c, 2);
     SB_CUDA(cudaStreamSynchronize(st));
-    // ---- feature-major tiled copy (needs Xt)
-    const auto wall_s1 = std::chrono::steady_clock::now();
-    if (use_tiled(c, c->block)) {
-        sell_build(c, c->Xt, c->S1, c->block);
-        SB_CUDA(cudaStreamSynchronize(st));
-    }
-    const double ms_s1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall_s1).count();
     {
         float ms_t = 0.f;
         cudaEventElapsedTime(&ms_t, c->ev0, c->ev1);   // counts + slab loop as seen on the main stream

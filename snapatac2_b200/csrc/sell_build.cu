@@ -47,6 +47,17 @@ __host__ __device__ __forceinline__ int padded_slots(int len, int nc) {
     if (rotation_depth(len, nc) == 0) return len;
     return len + static_cast<int>(0.45f * sqrtf(static_cast<float>(nc * len))) + 1;
 }
+// A lane lays its segment out in pieces of kPiece entries, each with its own rotation, so that the
+// fill kernel can stage one piece window of every lane of a chunk in shared memory whatever the
+// segment length.  Every full piece owns the same number of slots (kPieceSlots), which keeps the
+// piece windows of the 32 lanes of a chunk aligned; only a lane's last, partial piece is shorter.
+constexpr int kPiece = 256;
+template <int NC> struct PieceSlots { static constexpr int value = (NC == 8) ? 280 : 272; };   // round4(padded_slots(kPiece, NC))
+__host__ __device__ __forceinline__ int piece_slots(int nc) { return nc == 8 ? PieceSlots<8>::value : PieceSlots<4>::value; }
+__host__ __device__ __forceinline__ int total_slots(int len, int nc) {
+    const int full = len / kPiece;
+    return full * piece_slots(nc) + padded_slots(len - full * kPiece, nc);
+}
 
 // segptr[row*(T+1) + t] = number of entries of `row` with column < t*tile_cols
 __global__ void seg_bounds_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t nrows,
@@ -84,7 +95,7 @@ sell_plan_kernel(const int64_t* __restrict__ window_start, const int64_t* __rest
         if (i < nr) {
             const int32_t* sp = segptr + (r0 + i) * (n_tiles + 1) + t;
             int len = sp[1] - sp[0];
-            if (pad_nc) len = padded_slots(len, pad_nc);   // slots, not entries
+            if (pad_nc) len = total_slots(len, pad_nc);   // slots, not entries
             key = ((kLenBias - static_cast<uint32_t>(len)) << 13) | static_cast<uint32_t>(i);
         }
         keys[i] = key;
@@ -164,9 +175,9 @@ __device__ __forceinline__ unsigned rotl_nc(unsigned x, int r) {
     return ((x << r) | (x >> (NC - r))) & ((1u << NC) - 1u);
 }
 
-// Simple per-lane layout (used for chunks longer than the staging capacity):
-// class rotation while every class has entries, the rest in column order.
-template <bool HAS_VAL, int NC, bool PAD>
+// Plain per-lane layout straight from global memory: class rotation while every
+// class has entries (depth = smallest class count, no holes), the rest in column order.
+template <bool HAS_VAL, int NC>
 __device__ void fill_lane_simple(const int32_t* __restrict__ idx, const float* __restrict__ val, int64_t s, int64_t e,
                                  int o, int col0, int row_bytes, int steps, int32_t* __restrict__ d,
                                  float* __restrict__ dv) {
@@ -182,26 +193,10 @@ __device__ void fill_lane_simple(const int32_t* __restrict__ idx, const float* _
         for (int u = 0; u < 8; ++u)
             if (jj[u] >= 0) cnt.add(jj[u] & (NC - 1), 1);
     }
-    // rotation depth: padded rotation (holes written as -1) or plain (no holes: depth = min class count)
     const int len = static_cast<int>(e - s);
-    const int R = PAD ? rotation_depth(len, NC) : cnt.min_all();
-    const int tail_cap = PAD ? padded_slots(len, NC) - NC * R : len;
-    const Packed<NC> tot = cnt;   // final class counts (hole enumeration)
-    if (PAD) {   // holes of the rotation region: classes with fewer than R entries
-#pragma unroll
-        for (int cl = 0; cl < NC; ++cl) {
-            const int x = (cl - o) & (NC - 1);
-            for (int q = tot.get(cl); q < R; ++q) {
-                const int k = NC * q + x;
-                const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
-                d[pos] = -1;
-                if (HAS_VAL) dv[pos] = 0.f;
-            }
-        }
-    }
+    const int R = cnt.min_all();
     cnt.clear();
     int left = 0;
-    int hole_c = 0, hole_q = PAD ? tot.get(0) : 0;   // next hole (only used when the tail overflows)
     for (int64_t p = s; p < e; p += 8) {
         int jj[8];
         float vv[8];
@@ -216,31 +211,21 @@ __device__ void fill_lane_simple(const int32_t* __restrict__ idx, const float* _
             const int cl = jj[u] & (NC - 1);
             const int q = cnt.get(cl);
             cnt.add(cl, 1);
-            int k;
-            if (q < R) {
-                k = NC * q + ((cl - o) & (NC - 1));
-            } else if (left < tail_cap) {
-                k = NC * R + left++;
-            } else {   // tail full (rare): use a leftover hole of the rotation region
-                while (hole_q >= R) { ++hole_c; hole_q = tot.get(hole_c); }
-                k = NC * hole_q + ((hole_c - o) & (NC - 1));
-                ++hole_q;
-            }
+            const int k = (q < R) ? NC * q + ((cl - o) & (NC - 1)) : NC * R + left++;
             const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
             d[pos] = (jj[u] - col0) * row_bytes;
             if (HAS_VAL) dv[pos] = vv[u];
         }
     }
-    // everything after the lane's last tail slot up to the chunk length
-    for (int k = (len > 0 ? NC * R + left : 0); k < steps; ++k) {
+    for (int k = len; k < steps; ++k) {
         const int64_t pos = static_cast<int64_t>(k >> 2) * 128 + (k & 3);
         d[pos] = -1;
         if (HAS_VAL) dv[pos] = 0.f;
     }
 }
 
-// ---- simple order: one warp per chunk, every lane lays out its own segment ----
-template <bool HAS_VAL, int NC, bool PAD>
+// ---- plain order: one warp per chunk, every lane lays out its own segment ----
+template <bool HAS_VAL, int NC>
 __global__ void __launch_bounds__(256)
 sell_fill_simple_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
                         const int32_t* __restrict__ segptr, int n_tiles, int tile_cols, int row_bytes, int64_t n_chunks,
@@ -264,7 +249,154 @@ sell_fill_simple_kernel(const int64_t* __restrict__ ptr, const int32_t* __restri
             s = ptr[row] + sp[0];
             e = ptr[row] + sp[1];
         }
-        fill_lane_simple<HAS_VAL, NC, PAD>(idx, val, s, e, o, t * tile_cols, row_bytes, steps, d, dv);
+        fill_lane_simple<HAS_VAL, NC>(idx, val, s, e, o, t * tile_cols, row_bytes, steps, d, dv);
+    }
+}
+
+// ---- padded class rotation (default): staged in shared memory -------------
+// One warp per chunk, one lane per row segment.  A lane walks its segment once, in pieces of kPiece
+// entries read with aligned 16-byte loads, and drops every entry at its slot of a per-lane column
+// in shared memory (16-bit tile-local columns, 0xFFFF = empty); the column is then written out as
+// 16-byte groups, so that the warp stores 512 contiguous bytes per instruction instead of 32
+// scattered words.  Slot of the q-th entry of class cl in a piece of plen entries:
+//   q < R (= rotation_depth(plen)):  NC*q + ((cl - o) mod NC)        (conflict-free rotation)
+//   else, while the tail has room:   NC*R + (running tail count)      (column order)
+//   else (tail full, ~1 lane in 5):  the leftover rotation holes in class order -- those are only
+//        known once the class totals are, so such entries wait in a small per-lane list (walked
+//        again from global memory if even that overflows, e.g. all columns in one class).
+// With values, the same walk runs a second time staging the entry's position in the piece, and the
+// write-out gathers val[] through it.
+constexpr int kStageWarps = 12;
+constexpr int kOvfCap = 16;
+template <int NC> struct StagePitch { static constexpr int value = 4 * ((PieceSlots<NC>::value / 4) | 1); };   // u16 units; odd in 8-byte words: conflict-free LDS.64
+
+__device__ __forceinline__ int4 load_idx4(const int32_t* __restrict__ idx, int64_t q, int64_t nnz) {
+    if (q + 3 < nnz) return *reinterpret_cast<const int4*>(idx + q);
+    int4 v = make_int4(0, 0, 0, 0);
+    if (q < nnz) v.x = idx[q];
+    if (q + 1 < nnz) v.y = idx[q + 1];
+    if (q + 2 < nnz) v.z = idx[q + 2];
+    return v;
+}
+
+template <bool HAS_VAL, int NC>
+__global__ void __launch_bounds__(kStageWarps * 32)
+sell_fill_staged_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
+                        int64_t nnz, const int32_t* __restrict__ segptr, int n_tiles, int tile_cols, int row_bytes,
+                        int64_t n_chunks, int64_t chunks_per_tile, const int32_t* __restrict__ chunk_rows,
+                        const int32_t* __restrict__ chunk_len4, const int64_t* __restrict__ chunk_off,
+                        int32_t* __restrict__ data, float* __restrict__ vals) {
+    constexpr int SP = PieceSlots<NC>::value, PITCH = StagePitch<NC>::value;
+    extern __shared__ __align__(16) unsigned char stage_smem[];
+    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
+    uint16_t* col = reinterpret_cast<uint16_t*>(stage_smem) + static_cast<size_t>(wic) * (32 * PITCH + kOvfCap * 32) + lane * PITCH;
+    uint16_t* ovf = reinterpret_cast<uint16_t*>(stage_smem) + static_cast<size_t>(wic) * (32 * PITCH + kOvfCap * 32) + 32 * PITCH + lane;
+    uint64_t* col64 = reinterpret_cast<uint64_t*>(col);
+    const int64_t warp = static_cast<int64_t>(blockIdx.x) * kStageWarps + wic;
+    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kStageWarps;
+    const int o = group_member<NC>(lane);
+    for (int64_t c = warp; c < n_chunks; c += nwarps) {
+        const int steps = chunk_len4[c] * 4;
+        if (steps == 0) continue;
+        const int row = chunk_rows[c * 32 + lane];
+        const int t = static_cast<int>(c / chunks_per_tile);
+        const int col0 = t * tile_cols;
+        const int64_t obase = chunk_off[c] * 128 + lane * 4;
+        int64_t s = 0, e = 0;
+        if (row >= 0) {
+            const int32_t* sp = segptr + static_cast<int64_t>(row) * (n_tiles + 1) + t;
+            s = ptr[row] + sp[0];
+            e = ptr[row] + sp[1];
+        }
+        for (int k0 = 0; k0 < steps; k0 += SP, s += kPiece) {
+            const int nst4 = min(SP, steps - k0) >> 2;
+            const int64_t pe = (e - s > kPiece) ? s + kPiece : e;
+            const int plen = pe > s ? static_cast<int>(pe - s) : 0;
+            const int R = rotation_depth(plen, NC);
+            const int tail_cap = padded_slots(plen, NC) - NC * R;
+#pragma unroll 1
+            for (int pass = 0; pass < (HAS_VAL ? 2 : 1); ++pass) {
+                for (int g = 0; g < nst4; ++g) col64[g] = ~0ull;
+                if (plen > 0) {
+                    Packed<NC> cnt;
+                    cnt.clear();
+                    int left = 0, novf = 0;
+                    for (int64_t a = s & ~static_cast<int64_t>(3); a < pe; a += 16) {
+                        int4 v[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            v[u] = (a + 4 * u < pe) ? load_idx4(idx, a + 4 * u, nnz) : make_int4(0, 0, 0, 0);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int jj[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                            for (int w = 0; w < 4; ++w) {
+                                const int64_t p = a + 4 * u + w;
+                                if (p < s || p >= pe) continue;
+                                const int cl = jj[w] & (NC - 1);
+                                const int q = cnt.get(cl);
+                                cnt.add(cl, 1);
+                                const uint16_t item = static_cast<uint16_t>(pass == 0 ? jj[w] - col0 : static_cast<int>(p - s));
+                                if (q < R) {
+                                    col[NC * q + ((cl - o) & (NC - 1))] = item;
+                                } else if (left < tail_cap) {
+                                    col[NC * R + left++] = item;
+                                } else {
+                                    if (novf < kOvfCap) ovf[novf * 32] = item;
+                                    ++novf;
+                                }
+                            }
+                        }
+                    }
+                    if (novf > 0) {   // tail overflow: fill the leftover holes of the rotation region in class order
+                        int hole_c = 0, hole_q = cnt.get(0);
+                        auto put = [&](uint16_t item) {
+                            while (hole_q >= R) { ++hole_c; hole_q = cnt.get(hole_c); }
+                            col[NC * hole_q + ((hole_c - o) & (NC - 1))] = item;
+                            ++hole_q;
+                        };
+                        if (novf <= kOvfCap) {
+                            for (int i = 0; i < novf; ++i) put(ovf[i * 32]);
+                        } else {   // the list was too small: walk the piece again
+                            Packed<NC> c2;
+                            c2.clear();
+                            int left2 = 0;
+                            for (int64_t p = s; p < pe; ++p) {
+                                const int j = idx[p];
+                                const int cl = j & (NC - 1);
+                                const int q = c2.get(cl);
+                                c2.add(cl, 1);
+                                if (q < R) continue;
+                                if (left2 < tail_cap) { ++left2; continue; }
+                                put(static_cast<uint16_t>(pass == 0 ? j - col0 : static_cast<int>(p - s)));
+                            }
+                        }
+                    }
+                }
+                // write-out: 4 slots (16 bytes) per lane and instruction, 512 contiguous bytes per warp
+                const int64_t ob = obase + static_cast<int64_t>(k0) * 32;
+                for (int g = 0; g < nst4; ++g) {
+                    const uint64_t w4 = col64[g];
+                    const int c0 = static_cast<int>(w4 & 0xFFFFu), c1 = static_cast<int>((w4 >> 16) & 0xFFFFu);
+                    const int c2 = static_cast<int>((w4 >> 32) & 0xFFFFu), c3 = static_cast<int>(w4 >> 48);
+                    if (pass == 0) {
+                        int4 out;
+                        out.x = c0 == 0xFFFF ? -1 : c0 * row_bytes;
+                        out.y = c1 == 0xFFFF ? -1 : c1 * row_bytes;
+                        out.z = c2 == 0xFFFF ? -1 : c2 * row_bytes;
+                        out.w = c3 == 0xFFFF ? -1 : c3 * row_bytes;
+                        __stcs(reinterpret_cast<int4*>(data + ob + static_cast<int64_t>(g) * 128), out);
+                    } else {
+                        float4 out;
+                        out.x = c0 == 0xFFFF ? 0.f : val[s + c0];
+                        out.y = c1 == 0xFFFF ? 0.f : val[s + c1];
+                        out.z = c2 == 0xFFFF ? 0.f : val[s + c2];
+                        out.w = c3 == 0xFFFF ? 0.f : val[s + c3];
+                        __stcs(reinterpret_cast<float4*>(vals + ob + static_cast<int64_t>(g) * 128), out);
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -335,7 +467,7 @@ sell_fill_matched_kernel(const int64_t* __restrict__ ptr, const int32_t* __restr
         const int col0 = t * tile_cols;
         const int len = static_cast<int>(e - s);
         if (steps > CAP) {   // warp-uniform; rare (very long segments): simple order straight from global memory
-            fill_lane_simple<HAS_VAL, NC, false>(idx, val, s, e, o, col0, row_bytes, steps, d, dv);
+            fill_lane_simple<HAS_VAL, NC>(idx, val, s, e, o, col0, row_bytes, steps, d, dv);
             continue;
         }
         // ---- 1. cooperative staging of the chunk's columns
@@ -542,23 +674,29 @@ void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b) {
         const bool matched = c->fill_mode == 1;
         const int rb = 4 * b;
 #define SB_FILL_ARGS                                                                                                   \
-    M.ptr.p, M.idx.p, M.val.p, segptr.p, T, S.tile_cols, rb, n_chunks, S.chunks_per_tile, S.chunk_rows.p,             \
-        S.chunk_len4.p, S.chunk_off.p, S.data.p, S.vals.p
+    segptr.p, T, S.tile_cols, rb, n_chunks, S.chunks_per_tile, S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p,          \
+        S.data.p, S.vals.p
 #define SB_FILL(HV, NC, CAP)                                                                                           \
     do {                                                                                                               \
-        if (matched) {                                                                                                 \
+        if (pad_mode) {                                                                                                \
+            SB_CHECK(PieceSlots<NC>::value == ((padded_slots(kPiece, NC) + 3) & ~3), "piece slot table out of date");  \
+            const size_t fsm = static_cast<size_t>(kStageWarps) * (32 * StagePitch<NC>::value + kOvfCap * 32) * 2;     \
+            auto kern = sell_fill_staged_kernel<HV, NC>;                                                               \
+            SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));   \
+            const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_chunks, kStageWarps), c->num_sms));       \
+            kern<<<blocks, kStageWarps * 32, fsm, st>>>(M.ptr.p, M.idx.p, M.val.p, M.nnz, SB_FILL_ARGS);               \
+        } else if (matched) {                                                                                          \
             const size_t fsm = static_cast<size_t>(kFillWarps) * CAP * (kColPitch * 2 + 32);                           \
             auto kern = sell_fill_matched_kernel<HV, NC, CAP>;                                                         \
             SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));   \
             const int per_sm = std::max<int>(1, static_cast<int>((220u << 10) / fsm));                                 \
             const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_chunks, kFillWarps),                      \
                                                                   static_cast<int64_t>(c->num_sms) * per_sm));         \
-            kern<<<blocks, kFillWarps * 32, fsm, st>>>(SB_FILL_ARGS);                                                  \
+            kern<<<blocks, kFillWarps * 32, fsm, st>>>(M.ptr.p, M.idx.p, M.val.p, SB_FILL_ARGS);                       \
         } else {                                                                                                       \
             const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_chunks, 8),                               \
                                                                   static_cast<int64_t>(c->num_sms) * 8));              \
-            if (pad_mode) sell_fill_simple_kernel<HV, NC, true><<<blocks, 256, 0, st>>>(SB_FILL_ARGS);                 \
-            else          sell_fill_simple_kernel<HV, NC, false><<<blocks, 256, 0, st>>>(SB_FILL_ARGS);                \
+            sell_fill_simple_kernel<HV, NC><<<blocks, 256, 0, st>>>(M.ptr.p, M.idx.p, M.val.p, SB_FILL_ARGS);          \
         }                                                                                                              \
     } while (0)
         const bool hv = M.has_values();

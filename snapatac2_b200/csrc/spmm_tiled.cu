@@ -243,6 +243,118 @@ reduce_tiles_kernel(const float* __restrict__ partial, int n_tiles, int64_t nrow
     reinterpret_cast<float4*>(out)[g] = y;
 }
 
+// ---- fp64 SpMV through the same format (prepare: row norms, column sums, degrees) ----
+// The dense operand is one fp64 vector, staged as 8-byte rows (tile_cols * 8 bytes per tile); an
+// entry's byte offset col * RB becomes col * 8 by a shift.  partial64[t][row] is written once.
+//   SQ: the stored value is squared (row norms of the weighted rows).
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+template <bool HAS_VAL, bool SQ>
+__device__ __forceinline__ void gather64(int e, float v, uint32_t tile, int sh, double& a) {
+    if (e >= 0) {
+        const double x = lds_f64(tile + (static_cast<uint32_t>(e) >> sh));
+        if (HAS_VAL) {
+            double dv = static_cast<double>(v);
+            if (SQ) dv *= dv;
+            a = fma(dv, x, a);
+        } else {
+            a += x;
+        }
+    }
+}
+
+template <bool HAS_VAL, bool SQ>
+__global__ void __launch_bounds__(kTiledThreads, 1)
+sell_spmv64_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restrict__ chunk_len4,
+                   const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ data, const float* __restrict__ vals,
+                   const double* __restrict__ in, double* __restrict__ partial, int64_t n_chunks, int64_t chunks_per_tile,
+                   int tile_cols, int64_t ncols, int64_t nrows, int sh) {
+    constexpr int U = 2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    double* tile = reinterpret_cast<double*>(smem);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + static_cast<size_t>(tile_cols) * 8);
+    unsigned long long* next_chunk = reinterpret_cast<unsigned long long*>(bar + 1);
+    int64_t* range = reinterpret_cast<int64_t*>(bar + 2);
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile_a = smem_u32(tile);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        const int64_t groups = chunk_off[n_chunks];
+        const int64_t g_lo = static_cast<int64_t>((static_cast<__int128>(groups) * blockIdx.x) / gridDim.x);
+        const int64_t g_hi = static_cast<int64_t>((static_cast<__int128>(groups) * (blockIdx.x + 1)) / gridDim.x);
+        range[0] = (blockIdx.x == 0) ? 0 : chunk_lower_bound(chunk_off, n_chunks, g_lo);
+        range[1] = (blockIdx.x == gridDim.x - 1) ? n_chunks : chunk_lower_bound(chunk_off, n_chunks, g_hi);
+    }
+    __syncthreads();
+    const int64_t c_begin = range[0], c_end = range[1];
+    if (c_begin >= c_end) return;
+    uint32_t phase = 0;
+    for (int64_t t = c_begin / chunks_per_tile; t * chunks_per_tile < c_end; ++t) {
+        const int64_t lo = max(c_begin, t * chunks_per_tile);
+        const int64_t hi = min(c_end, (t + 1) * chunks_per_tile);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            *next_chunk = static_cast<unsigned long long>(lo);
+            const int64_t c0 = t * tile_cols;
+            // bulk copies move multiples of 16 bytes: an odd tail reads one double of slack (callers pad x)
+            const uint32_t bytes = (static_cast<uint32_t>(min(static_cast<int64_t>(tile_cols), ncols - c0)) * 8 + 15u) & ~15u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(bar, bytes);
+            tma_load_1d(tile, in + c0, bytes, bar);
+        }
+        __syncthreads();
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        double* part_t = partial + t * nrows;
+        while (true) {
+            unsigned long long cu = 0;
+            if (lane == 0) cu = atomicAdd(next_chunk, 1ull);
+            const int64_t c = static_cast<int64_t>(__shfl_sync(0xffffffffu, cu, 0));
+            if (c >= hi) break;
+            const int row = chunk_rows[c * 32 + lane];
+            const int len4 = chunk_len4[c];
+            const int4* d = reinterpret_cast<const int4*>(data) + chunk_off[c] * 32 + lane;
+            const float4* dv = HAS_VAL ? reinterpret_cast<const float4*>(vals) + chunk_off[c] * 32 + lane : nullptr;
+            double a0 = 0.0, a1 = 0.0;   // two fixed chains
+            for (int g = 0; g < len4; g += U) {
+                int4 e[U];
+                float4 v[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    e[u] = make_int4(-1, -1, -1, -1);
+                    v[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (g + u < len4) {
+                        e[u] = ld_stream_int4(d + (g + u) * 32);
+                        if (HAS_VAL) v[u] = ld_stream_float4(dv + (g + u) * 32);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    gather64<HAS_VAL, SQ>(e[u].x, v[u].x, tile_a, sh, a0);
+                    gather64<HAS_VAL, SQ>(e[u].y, v[u].y, tile_a, sh, a1);
+                    gather64<HAS_VAL, SQ>(e[u].z, v[u].z, tile_a, sh, a0);
+                    gather64<HAS_VAL, SQ>(e[u].w, v[u].w, tile_a, sh, a1);
+                }
+            }
+            if (row >= 0) part_t[row] = a0 + a1;
+        }
+    }
+}
+
+// mode 0: out = sqrt(sum_t partial)    mode 1: out = scale * sum_t partial + shift
+__global__ void __launch_bounds__(256)
+reduce_tiles64_kernel(const double* __restrict__ partial, int n_tiles, int64_t nrows, int mode,
+                      const double* __restrict__ scale, double shift, double* __restrict__ out) {
+    const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    double s = 0.0;
+    for (int t = 0; t < n_tiles; ++t) s += partial[static_cast<int64_t>(t) * nrows + r];
+    out[r] = (mode == 0) ? sqrt(s) : (scale ? scale[r] : 1.0) * s + shift;
+}
+
 template <int B>
 void spmm_impl(snapb200_ctx* c, const Sell& S, const float* in, float* out, const float* scale, const float* subscale,
                const float* sub, int64_t lds) {
@@ -293,6 +405,35 @@ void ensure_tiled(snapb200_ctx* c, int b) {
     float ms = 0.f;
     SB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
     c->stats.ms_format = ms;
+}
+
+void sell_spmv64(snapb200_ctx* c, const Sell& S, const double* x, int mode, const double* scale, double shift,
+                 double* out) {
+    SB_CHECK(S.built, "tiled SpMV: format not built");
+    if (S.nrows == 0) return;
+    cudaStream_t st = c->stream;
+    // the fp32 partial buffer doubles as the fp64 one (n_tiles x nrows doubles)
+    c->partial.ensure(static_cast<int64_t>(S.n_tiles) * S.nrows * 2);
+    double* part = reinterpret_cast<double*>(c->partial.p);
+    const size_t smem = static_cast<size_t>(S.tile_cols) * 8 + 64;
+    const int sh = (S.b == 8) ? 2 : 1;   // entry = col * 4b bytes -> col * 8
+    const bool sq = mode == 0;
+#define SB_SPMV64(HV, SQ)                                                                                              \
+    do {                                                                                                               \
+        auto k = sell_spmv64_kernel<HV, SQ>;                                                                           \
+        SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));         \
+        k<<<c->num_sms, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p, S.data.p, S.vals.p,  \
+                                                   x, part, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols,       \
+                                                   S.nrows, sh);                                                       \
+    } while (0)
+    if (S.vals.p) { if (sq) SB_SPMV64(true, true); else SB_SPMV64(true, false); }
+    else          SB_SPMV64(false, false);
+#undef SB_SPMV64
+    SB_LAUNCH_CHECK();
+    reduce_tiles64_kernel<<<static_cast<unsigned>(ceil_div(S.nrows, 256)), 256, 0, st>>>(part, S.n_tiles, S.nrows, mode,
+                                                                                        scale, shift, out);
+    SB_LAUNCH_CHECK();
+    count_launch(c, 2);
 }
 
 void sell_spmm(snapb200_ctx* c, const Sell& S, const float* in, float* out, const float* scale,
