@@ -147,11 +147,9 @@ int  snapb200_eigsh(snapb200_ctx* ctx, int k, int64_t seed, double tol,
 int  snapb200_get_stats(snapb200_ctx* ctx, snapb200_stats* out);
 
 /* SpMM kernel selection: 0 = automatic (tiled for >= 2^25 stored entries and
- * b = 4 or 8), 1 = CSR gather out of L2, 2 = shared-memory tiled sliced-ELL.
- * The tiled entry order defaults to a padded class rotation (the lanes of a
- * quarter warp read distinct shared-memory bank groups; ~11% padding slots).
- * Adding 8 selects the group-matched order (no padding, ~2x slower format
- * build), adding 16 the plain rotation without padding (most bank conflicts).
+ * b = 4 or 8), 1 = CSR gather out of L2, 2 = shared-memory tiled sliced-ELL
+ * (16-bit tile-local entries ordered by a padded class rotation so that the
+ * lanes of a quarter warp read distinct shared-memory bank groups).
  * Takes effect at the next prepare. */
 int  snapb200_set_spmm_mode(snapb200_ctx* ctx, int mode);
 

@@ -19,7 +19,7 @@ CSRC = HERE / "csrc"
 BUILD = HERE / "_build"
 LIB = HERE / "libsnapb200.so"
 
-SOURCES = ["api.cu", "pool.cu", "comm.cu", "util.cu", "synth.cu", "prep.cu", "spmm.cu", "sell_build.cu", "spmm_tiled.cu", "dense.cu", "lanczos.cu"]
+SOURCES = ["api.cu", "pool.cu", "comm.cu", "util.cu", "synth.cu", "prep.cu", "transpose_tiled.cu", "spmm.cu", "sell_build.cu", "spmm_tiled.cu", "dense.cu", "lanczos.cu"]
 
 
 def _nccl_paths():

@@ -116,6 +116,8 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     const bool dev = on_device != 0;
     Csr& X = c->X;
     c->Xt.clear();
+    c->xt_built = false;
+    c->XtT.clear();
     X.nrows = n_local;
     X.ncols = m;
     X.ptr.alloc(n_local + 1);
@@ -236,9 +238,6 @@ int snapb200_create(int device, snapb200_ctx** out) {
         c->device = device;
         c->num_sms = prop.multiProcessorCount;
         SB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        SB_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
-        SB_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        SB_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         SB_CUDA(cudaEventCreate(&c->ev0));
         SB_CUDA(cudaEventCreate(&c->ev1));
         *out = c;
@@ -250,16 +249,12 @@ int snapb200_destroy(snapb200_ctx* c) {
         if (!c) return;
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
-        if (c->stream2) cudaStreamSynchronize(c->stream2);
         comm_destroy(c);
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
-        if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-        if (c->ev_join) cudaEventDestroy(c->ev_join);
-        cudaStream_t st = c->stream, st2 = c->stream2;
+        cudaStream_t st = c->stream;
         delete c;
         if (st) cudaStreamDestroy(st);
-        if (st2) cudaStreamDestroy(st2);
     });
 }
 
@@ -289,6 +284,8 @@ int snapb200_generate(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_
     return guarded([&] {
         bind(c);
         c->Xt.clear();
+        c->xt_built = false;
+        c->XtT.clear();
         generate_rows(c, n_local, n_global, row0, m, nnz_row, n_clusters, seed, feat_cdf, cluster_cdf, block_start, alpha);
     });
 }
@@ -412,9 +409,8 @@ int snapb200_get_stats(snapb200_ctx* c, snapb200_stats* out) {
 int snapb200_set_spmm_mode(snapb200_ctx* c, int mode) {
     return guarded([&] {
         SB_CHECK(c != nullptr, "null context");
-        SB_CHECK((mode & 7) <= 2 && (mode >> 3) <= 2, "set_spmm_mode: bad mode");
-        c->spmm_mode = mode & 7;
-        c->fill_mode = mode >> 3;
+        SB_CHECK(mode >= 0 && mode <= 2, "set_spmm_mode: mode must be 0 (auto), 1 (csr) or 2 (tiled)");
+        c->spmm_mode = mode;
         c->prepared = false;
     });
 }

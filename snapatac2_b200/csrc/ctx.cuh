@@ -75,35 +75,55 @@ struct Csr {
     }
 };
 
+// Tile-major transpose of the pattern (prep.cu: transpose_tiled), the input of the feature-major
+// tiled copy.  The local cells are cut into tiles of `tile_rows` (= the column tile of that copy);
+// tile t stores, feature by feature, the tile-local ids (16 bit, ascending) of its cells that have
+// the feature: segment (t, j) = ids[tile_base[t] + segoff[t*m + j] .. + cnt[t*m + j]).
+struct TileT {
+    int tile_rows = 0, n_tiles = 0;
+    int64_t m = 0, nnz = 0;
+    DevBuf<uint16_t> cnt;        // n_tiles * m   segment lengths
+    DevBuf<uint32_t> segoff;     // n_tiles * m   segment starts relative to the tile
+    DevBuf<int64_t> tile_base;   // n_tiles + 1
+    DevBuf<uint16_t> ids;        // nnz
+    DevBuf<float> vals;          // nnz or empty
+    bool built = false;
+    void clear() {
+        cnt.release(); segoff.release(); tile_base.release(); ids.release(); vals.release();
+        built = false; nnz = 0; n_tiles = 0;
+    }
+};
+
 // Column-tiled sliced-ELL copy of a CSR matrix for the shared-memory SpMM
 // (sell_build.cu / spmm_tiled.cu).  Columns are cut into tiles of `tile_cols`
-// columns so that a tile of the dense operand (tile_cols x 8 floats) fits in
+// columns so that a tile of the dense operand (tile_cols x b floats) fits in
 // shared memory; rows into `n_windows` windows of at most kSellWindowRows rows.
 // The chunk list is TILE-MAJOR: tile 0 of every window, then tile 1, ...  Inside
 // one (tile, window) the row segments are sorted by length and cut into chunks
 // of 32 (one lane per row segment; every row appears in every tile, possibly
 // with an empty segment, so each (tile, row) partial result is written exactly
-// once).  A chunk stores its entries interleaved, four per lane at a time, so a
-// warp reads 512 contiguous bytes per step.  Entries are byte offsets of the
-// dense row inside the staged tile (local column * 32), -1 = padding.  Within
-// a lane the entries are ordered so that the eight lanes of a quarter warp hit
-// eight different 16-byte bank groups (see sell_build.cu).
+// once).  An entry is the 16-bit tile-local column (0xFFFF = empty slot): 2
+// bytes per stored entry.  A chunk stores its entries interleaved, eight per
+// lane at a time (one "group" = 32 lanes x 16 bytes), so a warp reads 512
+// contiguous bytes per step.  Within a lane the entries are ordered so that the
+// eight lanes of a quarter warp hit eight different 16-byte bank groups (see
+// sell_build.cu).
 struct Sell {
     int b = 0;                                // dense block width the tiles are sized for (4 or 8)
     int n_windows = 0, n_tiles = 0, tile_cols = 0;
     int64_t chunks_per_tile = 0;              // the same for every tile
     int64_t nrows = 0, ncols = 0;
-    int64_t n_chunks = 0, n_entries = 0;      // n_entries counts padded slots
+    int64_t n_chunks = 0, n_entries = 0;      // n_entries counts slots (entries + empty)
     DevBuf<int64_t> window_start;             // n_windows + 1 row boundaries
     DevBuf<int64_t> window_chunk0;            // n_windows + 1 first chunk of a window inside a tile
     DevBuf<int32_t> chunk_rows;               // n_chunks * 32 (global row id, -1 = none)
-    DevBuf<int32_t> chunk_len4;               // n_chunks   (steps of 4 entries)
-    DevBuf<int64_t> chunk_off;                // n_chunks + 1, in units of 128 entries
-    DevBuf<int32_t> data;                     // n_entries
+    DevBuf<int32_t> chunk_groups;             // n_chunks   (groups of 8 slots per lane)
+    DevBuf<int64_t> chunk_off;                // n_chunks + 1, in groups (256 slots)
+    DevBuf<uint16_t> data;                    // n_entries
     DevBuf<float> vals;                       // n_entries or empty
     bool built = false;
     void clear() {
-        window_start.release(); window_chunk0.release(); chunk_rows.release(); chunk_len4.release();
+        window_start.release(); window_chunk0.release(); chunk_rows.release(); chunk_groups.release();
         chunk_off.release(); data.release(); vals.release();
         built = false; n_chunks = n_entries = 0;
     }
@@ -119,8 +139,6 @@ struct Comm;  // NCCL wrapper (comm.cu)
 struct snapb200_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;    // the context's stream: every call is ordered on it
-    cudaStream_t stream2 = nullptr;   // helper stream: independent prepare phases overlap with the transpose
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     int num_sms = snapb::kNumSMsB200;
 
     // multi-GPU
@@ -132,17 +150,16 @@ struct snapb200_ctx {
     bool loaded = false, prepared = false;
 
     snapb::Csr X;    // cells x features (this rank's rows)
-    snapb::Csr Xt;   // features x local cells (built by prepare)
+    snapb::Csr Xt;   // features x local cells, CSR: only built for the CSR-gather operator (ensure_xt)
+    bool xt_built = false;
+    snapb::TileT XtT;  // tile-major 16-bit transpose: the input of S1 (tiled path), released once S1 is built
     snapb::Sell S2;  // tiled copy of X  (pass 2: gathers W rows by feature)
     snapb::Sell S1;  // tiled copy of Xt (pass 1: gathers r.*V rows by cell)
     int spmm_mode = 0;   // 0 = auto, 1 = CSR gather from L2, 2 = shared-memory tiled SELL
     // default Lanczos block width (prepare builds the tiled copies for it).  4: a dense row is one
     // 16-byte bank group, half the shared-memory traffic per entry of b = 8; the solver needs ~1.6x the
-    // operator applications but each costs half, and the SpMM runs at ~60% instead of ~35% of HBM peak.
+    // operator applications but each costs less than half.
     int block = 4;
-    // tiled format entry order: 0 = padded class rotation (default), 1 = group-matched (no padding,
-    // slow build), 2 = plain rotation without padding (first version, most bank conflicts)
-    int fill_mode = 0;
 
     // user feature weights (host copy, optional)
     std::vector<double> user_weights;
@@ -196,7 +213,10 @@ void flush_l2(snapb200_ctx* c);
 
 // ---- prep.cu
 void select_features(snapb200_ctx* c, const uint8_t* keep_host, int64_t m);
-void build_transpose(snapb200_ctx* c);
+void ensure_xt(snapb200_ctx* c);   // builds the CSR feature-major copy c->Xt if it is missing
+// tile-major transpose c->XtT for cell tiles of `tile_rows`; also leaves the local document
+// frequencies in df_local (m int64) when it is non-null
+void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local);
 void prepare(snapb200_ctx* c, double* idf_out, double* degree_out);
 void view_norms(snapb200_ctx* c, double* idf_out, double* rho_out);
 
@@ -209,6 +229,9 @@ void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, 
 
 // ---- sell_build.cu / spmm_tiled.cu
 void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b);
+// the same from the tile-major transpose (rows = features, columns = local cells; T.tile_rows must
+// equal the format's column tile for b)
+void sell_build_transposed(snapb200_ctx* c, const TileT& T, int64_t n_cells, Sell& S, int b);
 // out[row, 0:b] = scale[row] * (M in)[row, 0:b] - (sub ? subscale[row] * sub[row*lds + 0:b] : 0)
 // through the tiled copy (b = S.b); `in` and `out` are packed (leading dimension b).
 void sell_spmm(snapb200_ctx* c, const Sell& S, const float* in, float* out, const float* scale,

@@ -279,14 +279,6 @@ inline int grid_for_rows(snapb200_ctx* c, int64_t nrows) {
 }
 inline unsigned grid1d(int64_t n, int threads = 256) { return static_cast<unsigned>(std::max<int64_t>(1, ceil_div(n, threads))); }
 
-float elapsed_ms(snapb200_ctx* c) {
-    SB_CUDA(cudaEventRecord(c->ev1, c->stream));
-    SB_CUDA(cudaEventSynchronize(c->ev1));
-    float ms = 0.f;
-    SB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-    return ms;
-}
-
 }  // namespace
 
 // --------------------------------------------------------------------------
@@ -333,6 +325,9 @@ void select_features(snapb200_ctx* c, const uint8_t* keep_host, int64_t m) {
     X.ncols = m_new;
     c->m = m_new;
     c->prepared = false;
+    c->Xt.clear();
+    c->xt_built = false;
+    c->XtT.clear();
     c->stats.nnz_local = nnz;
 }
 
@@ -398,15 +393,22 @@ static void transpose_enqueue(snapb200_ctx* c, TransposeState& ts) {
     }
 }
 
-void build_transpose(snapb200_ctx* c) {
+void ensure_xt(snapb200_ctx* c) {
+    if (c->xt_built) return;
     DevBuf<int32_t> cnt;
     TransposeState ts;
     transpose_begin(c, cnt, ts);
     transpose_enqueue(c, ts);
     SB_CUDA(cudaStreamSynchronize(c->stream));
+    c->xt_built = true;
 }
 
 // --------------------------------------------------------------------------
+// prepare(): document frequencies -> IDF, both layouts of the pattern the operator gathers over,
+// row norms, column sums, degrees, and the derived fp32 vectors.
+//   tiled path (large problems): tile-major transpose -> S1, S2 from the rows; the three fp64 SpMVs
+//   run through the tiled copies.
+//   CSR path (small problems): CSR transpose, fp64 gather SpMVs.
 void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     SB_CHECK(c->loaded, "prepare: no matrix loaded");
     Csr& X = c->X;
@@ -414,101 +416,88 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     SB_CHECK(m >= 1, "prepare: matrix has no columns");
     cudaStream_t st = c->stream;
     const auto wall0 = std::chrono::steady_clock::now();
-
-    // ---- local document frequencies, row pointers of the feature-major copy (main stream)
-    SB_CUDA(cudaEventRecord(c->ev0, st));
-    DevBuf<int32_t> cnt;
-    TransposeState ts;
-    transpose_begin(c, cnt, ts);
-    c->w.alloc(m);
-    DevBuf<int64_t> df, mm;
-    if (!c->user_weights.empty()) {
+    auto since = [](std::chrono::steady_clock::time_point t0) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    };
+    const bool tiled = use_tiled(c, c->block);
+    const bool user_w = !c->user_weights.empty();
+    if (user_w)
         SB_CHECK(static_cast<int64_t>(c->user_weights.size()) == m,
                  "feature_weights length must equal the number of selected features");
-        SB_CUDA(cudaMemcpyAsync(c->w.p, c->user_weights.data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
-    } else {
-        df.alloc(m);
-        mm.alloc(2);
-        i32_to_i64_kernel<<<grid1d(m), 256, 0, st>>>(cnt.p, df.p, m);
-        SB_LAUNCH_CHECK();
-        allreduce_i64(c, df.p, m);   // every NCCL call stays on the main stream
-        count_launch(c);
-    }
+
+    c->w.alloc(m);
     c->rho.alloc(std::max<int64_t>(1, n));
     c->degree.alloc(std::max<int64_t>(1, n));
     c->csum.alloc(m);
     DevBuf<double> rinv, wc;
+    DevBuf<int64_t> df, mm;
     rinv.alloc(n + 2);   // (+2: the tiled fp64 SpMV stages whole 16-byte units)
     wc.alloc(m + 2);
-    const bool tiled = use_tiled(c, c->block);
+    df.alloc(m);
+    mm.alloc(2);
     c->S1.clear();
     c->S2.clear();
-    c->stats.ms_format = 0.0;
-    SB_CUDA(cudaEventRecord(c->ev_fork, st));
+    c->XtT.clear();
+    double ms_format = 0.0;
 
-    // ---- main stream: the transpose slab loop (~2 launches per 1024 rows), enqueued asynchronously
-    transpose_enqueue(c, ts);
-    SB_CUDA(cudaEventRecord(c->ev1, st));   // end of the transpose on the main stream's timeline
-
-    // ---- helper stream, concurrently: IDF weights, row norms, the cell-major tiled copy.  These
-    //      need X and the document frequencies only; they overlap with the atomics-bound transpose.
-    const auto wall_fork = std::chrono::steady_clock::now();
-    {
-        cudaStream_t aux = c->stream2;
-        SB_CUDA(cudaStreamWaitEvent(aux, c->ev_fork, 0));
-        c->stream = aux;
-        pool_set_stream(aux);
-        try {
-            if (c->user_weights.empty()) {
-                df_minmax_kernel<<<1, 256, 0, aux>>>(df.p, m, mm.p);
-                SB_LAUNCH_CHECK();
-                idf_kernel<<<grid1d(m), 256, 0, aux>>>(df.p, mm.p, m, static_cast<double>(c->n_global), c->w.p);
-                SB_LAUNCH_CHECK();
-                count_launch(c, 2);
-            }
-            // cell-major tiled copy, then row norms rho_i = || w .* x_i ||   (:315-326)
-            if (tiled) {
-                sell_build(c, c->X, c->S2, c->block);
-                if (n > 0) {
-                    sqr_kernel<<<grid1d(m), 256, 0, aux>>>(c->w.p, wc.p, m);   // wc is free until the degrees
-                    SB_LAUNCH_CHECK();
-                    sell_spmv64(c, c->S2, wc.p, 0, nullptr, 0.0, c->rho.p);
-                    count_launch(c);
-                }
-            } else if (n > 0) {
-                spmv_f64_kernel<0><<<grid_for_rows(c, n), 256, 0, aux>>>(X.ptr.p, X.idx.p, X.val.p, c->w.p, nullptr, 0.0,
-                                                                        n, c->rho.p);
-                SB_LAUNCH_CHECK();
-                count_launch(c);
-            }
-            if (n > 0) {
-                recip_kernel<<<grid1d(n), 256, 0, aux>>>(c->rho.p, rinv.p, n);
-                SB_LAUNCH_CHECK();
-                count_launch(c);
-            }
-            SB_CUDA(cudaEventRecord(c->ev_join, aux));
-        } catch (...) {
-            c->stream = st;
-            pool_set_stream(st);
-            cudaStreamSynchronize(aux);
-            cudaStreamSynchronize(st);
-            throw;
-        }
-        c->stream = st;
-        pool_set_stream(st);
-        SB_CUDA(cudaStreamWaitEvent(st, c->ev_join, 0));
-    }
-    const double ms_aux_host =
-        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall_fork).count();
-    cnt.release();
-
-    // ---- feature-major tiled copy (needs Xt)
-    const auto wall_s1 = std::chrono::steady_clock::now();
+    // ---- transpose (also yields the local document frequencies)
+    SB_CUDA(cudaEventRecord(c->ev0, st));
     if (tiled) {
-        sell_build(c, c->Xt, c->S1, c->block);
+        c->Xt.clear();
+        c->xt_built = false;
+        transpose_tiled(c, kSellTileBytes / (4 * c->block), df.p);
+    } else {
+        c->xt_built = false;
+        DevBuf<int32_t> cnt;
+        TransposeState ts;
+        transpose_begin(c, cnt, ts);
+        i32_to_i64_kernel<<<grid1d(m), 256, 0, st>>>(cnt.p, df.p, m);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+        transpose_enqueue(c, ts);
         SB_CUDA(cudaStreamSynchronize(st));
+        c->xt_built = true;
     }
-    const double ms_s1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall_s1).count();
+    SB_CUDA(cudaEventRecord(c->ev1, st));
+    if (user_w) {
+        SB_CUDA(cudaMemcpyAsync(c->w.p, c->user_weights.data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    } else {
+        allreduce_i64(c, df.p, m);
+    }
+
+    // ---- IDF weights (:269-286)
+    if (!user_w) {
+        df_minmax_kernel<<<1, 256, 0, st>>>(df.p, m, mm.p);
+        SB_LAUNCH_CHECK();
+        idf_kernel<<<grid1d(m), 256, 0, st>>>(df.p, mm.p, m, static_cast<double>(c->n_global), c->w.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c, 2);
+    }
+    // ---- both tiled copies, then row norms rho_i = || w .* x_i ||   (:315-326)
+    if (tiled) {
+        const auto w0 = std::chrono::steady_clock::now();
+        sell_build_transposed(c, c->XtT, n, c->S1, c->block);
+        c->XtT.clear();   // only the input of S1: released (rebuilt on demand if the block width changes)
+        sell_build(c, c->X, c->S2, c->block);
+        ms_format = since(w0);
+        if (n > 0) {
+            sqr_kernel<<<grid1d(m), 256, 0, st>>>(c->w.p, wc.p, m);   // wc is free until the degrees
+            SB_LAUNCH_CHECK();
+            sell_spmv64(c, c->S2, wc.p, 0, nullptr, 0.0, c->rho.p);
+            count_launch(c);
+        }
+    } else if (n > 0) {
+        spmv_f64_kernel<0><<<grid_for_rows(c, n), 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, c->w.p, nullptr, 0.0, n,
+                                                               c->rho.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
+    if (n > 0) {
+        recip_kernel<<<grid1d(n), 256, 0, st>>>(c->rho.p, rinv.p, n);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
+
     // ---- column sums c_j = w_j sum_i x_ij / rho_i               (:139-144)
     if (tiled) {
         sell_spmv64(c, c->S1, rinv.p, 1, c->w.p, 0.0, c->csum.p);
@@ -585,13 +574,12 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     SB_CUDA(cudaStreamSynchronize(st));
     {
         float ms_t = 0.f;
-        cudaEventElapsedTime(&ms_t, c->ev0, c->ev1);   // counts + slab loop as seen on the main stream
+        cudaEventElapsedTime(&ms_t, c->ev0, c->ev1);
         c->stats.ms_transpose = ms_t;
     }
-    c->stats.ms_format = ms_aux_host + ms_s1;   // host view: helper-stream phase (overlaps the transpose) + S1 build
-    c->stats.ms_prepare_wall =
-        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
-    c->stats.ms_prepare = c->stats.ms_prepare_wall - c->stats.ms_transpose - ms_s1;   // the rest (overlap aside)
+    c->stats.ms_format = ms_format;
+    c->stats.ms_prepare_wall = since(wall0);
+    c->stats.ms_prepare = std::max(0.0, c->stats.ms_prepare_wall - c->stats.ms_transpose - ms_format);
     c->prepared = true;
 }
 

@@ -146,6 +146,7 @@ void apply_impl(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t 
         SB_LAUNCH_CHECK();
         count_launch(c);
     }
+    ensure_xt(c);   // the CSR feature-major copy is built on first use
     if (evs) SB_CUDA(cudaEventRecord(evs[0], st));
     // pass 1: W = w^2 .* P^T (r V)
     if (c->Xt.has_values())

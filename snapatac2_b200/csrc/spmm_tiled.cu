@@ -8,16 +8,16 @@
 // which touches one or two column tiles.  For each of them it stages the dense
 // operand tile (192 KB: 6144 rows of 32 B or 12288 rows of 16 B) in shared
 // memory with one TMA bulk copy (cp.async.bulk + mbarrier), then its 24 warps
-// pull chunks from a shared counter: one lane per row segment, four entries
-// per 128-bit index load (512 contiguous bytes per warp-load, double buffered
+// pull chunks from a shared counter: one lane per row segment, eight 16-bit
+// entries per 128-bit load (512 contiguous bytes per warp-load, double buffered
 // in registers), b/4 LDS.128 per entry.  The build orders entries so the
 // LDS.128 of a quarter warp are (mostly) bank-conflict free.  Every
 // (tile, row) partial is written exactly once with a plain store: no atomics,
 // bitwise reproducible.
 //
-// Algorithmic bytes per stored entry: 4 (the int32 entry) -- the HBM roofline
-// of the pass; on chip it needs 4b bytes of shared-memory bandwidth per entry,
-// which is what bounds b = 8 (ncu: l1tex data-pipe 93% busy at C3).
+// Bytes per stored entry: 2 from HBM (the 16-bit tile-local column; CSR's int32
+// index is the 4-byte algorithmic figure the roofline line of bench.py uses) and
+// 4b bytes of shared-memory bandwidth, which is what bounds the kernel.
 #include "ctx.cuh"
 
 #include <algorithm>
@@ -77,25 +77,32 @@ __device__ __forceinline__ void acc4(float4& a, const float4& x, float v, bool h
     }
 }
 
-// one stored entry: B/4 LDS.128 from the staged tile
+// one stored entry (16-bit tile-local column, 0xFFFF = empty slot): B/4 LDS.128 from the staged tile
 template <int B, bool HAS_VAL>
-__device__ __forceinline__ void gather_one(int e, float v, uint32_t tile1, uint32_t tile2, float4& a, float4& b) {
-    if (e >= 0) {
-        const float4 x1 = lds128(tile1 + e);
+__device__ __forceinline__ void gather_one(uint32_t col, float v, uint32_t tile1, uint32_t tile2, float4& a, float4& b) {
+    if (col != 0xFFFFu) {
+        const uint32_t off = col * (4u * B);
+        const float4 x1 = lds128(tile1 + off);
         acc4(a, x1, v, HAS_VAL);
         if (B == 8) {
-            const float4 x2 = lds128(tile2 + e);
+            const float4 x2 = lds128(tile2 + off);
             acc4(b, x2, v, HAS_VAL);
         }
     }
 }
 template <int B, bool HAS_VAL>
-__device__ __forceinline__ void gather_four(const int4& e, const float4& v, uint32_t tile1, uint32_t tile2, float4& a,
-                                            float4& b) {
-    gather_one<B, HAS_VAL>(e.x, v.x, tile1, tile2, a, b);
-    gather_one<B, HAS_VAL>(e.y, v.y, tile1, tile2, a, b);
-    gather_one<B, HAS_VAL>(e.z, v.z, tile1, tile2, a, b);
-    gather_one<B, HAS_VAL>(e.w, v.w, tile1, tile2, a, b);
+__device__ __forceinline__ void gather_eight(const int4& e, const float4& v0, const float4& v1, uint32_t tile1,
+                                             uint32_t tile2, float4& a, float4& b) {
+    const uint32_t x = static_cast<uint32_t>(e.x), y = static_cast<uint32_t>(e.y);
+    const uint32_t z = static_cast<uint32_t>(e.z), w = static_cast<uint32_t>(e.w);
+    gather_one<B, HAS_VAL>(x & 0xFFFFu, v0.x, tile1, tile2, a, b);
+    gather_one<B, HAS_VAL>(x >> 16, v0.y, tile1, tile2, a, b);
+    gather_one<B, HAS_VAL>(y & 0xFFFFu, v0.z, tile1, tile2, a, b);
+    gather_one<B, HAS_VAL>(y >> 16, v0.w, tile1, tile2, a, b);
+    gather_one<B, HAS_VAL>(z & 0xFFFFu, v1.x, tile1, tile2, a, b);
+    gather_one<B, HAS_VAL>(z >> 16, v1.y, tile1, tile2, a, b);
+    gather_one<B, HAS_VAL>(w & 0xFFFFu, v1.z, tile1, tile2, a, b);
+    gather_one<B, HAS_VAL>(w >> 16, v1.w, tile1, tile2, a, b);
 }
 
 // first chunk index c in [0, n] with chunk_off[c] >= target
@@ -110,8 +117,8 @@ __device__ int64_t chunk_lower_bound(const int64_t* __restrict__ chunk_off, int6
 
 template <int B, bool HAS_VAL, int U>
 __global__ void __launch_bounds__(kTiledThreads, 1)
-sell_spmm_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restrict__ chunk_len4,
-                 const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ data, const float* __restrict__ vals,
+sell_spmm_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restrict__ chunk_groups,
+                 const int64_t* __restrict__ chunk_off, const uint16_t* __restrict__ data, const float* __restrict__ vals,
                  const float* __restrict__ in, float* __restrict__ partial, int64_t n_chunks, int64_t chunks_per_tile,
                  int tile_cols, int64_t ncols, int64_t nrows) {
     constexpr int RB = 4 * B;   // bytes per dense row
@@ -162,38 +169,48 @@ sell_spmm_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restri
             const int64_t c = static_cast<int64_t>(__shfl_sync(0xffffffffu, cu, 0));
             if (c >= hi) break;
             const int row = chunk_rows[c * 32 + lane];
-            const int len4 = chunk_len4[c];
-            const int4* d = reinterpret_cast<const int4*>(data) + chunk_off[c] * 32 + lane;
-            const float4* dv = HAS_VAL ? reinterpret_cast<const float4*>(vals) + chunk_off[c] * 32 + lane : nullptr;
+            const int ng = chunk_groups[c];
+            const int4* d = reinterpret_cast<const int4*>(data) + chunk_off[c] * 32 + lane;   // a group: 32 lanes x 16 B
+            // values: 8 floats per lane and group = two float4 (a group: 64 float4)
+            const float4* dv = HAS_VAL ? reinterpret_cast<const float4*>(vals) + chunk_off[c] * 64 + lane * 2 : nullptr;
             float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
             const float4 ones = make_float4(1.f, 1.f, 1.f, 1.f);
+            const int4 none = make_int4(-1, -1, -1, -1);
             int4 cur[U], nxt[U];
-            float4 vcur[U], vnxt[U];
+            float4 vcur[2 * U], vnxt[2 * U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                cur[u] = make_int4(-1, -1, -1, -1);
-                vcur[u] = ones;
-                if (u < len4) {
+                cur[u] = none;
+                vcur[2 * u] = vcur[2 * u + 1] = ones;
+                if (u < ng) {
                     cur[u] = ld_stream_int4(d + u * 32);
-                    if (HAS_VAL) vcur[u] = ld_stream_float4(dv + u * 32);
+                    if (HAS_VAL) {
+                        vcur[2 * u] = ld_stream_float4(dv + u * 64);
+                        vcur[2 * u + 1] = ld_stream_float4(dv + u * 64 + 1);
+                    }
                 }
             }
-            for (int g = 0; g < len4; g += U) {
+            for (int g = 0; g < ng; g += U) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {   // prefetch the next U groups while this batch is consumed
-                    nxt[u] = make_int4(-1, -1, -1, -1);
-                    vnxt[u] = ones;
-                    if (g + U + u < len4) {
+                    nxt[u] = none;
+                    vnxt[2 * u] = vnxt[2 * u + 1] = ones;
+                    if (g + U + u < ng) {
                         nxt[u] = ld_stream_int4(d + (g + U + u) * 32);
-                        if (HAS_VAL) vnxt[u] = ld_stream_float4(dv + (g + U + u) * 32);
+                        if (HAS_VAL) {
+                            vnxt[2 * u] = ld_stream_float4(dv + (g + U + u) * 64);
+                            vnxt[2 * u + 1] = ld_stream_float4(dv + (g + U + u) * 64 + 1);
+                        }
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < U; ++u) gather_four<B, HAS_VAL>(cur[u], vcur[u], tile1, tile2, a, b);
+                for (int u = 0; u < U; ++u)
+                    gather_eight<B, HAS_VAL>(cur[u], vcur[2 * u], vcur[2 * u + 1], tile1, tile2, a, b);
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     cur[u] = nxt[u];
-                    vcur[u] = vnxt[u];
+                    vcur[2 * u] = vnxt[2 * u];
+                    vcur[2 * u + 1] = vnxt[2 * u + 1];
                 }
             }
             if (row >= 0) {
@@ -244,8 +261,8 @@ reduce_tiles_kernel(const float* __restrict__ partial, int n_tiles, int64_t nrow
 }
 
 // ---- fp64 SpMV through the same format (prepare: row norms, column sums, degrees) ----
-// The dense operand is one fp64 vector, staged as 8-byte rows (tile_cols * 8 bytes per tile); an
-// entry's byte offset col * RB becomes col * 8 by a shift.  partial64[t][row] is written once.
+// The dense operand is one fp64 vector, staged as 8-byte rows (tile_cols * 8 bytes per tile).
+// partial64[t][row] is written once.
 //   SQ: the stored value is squared (row norms of the weighted rows).
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double v;
@@ -253,9 +270,9 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
     return v;
 }
 template <bool HAS_VAL, bool SQ>
-__device__ __forceinline__ void gather64(int e, float v, uint32_t tile, int sh, double& a) {
-    if (e >= 0) {
-        const double x = lds_f64(tile + (static_cast<uint32_t>(e) >> sh));
+__device__ __forceinline__ void gather64(uint32_t col, float v, uint32_t tile, double& a) {
+    if (col != 0xFFFFu) {
+        const double x = lds_f64(tile + col * 8u);
         if (HAS_VAL) {
             double dv = static_cast<double>(v);
             if (SQ) dv *= dv;
@@ -268,10 +285,10 @@ __device__ __forceinline__ void gather64(int e, float v, uint32_t tile, int sh, 
 
 template <bool HAS_VAL, bool SQ>
 __global__ void __launch_bounds__(kTiledThreads, 1)
-sell_spmv64_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restrict__ chunk_len4,
-                   const int64_t* __restrict__ chunk_off, const int32_t* __restrict__ data, const float* __restrict__ vals,
+sell_spmv64_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restrict__ chunk_groups,
+                   const int64_t* __restrict__ chunk_off, const uint16_t* __restrict__ data, const float* __restrict__ vals,
                    const double* __restrict__ in, double* __restrict__ partial, int64_t n_chunks, int64_t chunks_per_tile,
-                   int tile_cols, int64_t ncols, int64_t nrows, int sh) {
+                   int tile_cols, int64_t ncols, int64_t nrows) {
     constexpr int U = 2;
     extern __shared__ __align__(128) unsigned char smem[];
     double* tile = reinterpret_cast<double*>(smem);
@@ -315,28 +332,37 @@ sell_spmv64_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __rest
             const int64_t c = static_cast<int64_t>(__shfl_sync(0xffffffffu, cu, 0));
             if (c >= hi) break;
             const int row = chunk_rows[c * 32 + lane];
-            const int len4 = chunk_len4[c];
+            const int ng = chunk_groups[c];
             const int4* d = reinterpret_cast<const int4*>(data) + chunk_off[c] * 32 + lane;
-            const float4* dv = HAS_VAL ? reinterpret_cast<const float4*>(vals) + chunk_off[c] * 32 + lane : nullptr;
+            const float4* dv = HAS_VAL ? reinterpret_cast<const float4*>(vals) + chunk_off[c] * 64 + lane * 2 : nullptr;
             double a0 = 0.0, a1 = 0.0;   // two fixed chains
-            for (int g = 0; g < len4; g += U) {
+            for (int g = 0; g < ng; g += U) {
                 int4 e[U];
-                float4 v[U];
+                float4 v[2 * U];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     e[u] = make_int4(-1, -1, -1, -1);
-                    v[u] = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (g + u < len4) {
+                    v[2 * u] = v[2 * u + 1] = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (g + u < ng) {
                         e[u] = ld_stream_int4(d + (g + u) * 32);
-                        if (HAS_VAL) v[u] = ld_stream_float4(dv + (g + u) * 32);
+                        if (HAS_VAL) {
+                            v[2 * u] = ld_stream_float4(dv + (g + u) * 64);
+                            v[2 * u + 1] = ld_stream_float4(dv + (g + u) * 64 + 1);
+                        }
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    gather64<HAS_VAL, SQ>(e[u].x, v[u].x, tile_a, sh, a0);
-                    gather64<HAS_VAL, SQ>(e[u].y, v[u].y, tile_a, sh, a1);
-                    gather64<HAS_VAL, SQ>(e[u].z, v[u].z, tile_a, sh, a0);
-                    gather64<HAS_VAL, SQ>(e[u].w, v[u].w, tile_a, sh, a1);
+                    const uint32_t x = static_cast<uint32_t>(e[u].x), y = static_cast<uint32_t>(e[u].y);
+                    const uint32_t z = static_cast<uint32_t>(e[u].z), w = static_cast<uint32_t>(e[u].w);
+                    gather64<HAS_VAL, SQ>(x & 0xFFFFu, v[2 * u].x, tile_a, a0);
+                    gather64<HAS_VAL, SQ>(x >> 16, v[2 * u].y, tile_a, a1);
+                    gather64<HAS_VAL, SQ>(y & 0xFFFFu, v[2 * u].z, tile_a, a0);
+                    gather64<HAS_VAL, SQ>(y >> 16, v[2 * u].w, tile_a, a1);
+                    gather64<HAS_VAL, SQ>(z & 0xFFFFu, v[2 * u + 1].x, tile_a, a0);
+                    gather64<HAS_VAL, SQ>(z >> 16, v[2 * u + 1].y, tile_a, a1);
+                    gather64<HAS_VAL, SQ>(w & 0xFFFFu, v[2 * u + 1].z, tile_a, a0);
+                    gather64<HAS_VAL, SQ>(w >> 16, v[2 * u + 1].w, tile_a, a1);
                 }
             }
             if (row >= 0) part_t[row] = a0 + a1;
@@ -363,14 +389,14 @@ void spmm_impl(snapb200_ctx* c, const Sell& S, const float* in, float* out, cons
     const size_t smem = static_cast<size_t>(S.tile_cols) * 4 * B + 64;
     const int grid = c->num_sms;
     if (S.vals.p) {
-        auto k = sell_spmm_kernel<B, true, 2>;
+        auto k = sell_spmm_kernel<B, true, 1>;
         SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        k<<<grid, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p, S.data.p, S.vals.p, in,
+        k<<<grid, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_groups.p, S.chunk_off.p, S.data.p, S.vals.p, in,
                                             c->partial.p, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols, S.nrows);
     } else {
-        auto k = sell_spmm_kernel<B, false, 4>;
+        auto k = sell_spmm_kernel<B, false, 2>;
         SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        k<<<grid, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p, S.data.p, nullptr, in,
+        k<<<grid, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_groups.p, S.chunk_off.p, S.data.p, nullptr, in,
                                             c->partial.p, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols, S.nrows);
     }
     SB_LAUNCH_CHECK();
@@ -394,12 +420,15 @@ bool use_tiled(const snapb200_ctx* c, int b) {
 
 void ensure_tiled(snapb200_ctx* c, int b) {
     if (c->S1.built && c->S2.built && c->S1.b == b && c->S2.b == b) return;
+    // block width differs from the one prepare() built for: rebuild both copies
     cudaStream_t st = c->stream;
     SB_CUDA(cudaEventRecord(c->ev0, st));
     c->S1.clear();
     c->S2.clear();
     sell_build(c, c->X, c->S2, b);
-    sell_build(c, c->Xt, c->S1, b);
+    transpose_tiled(c, kSellTileBytes / (4 * b), nullptr);
+    sell_build_transposed(c, c->XtT, c->n_local, c->S1, b);
+    c->XtT.clear();
     SB_CUDA(cudaEventRecord(c->ev1, st));
     SB_CUDA(cudaEventSynchronize(c->ev1));
     float ms = 0.f;
@@ -416,15 +445,14 @@ void sell_spmv64(snapb200_ctx* c, const Sell& S, const double* x, int mode, cons
     c->partial.ensure(static_cast<int64_t>(S.n_tiles) * S.nrows * 2);
     double* part = reinterpret_cast<double*>(c->partial.p);
     const size_t smem = static_cast<size_t>(S.tile_cols) * 8 + 64;
-    const int sh = (S.b == 8) ? 2 : 1;   // entry = col * 4b bytes -> col * 8
     const bool sq = mode == 0;
 #define SB_SPMV64(HV, SQ)                                                                                              \
     do {                                                                                                               \
         auto k = sell_spmv64_kernel<HV, SQ>;                                                                           \
         SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));         \
-        k<<<c->num_sms, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_len4.p, S.chunk_off.p, S.data.p, S.vals.p,  \
-                                                   x, part, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols,       \
-                                                   S.nrows, sh);                                                       \
+        k<<<c->num_sms, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_groups.p, S.chunk_off.p, S.data.p,          \
+                                                   S.vals.p, x, part, S.n_chunks, S.chunks_per_tile, S.tile_cols,      \
+                                                   S.ncols, S.nrows);                                                  \
     } while (0)
     if (S.vals.p) { if (sq) SB_SPMV64(true, true); else SB_SPMV64(true, false); }
     else          SB_SPMV64(false, false);

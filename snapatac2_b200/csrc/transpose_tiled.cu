@@ -1,0 +1,425 @@
+// Tile-major 16-bit transpose of the pattern (struct TileT, ctx.cuh): the input
+// of the feature-major tiled copy S1 (pass 1 of the operator gathers over
+// features; reference: the X^T product inside f(v), embedding.rs:162-163).
+//
+// The local cells are cut into tiles of H rows (H = the column tile of S1, at
+// most 12288, so a tile-local cell id fits 16 bits).  For every (tile, feature)
+// the transpose lists the tile's cells that have the feature, in ascending
+// order.  Two streaming passes over the CSR rows, all the scattered work in
+// shared memory, no global atomics on data and a result that does not depend
+// on scheduling:
+//   count:   one unit = (tile, 65536-feature range): a shared-memory histogram
+//            (16-bit counters, integer atomics: order independent) -> cnt[t][j];
+//   offsets: exclusive scan of cnt[t][.] per tile, tile bases, local document
+//            frequencies df[j] = sum_t cnt[t][j];
+//   emit:    one unit = (tile, group of 1024-feature ranges).  A per-row cursor
+//            in shared memory walks the (sorted) rows range by range.  For each
+//            range and each sub-block of 1024 rows the CTA sets a 1024 x 1024
+//            feature x row bitmap in shared memory (one thread per row), then
+//            one thread per feature walks its 1024 bits in row order and appends
+//            the set rows to the feature's segment, eight ids (16 bytes) per store:
+//            segments start on 16-byte boundaries (lengths padded to multiples of
+//            eight), and the segments of a range are contiguous in the output
+//            (~250 KB at 1% density), so the appends merge in L2 before they reach HBM.
+// Units are handed out through an atomic counter (only the assignment of units
+// to CTAs depends on timing, never the output).
+#include "ctx.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace snapb {
+
+namespace {
+
+constexpr int kTtThreads = 1024;
+constexpr int kTtHist = 65536;     // features per counting unit (two 16-bit counters per word: 128 KB)
+constexpr int kTtRange = 1024;     // features per emit range (one thread each)
+constexpr int kTtSub = 1024;       // rows per emit sub-block (one thread each)
+constexpr int kTtMaxRows = 12288;  // cursor capacity = largest tile
+
+__device__ __forceinline__ int64_t lower_bound_idx(const int32_t* __restrict__ idx, int64_t lo, int64_t hi, int64_t key) {
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (static_cast<int64_t>(idx[mid]) < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// two 16-bit counters per word; an index outside the unit (unsorted input) is dropped and shows up
+// as a count mismatch on the host
+__device__ __forceinline__ void hist_add(uint32_t* hist, int k) {
+    if (static_cast<unsigned>(k) < static_cast<unsigned>(kTtHist)) atomicAdd(&hist[k >> 1], (k & 1) ? 0x10000u : 1u);
+}
+
+__global__ void __launch_bounds__(kTtThreads, 1)
+tile_count_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int64_t m, int H,
+                  int n_hr, int64_t n_units, uint16_t* __restrict__ cnt, unsigned long long* __restrict__ counter) {
+    extern __shared__ __align__(16) uint32_t hist[];   // kTtHist / 2 words
+    __shared__ long long s_unit;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    while (true) {
+        if (tid == 0) s_unit = static_cast<long long>(atomicAdd(counter, 1ull));
+        __syncthreads();
+        const int64_t u = s_unit;
+        if (u >= n_units) break;
+        const int64_t t = u / n_hr;
+        const int hr = static_cast<int>(u - t * n_hr);
+        const int64_t f0 = static_cast<int64_t>(hr) * kTtHist, f1 = min(m, f0 + kTtHist);
+        for (int i = tid; i < kTtHist / 2; i += kTtThreads) hist[i] = 0u;
+        __syncthreads();
+        const int64_t r_lo = t * H;
+        const int nr = static_cast<int>(min(static_cast<int64_t>(H), n - r_lo));
+        for (int rb = warp * 32; rb < nr; rb += kTtThreads) {
+            int64_t s0 = 0, s1 = 0;
+            if (rb + lane < nr) {   // one row per lane: its entries inside [f0, f1)
+                const int64_t rs = ptr[r_lo + rb + lane], re = ptr[r_lo + rb + lane + 1];
+                s0 = (f0 == 0) ? rs : lower_bound_idx(idx, rs, re, f0);
+                s1 = (f1 >= m) ? re : lower_bound_idx(idx, s0, re, f1);
+            }
+            const int rows_here = min(32, nr - rb);
+            for (int i = 0; i < rows_here; ++i) {   // the warp streams each of the 32 segments
+                const int64_t a = __shfl_sync(0xffffffffu, s0, i), b = __shfl_sync(0xffffffffu, s1, i);
+                int64_t p = a + lane;
+                for (; p + 96 < b; p += 128) {
+                    const int j0 = ld_stream_int(idx + p), j1 = ld_stream_int(idx + p + 32);
+                    const int j2 = ld_stream_int(idx + p + 64), j3 = ld_stream_int(idx + p + 96);
+                    const int k0 = j0 - static_cast<int>(f0), k1 = j1 - static_cast<int>(f0);
+                    const int k2 = j2 - static_cast<int>(f0), k3 = j3 - static_cast<int>(f0);
+                    hist_add(hist, k0);
+                    hist_add(hist, k1);
+                    hist_add(hist, k2);
+                    hist_add(hist, k3);
+                }
+                for (; p < b; p += 32) {
+                    const int k0 = ld_stream_int(idx + p) - static_cast<int>(f0);
+                    hist_add(hist, k0);
+                }
+            }
+        }
+        __syncthreads();
+        uint16_t* out = cnt + t * m + f0;
+        for (int i = tid; i < static_cast<int>(f1 - f0); i += kTtThreads) {
+            const uint32_t w = hist[i >> 1];
+            out[i] = static_cast<uint16_t>((i & 1) ? (w >> 16) : (w & 0xFFFFu));
+        }
+        __syncthreads();
+    }
+}
+
+// One CTA per tile: segoff[t][j] = exclusive scan of the segment lengths of tile t, each rounded up
+// to a multiple of 8 entries (16 bytes); tile_total[t] = padded size, tile_total[n_tiles + t] = entries.
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(const uint16_t* __restrict__ cnt, int64_t m, uint32_t* __restrict__ segoff,
+                 int64_t* __restrict__ tile_total) {
+    __shared__ uint32_t wsum[32];
+    __shared__ unsigned long long s_carry;
+    __shared__ unsigned long long s_raw[32];
+    const int64_t t = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0ull;
+    unsigned long long raw = 0ull;
+    __syncthreads();
+    for (int64_t j0 = 0; j0 < m; j0 += 1024) {
+        const int64_t j = j0 + tid;
+        const uint32_t c0 = (j < m) ? cnt[t * m + j] : 0u;
+        raw += c0;
+        const uint32_t v = (c0 + 7u) & ~7u;
+        uint32_t x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = wsum[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += y;
+            }
+            wsum[lane] = w;   // inclusive
+        }
+        __syncthreads();
+        const unsigned long long carry = s_carry;
+        const unsigned long long excl = carry + (warp > 0 ? wsum[warp - 1] : 0u) + (x - v);
+        // offsets beyond 2^32 - 1 are reported through tile_total (checked on the host)
+        if (j < m) segoff[t * m + j] = static_cast<uint32_t>(excl);
+        __syncthreads();
+        if (tid == 0) s_carry = carry + wsum[31];
+        __syncthreads();
+    }
+    // entries of the tile (fixed-order sum)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) raw += __shfl_down_sync(0xffffffffu, raw, d);
+    if (lane == 0) s_raw[warp] = raw;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned long long r = 0ull;
+        for (int w = 0; w < 32; ++w) r += s_raw[w];
+        tile_total[t] = static_cast<int64_t>(s_carry);
+        tile_total[gridDim.x + t] = static_cast<int64_t>(r);
+    }
+}
+
+__global__ void tile_df_kernel(const uint16_t* __restrict__ cnt, int64_t m, int n_tiles, int64_t* __restrict__ df) {
+    const int64_t j = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (j >= m) return;
+    int64_t s = 0;
+    for (int t = 0; t < n_tiles; ++t) s += cnt[static_cast<int64_t>(t) * m + j];
+    df[j] = s;
+}
+
+__global__ void __launch_bounds__(kTtThreads, 1)
+tile_emit_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t nnz, int64_t n, int64_t m,
+                 int H, int n_groups, int ranges_per_group, int n_ranges, int64_t n_units,
+                 const uint32_t* __restrict__ segoff, const int64_t* __restrict__ tile_base,
+                 uint16_t* __restrict__ ids, unsigned long long* __restrict__ counter) {
+    // bitmap word of (plane w, feature f): bm[w * kTtRange + f] -- plane w holds rows 32 w .. 32 w + 31
+    // of the sub-block (= warp w of the set phase, whose 32 lanes hit 32 random banks); the emit
+    // thread of feature f reads word f of every plane (consecutive threads, consecutive banks).
+    extern __shared__ __align__(16) uint32_t tt_smem[];
+    uint32_t* bm = tt_smem;                                    // 32 * kTtRange words (128 KB)
+    uint32_t* cur = tt_smem + 32 * kTtRange;                   // kTtMaxRows cursors (48 KB)
+    uint32_t* summary = cur + kTtMaxRows;                      // per feature: which planes have a bit (4 KB)
+    uint16_t* stg = reinterpret_cast<uint16_t*>(summary + kTtRange);   // [8][threads]: ids waiting for a full 16-byte unit
+    __shared__ long long s_unit;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 32 * kTtRange; i += kTtThreads) bm[i] = 0u;
+    summary[tid] = 0u;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_unit = static_cast<long long>(atomicAdd(counter, 1ull));
+        __syncthreads();
+        const int64_t u = s_unit;
+        if (u >= n_units) break;
+        const int64_t t = u / n_groups;
+        const int g = static_cast<int>(u - t * n_groups);
+        const int rg0 = g * ranges_per_group, rg1 = min(n_ranges, rg0 + ranges_per_group);
+        const int64_t r_lo = t * H;
+        const int nr = static_cast<int>(min(static_cast<int64_t>(H), n - r_lo));
+        const int64_t fg0 = static_cast<int64_t>(rg0) * kTtRange;
+        for (int lr = tid; lr < nr; lr += kTtThreads) {   // cursor = first entry of the row at or after the group
+            const int64_t rs = ptr[r_lo + lr], re = ptr[r_lo + lr + 1];
+            cur[lr] = (fg0 == 0) ? 0u : static_cast<uint32_t>(lower_bound_idx(idx, rs, re, fg0) - rs);
+        }
+        __syncthreads();
+        const int64_t tbase = tile_base[t];
+        for (int rg = rg0; rg < rg1; ++rg) {
+            const int fb = rg * kTtRange;
+            const int fe = static_cast<int>(min(m, static_cast<int64_t>(fb) + kTtRange));
+            const bool has_feature = fb + tid < fe;
+            // this thread's feature: next 16-byte unit of its segment, ids waiting for a full unit
+            uint4* out8 = reinterpret_cast<uint4*>(ids) + (has_feature ? ((tbase + segoff[t * m + fb + tid]) >> 3) : 0);
+            int nbuf = 0;
+            for (int sb = 0; sb < nr; sb += kTtSub) {
+                // ---- set: one thread per row of the sub-block, two aligned 16-byte index loads at a time.
+                //      The loops of both phases are warp-uniform (__any_sync) so the lanes stay converged.
+                {
+                    const int lr = sb + tid;
+                    int64_t pos = 0;
+                    int rem = 0;
+                    uint32_t c0 = 0u;
+                    if (lr < nr) {
+                        const int64_t rs = ptr[r_lo + lr], end = ptr[r_lo + lr + 1];
+                        c0 = cur[lr];
+                        pos = rs + c0;
+                        rem = static_cast<int>(end - pos);   // entries of the row not yet consumed
+                    }
+                    uint32_t* plane = bm + warp * kTtRange;
+                    const uint32_t bit = 1u << lane, wbit = 1u << warp;
+                    bool more = rem > 0;
+                    while (__any_sync(0xffffffffu, more)) {
+                        if (more) {
+                            const int64_t a = pos & ~static_cast<int64_t>(3);
+                            const int skip = static_cast<int>(pos - a);   // consumed earlier (alignment slack)
+                            int j[8];
+                            if (a + 7 < nnz) {
+                                const int4 v0 = *reinterpret_cast<const int4*>(idx + a);
+                                const int4 v1 = *reinterpret_cast<const int4*>(idx + a + 4);
+                                j[0] = v0.x; j[1] = v0.y; j[2] = v0.z; j[3] = v0.w;
+                                j[4] = v1.x; j[5] = v1.y; j[6] = v1.z; j[7] = v1.w;
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 8; ++q) j[q] = (a + q < nnz) ? idx[a + q] : 0x7fffffff;
+                            }
+                            const int avail = min(8 - skip, rem);
+                            int took = 0;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) {
+                                const int e = q - skip;
+                                if (e >= 0 && e == took && e < avail && j[q] < fe) {   // stops at the first entry past the range
+                                    const int f = j[q] - fb;
+                                    if (f >= 0) {
+                                        atomicOr(plane + f, bit);
+                                        atomicOr(summary + f, wbit);
+                                    }
+                                    ++took;
+                                }
+                            }
+                            c0 += took;
+                            rem -= took;
+                            pos = a + 8;
+                            more = (took == 8 - skip) && rem > 0;
+                        }
+                    }
+                    if (lr < nr) cur[lr] = c0;
+                }
+                __syncthreads();
+                // ---- emit: one thread per feature, rows in ascending order.  One loop iteration per set
+                //      bit; the planes without a bit are skipped through the summary word.
+                {
+                    uint32_t nz = 0u;
+                    if (has_feature) {
+                        nz = summary[tid];
+                        summary[tid] = 0u;
+                    }
+                    uint32_t word = 0u, row0 = 0u;
+                    bool act = nz != 0u;
+                    while (__any_sync(0xffffffffu, act)) {
+                        if (act) {
+                            if (word == 0u) {
+                                const int k = __ffs(nz) - 1;
+                                nz &= nz - 1;
+                                word = bm[k * kTtRange + tid];
+                                bm[k * kTtRange + tid] = 0u;
+                                row0 = static_cast<uint32_t>(sb + k * 32);
+                            }
+                            stg[nbuf * kTtThreads + tid] = static_cast<uint16_t>(row0 + (__ffs(word) - 1));
+                            word &= word - 1;
+                            if (++nbuf == 8) {
+                                uint32_t pk[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q)
+                                    pk[q] = static_cast<uint32_t>(stg[(2 * q) * kTtThreads + tid]) |
+                                            (static_cast<uint32_t>(stg[(2 * q + 1) * kTtThreads + tid]) << 16);
+                                *out8++ = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                                nbuf = 0;
+                            }
+                            act = (word | nz) != 0u;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+            if (nbuf > 0) {   // last, partial unit of the segment (the padding slots are never read)
+                uint32_t pk[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t a = (2 * q < nbuf) ? stg[(2 * q) * kTtThreads + tid] : 0u;
+                    const uint32_t b = (2 * q + 1 < nbuf) ? stg[(2 * q + 1) * kTtThreads + tid] : 0u;
+                    pk[q] = a | (b << 16);
+                }
+                *out8 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+        }
+    }
+}
+
+// values of the transposed entries (values path only): one warp per (tile, feature) segment
+__global__ void __launch_bounds__(256)
+tile_vals_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
+                 int64_t m, int H, int n_tiles, const uint16_t* __restrict__ cnt, const uint32_t* __restrict__ segoff,
+                 const int64_t* __restrict__ tile_base, const uint16_t* __restrict__ ids, float* __restrict__ tvals) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nseg = static_cast<int64_t>(n_tiles) * m;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t sg = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; sg < nseg; sg += nwarps) {
+        const int len = cnt[sg];
+        if (len == 0) continue;
+        const int64_t t = sg / m;
+        const int64_t j = sg - t * m;
+        const int64_t s = tile_base[t] + segoff[sg];
+        for (int k = lane; k < len; k += 32) {
+            const int64_t r = t * H + ids[s + k];
+            tvals[s + k] = val[lower_bound_idx(idx, ptr[r], ptr[r + 1], j)];
+        }
+    }
+}
+
+}  // namespace
+
+void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
+    SB_CHECK(tile_rows > 0 && tile_rows <= kTtMaxRows, "transpose_tiled: bad tile height");
+    const Csr& X = c->X;
+    TileT& T = c->XtT;
+    cudaStream_t st = c->stream;
+    const int64_t n = X.nrows, m = c->m;
+    T.clear();
+    T.tile_rows = tile_rows;
+    T.n_tiles = static_cast<int>(std::max<int64_t>(1, ceil_div(n, tile_rows)));
+    T.m = m;
+    T.nnz = X.nnz;
+    const int nt = T.n_tiles;
+    T.cnt.alloc(static_cast<int64_t>(nt) * m);
+    T.segoff.alloc(static_cast<int64_t>(nt) * m);
+    T.tile_base.alloc(nt + 1);
+    DevBuf<unsigned long long> counter;
+    DevBuf<int64_t> totals;
+    counter.alloc(2);
+    totals.alloc(2 * nt);
+    SB_CUDA(cudaMemsetAsync(counter.p, 0, 2 * sizeof(unsigned long long), st));
+
+    // ---- count
+    {
+        const int n_hr = static_cast<int>(ceil_div(m, kTtHist));
+        const int64_t n_units = static_cast<int64_t>(nt) * n_hr;
+        const size_t smem = static_cast<size_t>(kTtHist / 2) * sizeof(uint32_t);
+        SB_CUDA(cudaFuncSetAttribute(tile_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const int grid = static_cast<int>(std::min<int64_t>(n_units, c->num_sms));
+        tile_count_kernel<<<grid, kTtThreads, smem, st>>>(X.ptr.p, X.idx.p, n, m, tile_rows, n_hr, n_units, T.cnt.p,
+                                                          counter.p);
+        SB_LAUNCH_CHECK();
+    }
+    // ---- offsets, tile bases, document frequencies
+    tile_scan_kernel<<<nt, 1024, 0, st>>>(T.cnt.p, m, T.segoff.p, totals.p);
+    SB_LAUNCH_CHECK();
+    if (df_local) {
+        tile_df_kernel<<<static_cast<unsigned>(ceil_div(m, 256)), 256, 0, st>>>(T.cnt.p, m, nt, df_local);
+        SB_LAUNCH_CHECK();
+    }
+    std::vector<int64_t> ht(2 * nt), hb(nt + 1);
+    SB_CUDA(cudaMemcpyAsync(ht.data(), totals.p, sizeof(int64_t) * 2 * nt, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    hb[0] = 0;
+    int64_t counted = 0;
+    for (int t = 0; t < nt; ++t) {
+        SB_CHECK(ht[t] < (1ll << 32), "transpose_tiled: more than 2^32 stored entries in one cell tile");
+        hb[t + 1] = hb[t] + ht[t];
+        counted += ht[nt + t];
+    }
+    SB_CHECK(counted == X.nnz, "transpose_tiled: count mismatch (column index out of range or unsorted rows?)");
+    SB_CUDA(cudaMemcpyAsync(T.tile_base.p, hb.data(), sizeof(int64_t) * (nt + 1), cudaMemcpyHostToDevice, st));
+    T.ids.alloc(hb[nt] + 8);   // segments padded to 16-byte units
+
+    // ---- emit
+    if (X.nnz > 0) {
+        const int n_ranges = static_cast<int>(ceil_div(m, kTtRange));
+        int groups = static_cast<int>(std::min<int64_t>(n_ranges, std::max<int64_t>(1, ceil_div(4 * c->num_sms, nt))));
+        const int rpg = static_cast<int>(ceil_div(n_ranges, groups));
+        groups = static_cast<int>(ceil_div(n_ranges, rpg));
+        const int64_t n_units = static_cast<int64_t>(nt) * groups;
+        const size_t smem = (static_cast<size_t>(32) * kTtRange + kTtMaxRows + kTtRange) * sizeof(uint32_t) +
+                            static_cast<size_t>(8) * kTtThreads * sizeof(uint16_t);
+        SB_CUDA(cudaFuncSetAttribute(tile_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const int grid = static_cast<int>(std::min<int64_t>(n_units, c->num_sms));
+        tile_emit_kernel<<<grid, kTtThreads, smem, st>>>(X.ptr.p, X.idx.p, X.nnz, n, m, tile_rows, groups, rpg, n_ranges,
+                                                         n_units, T.segoff.p, T.tile_base.p, T.ids.p, counter.p + 1);
+        SB_LAUNCH_CHECK();
+        if (X.has_values()) {
+            T.vals.alloc(hb[nt] + 8);
+            const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(static_cast<int64_t>(nt) * m, 8),
+                                                                  static_cast<int64_t>(c->num_sms) * 16));
+            tile_vals_kernel<<<blocks, 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, m, tile_rows, nt, T.cnt.p, T.segoff.p,
+                                                     T.tile_base.p, T.ids.p, T.vals.p);
+            SB_LAUNCH_CHECK();
+        }
+    }
+    count_launch(c, 5);
+    SB_CUDA(cudaStreamSynchronize(st));   // hb / counters stay alive until the copies and kernels are done
+    T.built = true;
+}
+
+}  // namespace snapb

@@ -181,8 +181,7 @@ class Engine:
 
     def set_spmm_mode(self, mode: str | int):
         """'auto' | 'csr' (gather out of L2) | 'tiled' (shared-memory sliced-ELL)."""
-        code = {"auto": 0, "csr": 1, "tiled": 2, "auto+matched": 8, "tiled+matched": 10,
-                "auto+plain": 16, "tiled+plain": 18}.get(mode, mode)
+        code = {"auto": 0, "csr": 1, "tiled": 2}.get(mode, mode)
         _lib.check(self._lib.snapb200_set_spmm_mode(self._ctx, int(code)))
 
     def set_block(self, block: int):

@@ -36,7 +36,7 @@ def test_tiled_operator_matches_oracle_and_csr_path(engine, valued, block):
     got = {}
     engine.set_block(block)
     try:
-        for mode in ("csr", "tiled", "tiled+matched"):
+        for mode in ("csr", "tiled"):
             engine.set_spmm_mode(mode)
             engine.load_csr(X, binarized=not valued)
             engine.set_feature_weights(None)
@@ -51,7 +51,58 @@ def test_tiled_operator_matches_oracle_and_csr_path(engine, valued, block):
             # bitwise repeatable (no atomics anywhere on the path)
             np.testing.assert_array_equal(engine.operator_apply(V), Y)
         assert np.abs(got["csr"] - got["tiled"]).max() / np.abs(want).max() < 1e-5
-        assert np.abs(got["csr"] - got["tiled+matched"]).max() / np.abs(want).max() < 1e-5
+    finally:
+        engine.set_spmm_mode("auto")
+        engine.set_block(4)
+
+
+@pytest.mark.parametrize("valued,block", [(False, 4), (True, 4), (False, 8)])
+def test_tiled_long_and_single_class_segments(engine, valued, block):
+    """Format-build edge cases: segments longer than one 256-entry piece (dense rows, features
+    present in most cells), segments whose columns all fall into one shared-memory bank class
+    (every rotation slot but one class stays empty: the overflow list and its re-walk), empty
+    segments, and a ragged last window."""
+    rng = np.random.default_rng(3)
+    n, m = 9001, 26003
+    rows, cols = [], []
+    for i in range(n):
+        kind = i % 7
+        if kind == 0:      # long: ~1500 entries in the first feature tile
+            c = rng.choice(6000, size=1500, replace=False)
+        elif kind == 1:    # one bank class only: multiples of 8 (and of 4)
+            c = 8 * rng.choice(m // 8, size=300, replace=False)
+        elif kind == 2:    # very short
+            c = rng.choice(m, size=3, replace=False)
+        else:
+            c = rng.choice(m, size=120, replace=False)
+        rows.append(np.full(c.size, i))
+        cols.append(c)
+    # features seen by (almost) every cell, and one seen by every 8th cell only
+    for j in (5, 17, 12290):
+        keep = rng.random(n) < 0.9
+        rows.append(np.nonzero(keep)[0]); cols.append(np.full(int(keep.sum()), j))
+    rows.append(np.arange(0, n, 8)); cols.append(np.full(len(range(0, n, 8)), 26000))
+    r, cidx = np.concatenate(rows), np.concatenate(cols)
+    X = sp.csr_matrix((np.ones(r.size), (r, cidx)), shape=(n, m))
+    X.sum_duplicates()
+    X.data[:] = 1.0
+    if valued:
+        X.data = rng.integers(1, 5, size=X.nnz).astype(np.float64)
+    xt, dinv, w, deg = _oracle_operator(X)
+    V = rng.standard_normal((n, block)).astype(np.float32)
+    want = xt @ (xt.T @ V.astype(np.float64)) - dinv[:, None] * V
+    engine.set_block(block)
+    engine.set_spmm_mode("tiled")
+    try:
+        engine.load_csr(X, binarized=not valued)
+        engine.set_feature_weights(None)
+        idf, degree = engine.prepare()
+        np.testing.assert_allclose(idf, w, rtol=1e-5)
+        np.testing.assert_allclose(degree, deg, rtol=1e-5)
+        Y = engine.operator_apply(V)
+        assert engine.stats()["spmm_tiled"] == 1
+        assert np.abs(Y - want).max() / np.abs(want).max() < 2e-5
+        np.testing.assert_array_equal(engine.operator_apply(V), Y)
     finally:
         engine.set_spmm_mode("auto")
         engine.set_block(4)
