@@ -17,10 +17,11 @@
 //            range and each sub-block of 1024 rows the CTA sets a 1024 x 1024
 //            feature x row bitmap in shared memory (one thread per row), then
 //            one thread per feature walks its 1024 bits in row order and appends
-//            the set rows to the feature's segment, eight ids (16 bytes) per store:
-//            segments start on 16-byte boundaries (lengths padded to multiples of
-//            eight), and the segments of a range are contiguous in the output
-//            (~250 KB at 1% density), so the appends merge in L2 before they reach HBM.
+//            the set rows to the feature's segment.  Segments start on 16-byte
+//            boundaries (lengths padded to multiples of eight, so the format
+//            build reads them with aligned vector loads); the segments of a range
+//            are contiguous in the output (~250 KB at 1% density), so the appends
+//            merge in L2 before they reach HBM.
 // Units are handed out through an atomic counter (only the assignment of units
 // to CTAs depends on timing, never the output).
 #include "ctx.cuh"
@@ -34,8 +35,6 @@ namespace {
 
 constexpr int kTtThreads = 1024;
 constexpr int kTtHist = 65536;     // features per counting unit (two 16-bit counters per word: 128 KB)
-constexpr int kTtRange = 1024;     // features per emit range (one thread each)
-constexpr int kTtSub = 1024;       // rows per emit sub-block (one thread each)
 constexpr int kTtMaxRows = 12288;  // cursor capacity = largest tile
 
 __device__ __forceinline__ int64_t lower_bound_idx(const int32_t* __restrict__ idx, int64_t lo, int64_t hi, int64_t key) {
@@ -172,23 +171,34 @@ __global__ void tile_df_kernel(const uint16_t* __restrict__ cnt, int64_t m, int 
     df[j] = s;
 }
 
+// ---- emit ------------------------------------------------------------------
+// One unit = (cell tile, group of 1024-feature ranges).  A per-row cursor in shared memory walks
+// the (sorted) rows range by range.  For each range and each sub-block of 1024 rows the CTA sets
+// a 1024 x 1024 feature x row bitmap in shared memory (one thread per row), then one thread per
+// feature walks its 1024 bits in row order and appends the set rows to the feature's segment.
+// The segments of a range are contiguous in the output (~250 KB at 1% density), so the small
+// appends merge in L2 before they reach HBM.
+// (Tried and slower on the C3 workload, whose feature popularity is heavily skewed -- see
+// profiles/README.md: a warp-uniform bit loop with a per-feature plane summary, an entry-parallel
+// variant with per-feature row masks and two barriers per 32 rows, and a barrier-free variant
+// with one unit per warp.)
+constexpr int kTtRange = 1024;     // features per emit range (one thread each)
+constexpr int kTtSub = 1024;       // rows per emit sub-block (one thread each)
+
 __global__ void __launch_bounds__(kTtThreads, 1)
-tile_emit_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t nnz, int64_t n, int64_t m,
-                 int H, int n_groups, int ranges_per_group, int n_ranges, int64_t n_units,
+tile_emit_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int64_t m, int H,
+                 int n_groups, int ranges_per_group, int n_ranges, int64_t n_units,
                  const uint32_t* __restrict__ segoff, const int64_t* __restrict__ tile_base,
                  uint16_t* __restrict__ ids, unsigned long long* __restrict__ counter) {
-    // bitmap word of (plane w, feature f): bm[w * kTtRange + f] -- plane w holds rows 32 w .. 32 w + 31
-    // of the sub-block (= warp w of the set phase, whose 32 lanes hit 32 random banks); the emit
-    // thread of feature f reads word f of every plane (consecutive threads, consecutive banks).
+    // bitmap word of (plane w, feature f): bm[((w >> 2) * kTtRange + f) * 4 + (w & 3)] -- plane w holds
+    // rows 32 w .. 32 w + 31 of the sub-block (= warp w of the set phase); the emit thread of
+    // feature f reads four planes with one 16-byte load.
     extern __shared__ __align__(16) uint32_t tt_smem[];
     uint32_t* bm = tt_smem;                                    // 32 * kTtRange words (128 KB)
     uint32_t* cur = tt_smem + 32 * kTtRange;                   // kTtMaxRows cursors (48 KB)
-    uint32_t* summary = cur + kTtMaxRows;                      // per feature: which planes have a bit (4 KB)
-    uint16_t* stg = reinterpret_cast<uint16_t*>(summary + kTtRange);   // [8][threads]: ids waiting for a full 16-byte unit
     __shared__ long long s_unit;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 32 * kTtRange; i += kTtThreads) bm[i] = 0u;
-    summary[tid] = 0u;
     while (true) {
         __syncthreads();
         if (tid == 0) s_unit = static_cast<long long>(atomicAdd(counter, 1ull));
@@ -211,108 +221,57 @@ tile_emit_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
             const int fb = rg * kTtRange;
             const int fe = static_cast<int>(min(m, static_cast<int64_t>(fb) + kTtRange));
             const bool has_feature = fb + tid < fe;
-            // this thread's feature: next 16-byte unit of its segment, ids waiting for a full unit
-            uint4* out8 = reinterpret_cast<uint4*>(ids) + (has_feature ? ((tbase + segoff[t * m + fb + tid]) >> 3) : 0);
-            int nbuf = 0;
+            int64_t outpos = has_feature ? tbase + segoff[t * m + fb + tid] : 0;
             for (int sb = 0; sb < nr; sb += kTtSub) {
-                // ---- set: one thread per row of the sub-block, two aligned 16-byte index loads at a time.
-                //      The loops of both phases are warp-uniform (__any_sync) so the lanes stay converged.
-                {
-                    const int lr = sb + tid;
-                    int64_t pos = 0;
-                    int rem = 0;
-                    uint32_t c0 = 0u;
-                    if (lr < nr) {
-                        const int64_t rs = ptr[r_lo + lr], end = ptr[r_lo + lr + 1];
-                        c0 = cur[lr];
-                        pos = rs + c0;
-                        rem = static_cast<int>(end - pos);   // entries of the row not yet consumed
-                    }
-                    uint32_t* plane = bm + warp * kTtRange;
-                    const uint32_t bit = 1u << lane, wbit = 1u << warp;
-                    bool more = rem > 0;
-                    while (__any_sync(0xffffffffu, more)) {
-                        if (more) {
-                            const int64_t a = pos & ~static_cast<int64_t>(3);
-                            const int skip = static_cast<int>(pos - a);   // consumed earlier (alignment slack)
-                            int j[8];
-                            if (a + 7 < nnz) {
-                                const int4 v0 = *reinterpret_cast<const int4*>(idx + a);
-                                const int4 v1 = *reinterpret_cast<const int4*>(idx + a + 4);
-                                j[0] = v0.x; j[1] = v0.y; j[2] = v0.z; j[3] = v0.w;
-                                j[4] = v1.x; j[5] = v1.y; j[6] = v1.z; j[7] = v1.w;
+                // ---- set: one thread per row of the sub-block
+                const int lr = sb + tid;
+                if (lr < nr) {
+                    const int64_t rs = ptr[r_lo + lr], end = ptr[r_lo + lr + 1];
+                    uint32_t c0 = cur[lr];
+                    int64_t pos = rs + c0;
+                    uint32_t* plane = bm + (static_cast<size_t>(warp >> 2) * kTtRange) * 4 + (warp & 3);
+                    const uint32_t bit = 1u << lane;
+                    bool more = pos < end;
+                    while (more) {
+                        int j[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) j[q] = (pos + q < end) ? idx[pos + q] : 0x7fffffff;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            if (more && j[q] < fe) {
+                                if (j[q] >= fb) atomicOr(plane + static_cast<size_t>(j[q] - fb) * 4, bit);
+                                ++c0;
                             } else {
-#pragma unroll
-                                for (int q = 0; q < 8; ++q) j[q] = (a + q < nnz) ? idx[a + q] : 0x7fffffff;
+                                more = false;
                             }
-                            const int avail = min(8 - skip, rem);
-                            int took = 0;
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const int e = q - skip;
-                                if (e >= 0 && e == took && e < avail && j[q] < fe) {   // stops at the first entry past the range
-                                    const int f = j[q] - fb;
-                                    if (f >= 0) {
-                                        atomicOr(plane + f, bit);
-                                        atomicOr(summary + f, wbit);
-                                    }
-                                    ++took;
-                                }
-                            }
-                            c0 += took;
-                            rem -= took;
-                            pos = a + 8;
-                            more = (took == 8 - skip) && rem > 0;
                         }
+                        pos += 8;
                     }
-                    if (lr < nr) cur[lr] = c0;
+                    cur[lr] = c0;
                 }
                 __syncthreads();
-                // ---- emit: one thread per feature, rows in ascending order.  One loop iteration per set
-                //      bit; the planes without a bit are skipped through the summary word.
-                {
-                    uint32_t nz = 0u;
-                    if (has_feature) {
-                        nz = summary[tid];
-                        summary[tid] = 0u;
-                    }
-                    uint32_t word = 0u, row0 = 0u;
-                    bool act = nz != 0u;
-                    while (__any_sync(0xffffffffu, act)) {
-                        if (act) {
-                            if (word == 0u) {
-                                const int k = __ffs(nz) - 1;
-                                nz &= nz - 1;
-                                word = bm[k * kTtRange + tid];
-                                bm[k * kTtRange + tid] = 0u;
-                                row0 = static_cast<uint32_t>(sb + k * 32);
-                            }
-                            stg[nbuf * kTtThreads + tid] = static_cast<uint16_t>(row0 + (__ffs(word) - 1));
-                            word &= word - 1;
-                            if (++nbuf == 8) {
-                                uint32_t pk[4];
+                // ---- emit: one thread per feature, rows in ascending order
+                if (has_feature) {
+                    uint4* mine = reinterpret_cast<uint4*>(bm) + tid;
+#pragma unroll 1
+                    for (int g8 = 0; g8 < 8; ++g8) {
+                        const uint4 w4 = mine[g8 * kTtRange];
+                        if ((w4.x | w4.y | w4.z | w4.w) == 0u) continue;
+                        mine[g8 * kTtRange] = make_uint4(0u, 0u, 0u, 0u);
+                        const uint32_t ww[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                                for (int q = 0; q < 4; ++q)
-                                    pk[q] = static_cast<uint32_t>(stg[(2 * q) * kTtThreads + tid]) |
-                                            (static_cast<uint32_t>(stg[(2 * q + 1) * kTtThreads + tid]) << 16);
-                                *out8++ = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-                                nbuf = 0;
+                        for (int k = 0; k < 4; ++k) {
+                            uint32_t word = ww[k];
+                            const int row0 = sb + (g8 * 4 + k) * 32;
+                            while (word) {
+                                const int b = __ffs(word) - 1;
+                                word &= word - 1;
+                                ids[outpos++] = static_cast<uint16_t>(row0 + b);
                             }
-                            act = (word | nz) != 0u;
                         }
                     }
                 }
                 __syncthreads();
-            }
-            if (nbuf > 0) {   // last, partial unit of the segment (the padding slots are never read)
-                uint32_t pk[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const uint32_t a = (2 * q < nbuf) ? stg[(2 * q) * kTtThreads + tid] : 0u;
-                    const uint32_t b = (2 * q + 1 < nbuf) ? stg[(2 * q + 1) * kTtThreads + tid] : 0u;
-                    pk[q] = a | (b << 16);
-                }
-                *out8 = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
         }
     }
@@ -401,12 +360,11 @@ void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
         const int rpg = static_cast<int>(ceil_div(n_ranges, groups));
         groups = static_cast<int>(ceil_div(n_ranges, rpg));
         const int64_t n_units = static_cast<int64_t>(nt) * groups;
-        const size_t smem = (static_cast<size_t>(32) * kTtRange + kTtMaxRows + kTtRange) * sizeof(uint32_t) +
-                            static_cast<size_t>(8) * kTtThreads * sizeof(uint16_t);
+        const size_t smem = (static_cast<size_t>(32) * kTtRange + kTtMaxRows) * sizeof(uint32_t);
         SB_CUDA(cudaFuncSetAttribute(tile_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         const int grid = static_cast<int>(std::min<int64_t>(n_units, c->num_sms));
-        tile_emit_kernel<<<grid, kTtThreads, smem, st>>>(X.ptr.p, X.idx.p, X.nnz, n, m, tile_rows, groups, rpg, n_ranges,
-                                                         n_units, T.segoff.p, T.tile_base.p, T.ids.p, counter.p + 1);
+        tile_emit_kernel<<<grid, kTtThreads, smem, st>>>(X.ptr.p, X.idx.p, n, m, tile_rows, groups, rpg, n_ranges, n_units,
+                                                         T.segoff.p, T.tile_base.p, T.ids.p, counter.p + 1);
         SB_LAUNCH_CHECK();
         if (X.has_values()) {
             T.vals.alloc(hb[nt] + 8);
