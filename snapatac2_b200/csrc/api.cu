@@ -253,7 +253,11 @@ int snapb200_destroy(snapb200_ctx* c) {
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
         cudaStream_t st = c->stream;
+        // everything on the stream is done: the context's buffers go back to the pool as quiesced
+        // blocks (no event), and blocks parked earlier must stop referring to the stream
+        pool_set_stream(nullptr);
         delete c;
+        pool_forget_stream(st);
         if (st) cudaStreamDestroy(st);
     });
 }

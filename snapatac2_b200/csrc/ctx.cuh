@@ -13,6 +13,7 @@ void* pool_alloc(size_t bytes);
 void pool_free(void* p);
 void pool_trim();
 void pool_set_stream(cudaStream_t s);
+void pool_forget_stream(cudaStream_t s);   // before cudaStreamDestroy
 void pool_counters(long long* mallocs, long long* reuses, long long* trims, double* ms);
 
 // Owning device buffer (released to the pool with the context or on reassignment).

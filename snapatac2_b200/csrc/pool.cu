@@ -124,8 +124,31 @@ void pool_free(void* p) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaEvent_t ev = nullptr;
-    if (t_stream && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(ev, t_stream);
+    if (t_stream) {
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(ev, t_stream);
+    } else {
+        cudaDeviceSynchronize();   // no stream to order later users after: park the block fully quiesced
+    }
     P.parked[dev].emplace(sz, Parked{p, t_stream, ev});
+}
+
+// A stream is about to be destroyed (its work has been synchronised by the caller): parked blocks
+// must not refer to it any more.
+void pool_forget_stream(cudaStream_t s) {
+    Pool& P = pool();
+    std::lock_guard<std::mutex> lock(P.mu);
+    for (auto& dev : P.parked) {
+        for (auto& kv : dev.second) {
+            if (kv.second.stream != s) continue;
+            if (kv.second.ev) {
+                cudaEventSynchronize(kv.second.ev);
+                cudaEventDestroy(kv.second.ev);
+            }
+            kv.second.ev = nullptr;
+            kv.second.stream = nullptr;
+        }
+    }
+    if (t_stream == s) t_stream = nullptr;
 }
 
 void pool_counters(long long* mallocs, long long* reuses, long long* trims, double* ms) {

@@ -207,3 +207,26 @@ def test_multi_spectral_sampled_normaliser(engine):
     ev_o, evec_o = oracle.multi_spectral_embedding([atac, rna], [None, None], [1.0, 1.0], 6, 0, sample_rows=rows)
     evals, evecs = tl.multi_spectral_embedding(engine, [atac, rna], [None, None], [1.0, 1.0], 6, 0, sample_rows=rows)
     _check_against(ev_o, evec_o, evals, evecs)
+
+
+def test_second_context_lifetime(engine):
+    """Two contexts in one process share the caching allocator: destroying one (and its stream)
+    must leave the other usable, and blocks it parked reusable (regression: a parked block kept
+    the destroyed stream and the next release recorded an event on it)."""
+    from snapatac2_b200 import Engine
+    spec = synth.make_spec(3000, 20000, 300, n_clusters=24, seed=11)
+    engine.generate(spec)
+    engine.set_feature_weights(None)
+    idf0, deg0 = engine.prepare()
+    other = Engine(engine.device)
+    other.generate(spec)
+    idf1, deg1 = other.prepare()
+    ev1, _ = other.eigsh(8, seed=0)
+    other.close()
+    np.testing.assert_array_equal(idf0, idf1)
+    np.testing.assert_array_equal(deg0, deg1)
+    ev0, _ = engine.eigsh(8, seed=0)      # reuses blocks the closed context parked
+    np.testing.assert_array_equal(ev0, ev1)
+    third = Engine(engine.device)
+    third.generate(spec)
+    third.close()
