@@ -39,6 +39,7 @@ CONFIGS = {
     "c3": (1_000_000, 500_000, 5_000, 48, 30),
     "c4": (10_000_000, 500_000, 3_000, 64, 50),
     "tiny": (2_000, 20_000, 500, 40, 30),
+    "c3s": (125_000, 500_000, 5_000, 48, 30),   # the size of one rank's shard of c3 at 8 GPUs (tuning aid)
 }
 CONFIG_TEXT = {
     "c1": "synthetic 5k-cell x 100k-bin binarised tile matrix (~3k nnz/cell), n_comps=30",
@@ -46,6 +47,7 @@ CONFIG_TEXT = {
     "c3": "synthetic 1M cells x 500k bins (~5k nnz/cell), n_comps=30, row-sharded",
     "c4": "synthetic 10M cells x 500k bins (~3k nnz/cell), n_comps=50, row-sharded",
     "tiny": "synthetic 2k x 20k (~500 nnz/cell), n_comps=30 (harness test only)",
+    "c3s": "synthetic 125k cells x 500k bins (~5k nnz/cell), n_comps=30 (one rank's share of c3 at 8 GPUs; tuning aid)",
 }
 METRIC = "snap.tl.spectral cells/s"
 CPU_SAMPLE_ROWS = 4000

@@ -186,19 +186,24 @@ constexpr int kTtRange = 1024;     // features per emit range (one thread each)
 constexpr int kTtSub = 1024;       // rows per emit sub-block (one thread each)
 
 __global__ void __launch_bounds__(kTtThreads, 1)
-tile_emit_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int64_t m, int H,
-                 int n_groups, int ranges_per_group, int n_ranges, int64_t n_units,
-                 const uint32_t* __restrict__ segoff, const int64_t* __restrict__ tile_base,
-                 uint16_t* __restrict__ ids, unsigned long long* __restrict__ counter) {
+tile_emit_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t nnz, int64_t n, int64_t m,
+                 int H, int n_groups, int ranges_per_group, int n_ranges, int64_t n_units,
+                 const uint16_t* __restrict__ cnt, const uint32_t* __restrict__ segoff,
+                 const int64_t* __restrict__ tile_base, uint16_t* __restrict__ ids,
+                 unsigned long long* __restrict__ counter) {
     // bitmap word of (plane w, feature f): bm[((w >> 2) * kTtRange + f) * 4 + (w & 3)] -- plane w holds
     // rows 32 w .. 32 w + 31 of the sub-block (= warp w of the set phase); the emit thread of
     // feature f reads four planes with one 16-byte load.
     extern __shared__ __align__(16) uint32_t tt_smem[];
     uint32_t* bm = tt_smem;                                    // 32 * kTtRange words (128 KB)
     uint32_t* cur = tt_smem + 32 * kTtRange;                   // kTtMaxRows cursors (48 KB)
+    uint32_t* opos = cur + kTtMaxRows;                         // kTtRange: next free slot of a segment (tile relative)
+    uint16_t* plist = reinterpret_cast<uint16_t*>(opos + kTtRange);   // kTtRange: the range's popular features
     __shared__ long long s_unit;
+    __shared__ int s_npop;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 32 * kTtRange; i += kTtThreads) bm[i] = 0u;
+    if (tid == 0) s_npop = 0;
     while (true) {
         __syncthreads();
         if (tid == 0) s_unit = static_cast<long long>(atomicAdd(counter, 1ull));
@@ -221,37 +226,65 @@ tile_emit_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
             const int fb = rg * kTtRange;
             const int fe = static_cast<int>(min(m, static_cast<int64_t>(fb) + kTtRange));
             const bool has_feature = fb + tid < fe;
-            int64_t outpos = has_feature ? tbase + segoff[t * m + fb + tid] : 0;
+            // Feature popularity is heavily skewed: a thread that walked a popular feature's bits alone
+            // would hold its whole warp up.  Features with more than ~24 cells per sub-block in this
+            // tile are listed and emitted by a whole warp each (one lane per bitmap plane).
+            const int n_sub = (nr + kTtSub - 1) / kTtSub;
+            bool popular = false;
+            if (tid == 0) s_npop = 0;
+            __syncthreads();
+            if (has_feature) {
+                opos[tid] = segoff[t * m + fb + tid];
+                popular = static_cast<int>(cnt[t * m + fb + tid]) > 24 * n_sub;
+                if (popular) plist[atomicAdd(&s_npop, 1)] = static_cast<uint16_t>(tid);   // order irrelevant
+            }
+            __syncthreads();
+            const int npop = s_npop;
             for (int sb = 0; sb < nr; sb += kTtSub) {
-                // ---- set: one thread per row of the sub-block
+                // ---- set: one thread per row of the sub-block.  Rows are sorted, so the entries of a
+                //      batch that fall into the range form a prefix: no dependency between them.
                 const int lr = sb + tid;
                 if (lr < nr) {
-                    const int64_t rs = ptr[r_lo + lr], end = ptr[r_lo + lr + 1];
+                    const int64_t rs = ptr[r_lo + lr];
                     uint32_t c0 = cur[lr];
-                    int64_t pos = rs + c0;
+                    int left = static_cast<int>(ptr[r_lo + lr + 1] - rs) - static_cast<int>(c0);   // entries not yet consumed
+                    const int64_t pos = rs + c0;
+                    int64_t a = pos & ~static_cast<int64_t>(3);   // two aligned 16-byte loads per batch
+                    int skip = static_cast<int>(pos - a);
                     uint32_t* plane = bm + (static_cast<size_t>(warp >> 2) * kTtRange) * 4 + (warp & 3);
                     const uint32_t bit = 1u << lane;
-                    bool more = pos < end;
-                    while (more) {
+                    while (left > 0) {
                         int j[8];
+                        if (a + 7 < nnz) {
+                            const int4 v0 = *reinterpret_cast<const int4*>(idx + a);
+                            const int4 v1 = *reinterpret_cast<const int4*>(idx + a + 4);
+                            j[0] = v0.x; j[1] = v0.y; j[2] = v0.z; j[3] = v0.w;
+                            j[4] = v1.x; j[5] = v1.y; j[6] = v1.z; j[7] = v1.w;
+                        } else {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) j[q] = (pos + q < end) ? idx[pos + q] : 0x7fffffff;
+                            for (int q = 0; q < 8; ++q) j[q] = (a + q < nnz) ? idx[a + q] : 0x7fffffff;
+                        }
+                        int took = 0;
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
-                            if (more && j[q] < fe) {
-                                if (j[q] >= fb) atomicOr(plane + static_cast<size_t>(j[q] - fb) * 4, bit);
-                                ++c0;
-                            } else {
-                                more = false;
+                            if (q >= skip && q - skip < left && j[q] < fe) {
+                                const int f = j[q] - fb;
+                                if (f >= 0) atomicOr(plane + f * 4, bit);
+                                ++took;
                             }
                         }
-                        pos += 8;
+                        c0 += took;
+                        if (took < 8 - skip) break;
+                        left -= took;
+                        a += 8;
+                        skip = 0;
                     }
                     cur[lr] = c0;
                 }
                 __syncthreads();
-                // ---- emit: one thread per feature, rows in ascending order
-                if (has_feature) {
+                // ---- emit, ordinary features: one thread per feature, rows in ascending order
+                if (has_feature && !popular) {
+                    int64_t outpos = tbase + opos[tid];
                     uint4* mine = reinterpret_cast<uint4*>(bm) + tid;
 #pragma unroll 1
                     for (int g8 = 0; g8 < 8; ++g8) {
@@ -270,6 +303,31 @@ tile_emit_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
                             }
                         }
                     }
+                    opos[tid] = static_cast<uint32_t>(outpos - tbase);
+                }
+                // ---- emit, popular features: one warp per feature, lane p owns plane p (rows 32p..32p+31)
+                for (int i = warp; i < npop; i += kTtThreads / 32) {
+                    const int f = plist[i];
+                    uint32_t* wp = bm + (static_cast<size_t>(lane >> 2) * kTtRange + f) * 4 + (lane & 3);
+                    uint32_t word = *wp;
+                    *wp = 0u;
+                    const int c = __popc(word);
+                    int incl = c;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const int y = __shfl_up_sync(0xffffffffu, incl, d);
+                        if (lane >= d) incl += y;
+                    }
+                    const uint32_t base = opos[f];
+                    int64_t outpos = tbase + base + (incl - c);
+                    const int row0 = sb + lane * 32;
+                    while (word) {
+                        const int b = __ffs(word) - 1;
+                        word &= word - 1;
+                        ids[outpos++] = static_cast<uint16_t>(row0 + b);
+                    }
+                    __syncwarp();
+                    if (lane == 31) opos[f] = base + static_cast<uint32_t>(incl);
                 }
                 __syncthreads();
             }
@@ -360,11 +418,12 @@ void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
         const int rpg = static_cast<int>(ceil_div(n_ranges, groups));
         groups = static_cast<int>(ceil_div(n_ranges, rpg));
         const int64_t n_units = static_cast<int64_t>(nt) * groups;
-        const size_t smem = (static_cast<size_t>(32) * kTtRange + kTtMaxRows) * sizeof(uint32_t);
+        const size_t smem = (static_cast<size_t>(32) * kTtRange + kTtMaxRows + kTtRange) * sizeof(uint32_t) +
+                            static_cast<size_t>(kTtRange) * sizeof(uint16_t);
         SB_CUDA(cudaFuncSetAttribute(tile_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         const int grid = static_cast<int>(std::min<int64_t>(n_units, c->num_sms));
-        tile_emit_kernel<<<grid, kTtThreads, smem, st>>>(X.ptr.p, X.idx.p, n, m, tile_rows, groups, rpg, n_ranges, n_units,
-                                                         T.segoff.p, T.tile_base.p, T.ids.p, counter.p + 1);
+        tile_emit_kernel<<<grid, kTtThreads, smem, st>>>(X.ptr.p, X.idx.p, X.nnz, n, m, tile_rows, groups, rpg, n_ranges, n_units,
+                                                         T.cnt.p, T.segoff.p, T.tile_base.p, T.ids.p, counter.p + 1);
         SB_LAUNCH_CHECK();
         if (X.has_values()) {
             T.vals.alloc(hb[nt] + 8);
