@@ -118,13 +118,15 @@ struct Sell {
     DevBuf<int64_t> window_start;             // n_windows + 1 row boundaries
     DevBuf<int64_t> window_chunk0;            // n_windows + 1 first chunk of a window inside a tile
     DevBuf<int32_t> chunk_rows;               // n_chunks * 32 (global row id, -1 = none)
+    DevBuf<int32_t> chunk_span;               // n_chunks * 32: a lane of a split row covers pieces [lo, lo + cnt) of its
+                                              //   segment: lo | cnt << 16; 0xFFFF in the high half = the whole segment
     DevBuf<int32_t> chunk_groups;             // n_chunks   (groups of 8 slots per lane)
     DevBuf<int64_t> chunk_off;                // n_chunks + 1, in groups (256 slots)
     DevBuf<uint16_t> data;                    // n_entries
     DevBuf<float> vals;                       // n_entries or empty
     bool built = false;
     void clear() {
-        window_start.release(); window_chunk0.release(); chunk_rows.release(); chunk_groups.release();
+        window_start.release(); window_chunk0.release(); chunk_rows.release(); chunk_span.release(); chunk_groups.release();
         chunk_off.release(); data.release(); vals.release();
         built = false; n_chunks = n_entries = 0;
     }

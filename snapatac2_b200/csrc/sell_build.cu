@@ -149,16 +149,35 @@ struct TileSegs {
 
 // One CTA per (tile, window): sort the window's rows by segment length
 // (descending, ties by row) and cut them into chunks of 32 lanes.
+//
+// Splitting.  A warp works through a chunk at 1/24 of an SM's shared-memory bandwidth, so one very
+// long segment (a feature present in a large share of a tile's cells) can outlast the whole fair
+// share of its CTA when the shard is small (C3 on 8 GPUs: pass 1 ran at 56% instead of 77% of the
+// roofline).  Segments with more than `cap_slots` slots are therefore spread over p = 2..32
+// adjacent lanes (whole 256-entry pieces each); the SpMM adds the lanes of a row up before its single
+// store.  The longest rows come first in the sorted order and p is a non-increasing power of two,
+// so a row's lanes never straddle a chunk.  Every (tile, window) owns kSplitChunks spare chunks
+// for the extra lanes (unused ones have zero length).
+constexpr int kMaxSplitRows = 32;   // rows split per (tile, window) at most (the longest ones)
+__host__ __device__ __forceinline__ int pieces_of(int len) { return (len + kPiece - 1) / kPiece; }
+
 template <typename SEGS>
 __global__ void __launch_bounds__(kPlanThreads)
 sell_plan_kernel(const int64_t* __restrict__ window_start, const int64_t* __restrict__ window_chunk0,
-                 const SEGS segs, int n_tiles, int n_windows, int64_t chunks_per_tile,
-                 int nc, int32_t* __restrict__ chunk_rows, int32_t* __restrict__ chunk_groups) {
+                 const SEGS segs, int n_tiles, int n_windows, int64_t chunks_per_tile, int nc, int cap_slots,
+                 int32_t* __restrict__ chunk_rows, int32_t* __restrict__ chunk_span,
+                 int32_t* __restrict__ chunk_groups) {
     __shared__ uint32_t keys[kSellWindowRows];
+    __shared__ uint16_t split_slots[kMaxSplitRows * 32];   // slots of the lanes of split rows
+    __shared__ int32_t split_row[kMaxSplitRows * 32];      // their row (window relative) and span
+    __shared__ int32_t split_span[kMaxSplitRows * 32];
+    __shared__ int s_nsplit, s_lsplit;
     const int t = blockIdx.x / n_windows, w = blockIdx.x % n_windows;
     const int64_t r0 = window_start[w];
     const int nr = static_cast<int>(window_start[w + 1] - r0);
-    if (nr == 0) return;
+    const int64_t base = static_cast<int64_t>(t) * chunks_per_tile + window_chunk0[w];
+    const int nch = static_cast<int>(window_chunk0[w + 1] - window_chunk0[w]);   // chunks owned, spare ones included
+    if (nch == 0) return;
     int pow2 = 2;
     while (pow2 < nr) pow2 <<= 1;
     for (int i = threadIdx.x; i < pow2; i += kPlanThreads) {
@@ -182,16 +201,60 @@ sell_plan_kernel(const int64_t* __restrict__ window_start, const int64_t* __rest
             __syncthreads();
         }
     }
-    const int nch = (nr + 31) / 32;
-    const int64_t base = static_cast<int64_t>(t) * chunks_per_tile + window_chunk0[w];
-    for (int q = threadIdx.x; q < nch * 32; q += kPlanThreads) {
-        const bool valid = q < nr;
-        const uint32_t key = valid ? keys[q] : 0u;
-        chunk_rows[base * 32 + q] = valid ? static_cast<int32_t>(r0 + (key & 8191u)) : -1;
-        if ((q & 31) == 0) {
-            const int len = static_cast<int>(kLenBias - (key >> 13));   // longest segment of the chunk
-            chunk_groups[base + (q >> 5)] = (len + 7) >> 3;
+    // ---- split rows: a prefix of the sorted order
+    if (threadIdx.x == 0) {
+        int ns = 0, lanes = 0;
+        const int spare_lanes = (nch - (nr + 31) / 32) * 32;
+        while (ns < kMaxSplitRows && ns < nr) {
+            const uint32_t key = keys[ns];
+            const int slots = static_cast<int>(kLenBias - (key >> 13));
+            if (slots <= cap_slots) break;
+            const int len = segs.len(r0 + (key & 8191u), t);
+            const int np = pieces_of(len);
+            int p = 2;
+            while (p < 32 && p * cap_slots < slots) p <<= 1;
+            while (p > np) p >>= 1;                      // at least one piece per lane
+            if (p < 2 || lanes + p - 1 > spare_lanes) break;
+            const int pp = (np + p - 1) / p;             // pieces per lane
+            for (int j = 0; j < p; ++j) {
+                const int lo = j * pp, cnt = max(0, min(np, lo + pp) - lo);
+                int sl = 0;
+                if (cnt > 0) sl = (lo + cnt == np) ? (cnt - 1) * piece_slots(nc) + padded_slots(len - (np - 1) * kPiece, nc)
+                                                   : cnt * piece_slots(nc);
+                split_slots[lanes + j] = static_cast<uint16_t>(sl);
+                split_row[lanes + j] = static_cast<int32_t>(key & 8191u);
+                split_span[lanes + j] = lo | (cnt << 16);
+            }
+            lanes += p;
+            ++ns;
         }
+        s_nsplit = ns;
+        s_lsplit = lanes;
+    }
+    __syncthreads();
+    const int ns = s_nsplit, ls = s_lsplit;
+    const int n_lanes = ls + (nr - ns);
+    for (int q = threadIdx.x; q < nch * 32; q += kPlanThreads) {
+        int32_t row = -1, span = static_cast<int32_t>(0xFFFF0000u);   // whole segment
+        if (q < ls) {
+            row = static_cast<int32_t>(r0 + split_row[q]);
+            span = split_span[q];
+        } else if (q < n_lanes) {
+            row = static_cast<int32_t>(r0 + (keys[ns + q - ls] & 8191u));
+        }
+        chunk_rows[base * 32 + q] = row;
+        chunk_span[base * 32 + q] = span;
+    }
+    for (int ch = threadIdx.x; ch < nch; ch += kPlanThreads) {
+        int mx = 0;
+        for (int l = 0; l < 32; ++l) {
+            const int q = ch * 32 + l;
+            int sl = 0;
+            if (q < ls) sl = split_slots[q];
+            else if (q < n_lanes) sl = static_cast<int>(kLenBias - (keys[ns + q - ls] >> 13));
+            mx = max(mx, sl);
+        }
+        chunk_groups[base + ch] = (mx + 7) >> 3;
     }
 }
 
@@ -235,6 +298,7 @@ template <int NC> struct StagePitch { static constexpr int value = 8 * ((PieceSl
 template <bool HAS_VAL, int NC, typename SEGS>
 __global__ void __launch_bounds__(kStageWarps * 32)
 sell_fill_kernel(const SEGS segs, int64_t n_chunks, int64_t chunks_per_tile, const int32_t* __restrict__ chunk_rows,
+                 const int32_t* __restrict__ chunk_span,
                  const int32_t* __restrict__ chunk_groups, const int64_t* __restrict__ chunk_off,
                  uint16_t* __restrict__ data, float* __restrict__ vals) {
     constexpr int SP = PieceSlots<NC>::value, PITCH = StagePitch<NC>::value;
@@ -258,6 +322,11 @@ sell_fill_kernel(const SEGS segs, int64_t n_chunks, int64_t chunks_per_tile, con
         if (row >= 0) {
             s = segs.start(row, t);
             e = s + segs.len(row, t);
+            const uint32_t span = static_cast<uint32_t>(chunk_span[c * 32 + lane]);
+            if ((span >> 16) != 0xFFFFu) {   // one lane of a split row: pieces [lo, lo + cnt)
+                s += static_cast<int64_t>(span & 0xFFFFu) * kPiece;
+                e = min(e, s + static_cast<int64_t>(span >> 16) * kPiece);
+            }
         }
         for (int k0 = 0; k0 < steps; k0 += SP, s += kPiece) {
             const int nst8 = min(SP, steps - k0) >> 3;
@@ -343,7 +412,8 @@ sell_fill_kernel(const SEGS segs, int64_t n_chunks, int64_t chunks_per_tile, con
 // Windows, plan, offsets and fill, common to both segment sources.  `make_segs(T)` is called once
 // the number of column tiles is known (the CSR source needs it to size its boundary table).
 template <typename SEGS, typename MAKE>
-void build_impl(snapb200_ctx* c, int64_t nrows, int64_t ncols, bool has_values, Sell& S, int b, MAKE make_segs) {
+void build_impl(snapb200_ctx* c, int64_t nrows, int64_t ncols, int64_t nnz_estimate, bool has_values, Sell& S, int b,
+                MAKE make_segs) {
     SB_CHECK(b == 4 || b == 8, "tiled format: block width must be 4 or 8");
     cudaStream_t st = c->stream;
     S.clear();
@@ -361,7 +431,15 @@ void build_impl(snapb200_ctx* c, int64_t nrows, int64_t ncols, bool has_values, 
     std::vector<int64_t> ws(nw + 1), wc(nw + 1);
     wc[0] = 0;
     for (int w = 0; w <= nw; ++w) ws[w] = (R * w) / nw;
-    for (int w = 0; w < nw; ++w) wc[w + 1] = wc[w] + ceil_div(ws[w + 1] - ws[w], 32);
+    // a chunk may last at most about half of a warp's fair share of the pass (24 warps x #SMs);
+    // longer segments are split over lanes, for which every (tile, window) gets spare chunks
+    const int nc = (b == 8) ? 4 : 8;
+    const int64_t est_steps = (nnz_estimate + nnz_estimate / 6) / 32 + 1;   // per-lane slots in total (~1.16 x entries / 32)
+    const int cap_slots = static_cast<int>(std::min<int64_t>(
+        1 << 20, std::max<int64_t>(piece_slots(nc), est_steps / (static_cast<int64_t>(c->num_sms) * 48))));
+    const bool may_split = cap_slots < total_slots(S.tile_cols, nc);
+    const int spare = may_split ? kMaxSplitRows : 0;
+    for (int w = 0; w < nw; ++w) wc[w + 1] = wc[w] + ceil_div(ws[w + 1] - ws[w], 32) + (ws[w + 1] > ws[w] ? spare : 0);
     S.chunks_per_tile = wc[nw];
     S.n_chunks = S.chunks_per_tile * T;
     S.window_start.alloc(nw + 1);
@@ -370,17 +448,18 @@ void build_impl(snapb200_ctx* c, int64_t nrows, int64_t ncols, bool has_values, 
     SB_CUDA(cudaMemcpyAsync(S.window_chunk0.p, wc.data(), sizeof(int64_t) * (nw + 1), cudaMemcpyHostToDevice, st));
     const int64_t n_chunks = S.n_chunks;
 
-    const int nc = (b == 8) ? 4 : 8;
     SB_CHECK(piece_slots(nc) == ((padded_slots(kPiece, nc) + 7) & ~7), "piece slot table out of date");
     const SEGS segs = make_segs(T, S.tile_cols);
 
     // ---- plan: sorted chunk membership and chunk lengths, then offsets
     S.chunk_rows.alloc(std::max<int64_t>(1, n_chunks * 32));
+    S.chunk_span.alloc(std::max<int64_t>(1, n_chunks * 32));
     S.chunk_groups.alloc(std::max<int64_t>(1, n_chunks));
     S.chunk_off.alloc(n_chunks + 1);
     if (n_chunks > 0) {
         sell_plan_kernel<SEGS><<<static_cast<unsigned>(static_cast<int64_t>(T) * nw), kPlanThreads, 0, st>>>(
-            S.window_start.p, S.window_chunk0.p, segs, T, nw, S.chunks_per_tile, nc, S.chunk_rows.p, S.chunk_groups.p);
+            S.window_start.p, S.window_chunk0.p, segs, T, nw, S.chunks_per_tile, nc, cap_slots, S.chunk_rows.p,
+            S.chunk_span.p, S.chunk_groups.p);
         SB_LAUNCH_CHECK();
     }
     exclusive_scan_i32_to_i64(c, S.chunk_groups.p, S.chunk_off.p, n_chunks);
@@ -399,7 +478,7 @@ void build_impl(snapb200_ctx* c, int64_t nrows, int64_t ncols, bool has_values, 
         const size_t fsm = static_cast<size_t>(kStageWarps) * (32 * StagePitch<NC>::value + kOvfCap * 32) * 2;         \
         auto kern = sell_fill_kernel<HV, NC, SEGS>;                                                                    \
         SB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(fsm)));       \
-        kern<<<blocks, kStageWarps * 32, fsm, st>>>(segs, n_chunks, S.chunks_per_tile, S.chunk_rows.p,                 \
+        kern<<<blocks, kStageWarps * 32, fsm, st>>>(segs, n_chunks, S.chunks_per_tile, S.chunk_rows.p, S.chunk_span.p, \
                                                     S.chunk_groups.p, S.chunk_off.p, S.data.p, S.vals.p);              \
     } while (0)
         if (b == 8) { if (has_values) SB_FILL(true, 4); else SB_FILL(false, 4); }
@@ -416,7 +495,7 @@ void build_impl(snapb200_ctx* c, int64_t nrows, int64_t ncols, bool has_values, 
 
 void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b) {
     DevBuf<int32_t> segptr;
-    build_impl<CsrSegs>(c, M.nrows, M.ncols, M.has_values(), S, b, [&](int T, int tile_cols) {
+    build_impl<CsrSegs>(c, M.nrows, M.ncols, M.nnz, M.has_values(), S, b, [&](int T, int tile_cols) {
         // per-row tile boundaries
         const int64_t nseg = M.nrows * (T + 1);
         segptr.alloc(std::max<int64_t>(1, nseg));
@@ -432,7 +511,7 @@ void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b) {
 void sell_build_transposed(snapb200_ctx* c, const TileT& Tt, int64_t n_cells, Sell& S, int b) {
     SB_CHECK(Tt.built, "tiled format: the tile-major transpose is missing");
     SB_CHECK(Tt.tile_rows == kSellTileBytes / (4 * b), "tiled format: transpose tile height does not match the block width");
-    build_impl<TileSegs>(c, Tt.m, n_cells, Tt.vals.p != nullptr, S, b, [&](int T, int) {
+    build_impl<TileSegs>(c, Tt.m, n_cells, Tt.nnz, Tt.vals.p != nullptr, S, b, [&](int T, int) {
         SB_CHECK(T == Tt.n_tiles, "tiled format: tile count mismatch");
         return TileSegs{Tt.cnt.p, Tt.segoff.p, Tt.tile_base.p, Tt.ids.p, Tt.vals.p, Tt.m};
     });

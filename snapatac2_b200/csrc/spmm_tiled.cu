@@ -69,6 +69,10 @@ __device__ __forceinline__ void st_stream_float4(float4* p, const float4& v) {
     asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
+__device__ __forceinline__ float4 shfl_down4(const float4& v, int d) {
+    return make_float4(__shfl_down_sync(0xffffffffu, v.x, d), __shfl_down_sync(0xffffffffu, v.y, d),
+                       __shfl_down_sync(0xffffffffu, v.z, d), __shfl_down_sync(0xffffffffu, v.w, d));
+}
 __device__ __forceinline__ void acc4(float4& a, const float4& x, float v, bool has_val) {
     if (has_val) {
         a.x = fmaf(v, x.x, a.x); a.y = fmaf(v, x.y, a.y); a.z = fmaf(v, x.z, a.z); a.w = fmaf(v, x.w, a.w);
@@ -105,12 +109,46 @@ __device__ __forceinline__ void gather_eight(const int4& e, const float4& v0, co
     gather_one<B, HAS_VAL>(w >> 16, v1.w, tile1, tile2, a, b);
 }
 
+// End of a chunk: one partial sum per (tile, row).  The lanes of a split row (sell_build.cu) are
+// adjacent: they are added up in a fixed order and the first one stores.  Kept out of line so that
+// it does not disturb the code generation of the gather loop (predicated LDS.128 in flight).
+template <int B>
+__device__ __noinline__ void store_partial(float4 a, float4 b, int row, int lane, float* __restrict__ part_t) {
+    // canonical halves (b = 8: odd lanes gathered the upper half first)
+    float4 lo = (B == 8 && (lane & 1)) ? b : a;
+    float4 hi = (B == 8 && (lane & 1)) ? a : b;
+    const int nrow = __shfl_down_sync(0xffffffffu, row, 1);
+    if (__any_sync(0xffffffffu, row >= 0 && lane < 31 && nrow == row)) {
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int orow = __shfl_down_sync(0xffffffffu, row, d);
+            const float4 ol = shfl_down4(lo, d);
+            const float4 oh = (B == 8) ? shfl_down4(hi, d) : hi;
+            if (row >= 0 && lane + d < 32 && orow == row) {
+                lo.x += ol.x; lo.y += ol.y; lo.z += ol.z; lo.w += ol.w;
+                if (B == 8) { hi.x += oh.x; hi.y += oh.y; hi.z += oh.z; hi.w += oh.w; }
+            }
+        }
+    }
+    const int prow = __shfl_up_sync(0xffffffffu, row, 1);
+    if (row >= 0 && (lane == 0 || prow != row)) {
+        float4* o = reinterpret_cast<float4*>(part_t + static_cast<int64_t>(row) * B);
+        st_stream_float4(o, lo);
+        if (B == 8) st_stream_float4(o + 1, hi);
+    }
+}
+
 // first chunk index c in [0, n] with chunk_off[c] >= target
+// Cost of the chunk list up to chunk c: its groups of 8 slots plus a fixed per-chunk charge (fetching
+// the chunk's metadata, the epilogue and its store cost about as much as kChunkCost groups); ranges
+// of many short chunks would otherwise take longer than ranges of few long ones (ncu on a 1/8
+// shard of C3: slowest SM 1.45x the average in pass 1).
+constexpr int64_t kChunkCost = 3;
 __device__ int64_t chunk_lower_bound(const int64_t* __restrict__ chunk_off, int64_t n, int64_t target) {
     int64_t lo = 0, hi = n;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
-        if (chunk_off[mid] < target) lo = mid + 1; else hi = mid;
+        if (chunk_off[mid] + kChunkCost * mid < target) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
@@ -134,8 +172,8 @@ sell_spmm_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restri
 
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
-        // this CTA's share of the tile-major chunk list: equal stored entries
-        const int64_t groups = chunk_off[n_chunks];
+        // this CTA's share of the tile-major chunk list: equal cost
+        const int64_t groups = chunk_off[n_chunks] + kChunkCost * n_chunks;
         const int64_t g_lo = static_cast<int64_t>((static_cast<__int128>(groups) * blockIdx.x) / gridDim.x);
         const int64_t g_hi = static_cast<int64_t>((static_cast<__int128>(groups) * (blockIdx.x + 1)) / gridDim.x);
         range[0] = (blockIdx.x == 0) ? 0 : chunk_lower_bound(chunk_off, n_chunks, g_lo);
@@ -213,15 +251,7 @@ sell_spmm_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restri
                     vcur[2 * u + 1] = vnxt[2 * u + 1];
                 }
             }
-            if (row >= 0) {
-                float4* o = reinterpret_cast<float4*>(part_t + static_cast<int64_t>(row) * B);
-                if (B == 8) {
-                    st_stream_float4(o, (lane & 1) ? b : a);
-                    st_stream_float4(o + 1, (lane & 1) ? a : b);
-                } else {
-                    st_stream_float4(o, a);
-                }
-            }
+            store_partial<B>(a, b, row, lane, part_t);
         }
     }
 }
@@ -299,7 +329,7 @@ sell_spmv64_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __rest
     const uint32_t tile_a = smem_u32(tile);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
-        const int64_t groups = chunk_off[n_chunks];
+        const int64_t groups = chunk_off[n_chunks] + kChunkCost * n_chunks;
         const int64_t g_lo = static_cast<int64_t>((static_cast<__int128>(groups) * blockIdx.x) / gridDim.x);
         const int64_t g_hi = static_cast<int64_t>((static_cast<__int128>(groups) * (blockIdx.x + 1)) / gridDim.x);
         range[0] = (blockIdx.x == 0) ? 0 : chunk_lower_bound(chunk_off, n_chunks, g_lo);
@@ -365,7 +395,18 @@ sell_spmv64_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __rest
                     gather64<HAS_VAL, SQ>(w >> 16, v[2 * u + 1].w, tile_a, a1);
                 }
             }
-            if (row >= 0) part_t[row] = a0 + a1;
+            double acc = a0 + a1;
+            const int nrow = __shfl_down_sync(0xffffffffu, row, 1);
+            if (__any_sync(0xffffffffu, row >= 0 && lane < 31 && nrow == row)) {   // split rows (see sell_spmm_kernel)
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int orow = __shfl_down_sync(0xffffffffu, row, d);
+                    const double oa = __shfl_down_sync(0xffffffffu, acc, d);
+                    if (row >= 0 && lane + d < 32 && orow == row) acc += oa;
+                }
+            }
+            const int prow = __shfl_up_sync(0xffffffffu, row, 1);
+            if (row >= 0 && (lane == 0 || prow != row)) part_t[row] = acc;
         }
     }
 }
