@@ -124,6 +124,18 @@ int  snapb200_prepare(snapb200_ctx* ctx, double* idf_out, double* degree_out);
  * (embedding.rs:428-443) and runs the ordinary load/prepare/eigsh on the result. */
 int  snapb200_view_norms(snapb200_ctx* ctx, double* idf_out, double* rho_out);
 
+/* Nystrom extension (spectral_embedding_nystrom / nystrom, embedding.rs:61-129, 194-267): products
+ * with the feature-weighted, row-normalised matrix  Xhat = diag(1/rho) P diag(w)  on k dense
+ * columns (row-major f32 host buffers):
+ *   transposed == 0:  out[n_local x k] = Xhat   in[m x k]       -- "sample @ (...)" for every cell
+ *   transposed != 0:  out[m x k]       = Xhat^T in[n_local x k] -- "seed.T @ evecs" (summed over the
+ *                                                                  row shards); needs snapb200_prepare
+ * prepare_projection computes what the non-transposed product needs (IDF or user weights, row
+ * norms, the cell-major tiled copy) without the transpose; it is implied by the first project call.
+ * Its outputs may be NULL (idf_out: m doubles, rho_out: n_local doubles). */
+int  snapb200_prepare_projection(snapb200_ctx* ctx, double* idf_out, double* rho_out);
+int  snapb200_project(snapb200_ctx* ctx, int transposed, const float* in, int k, float* out);
+
 /* a6 alone: Y = X~ (X~^T V) - dinv .* V on b vectors (embedding.rs:162-163).
  * V and Y are host, row-major n_local x b, b in {4, 8, 16}. */
 int  snapb200_operator_apply(snapb200_ctx* ctx, const float* V, float* Y, int b);

@@ -27,4 +27,8 @@ from .reference_restatement import (  # noqa: F401
     matrix_free_twin,
     dense_check,
     operator_pieces,
+    compute_degrees,
+    nystrom,
+    orthogonalize,
+    spectral_embedding_nystrom,
 )

@@ -157,6 +157,68 @@ def spectral_embedding(x, selected_features, n_components, random_state,
 
 
 # --------------------------------------------------------------------------
+# Nystrom path                         embedding.rs:61-129, 194-267, 328-365
+# --------------------------------------------------------------------------
+def compute_degrees(x, selected_features, feature_weights):
+    """``compute_degrees`` (embedding.rs:328-360): degrees of every cell under the
+    full-data normalisation, ``Xhat (Xhat^T 1) - 1``."""
+    xhat = normalize(_select_columns(x, selected_features), feature_weights)
+    col_sum = np.asarray(xhat.sum(axis=0)).ravel()
+    return xhat @ col_sum - 1.0
+
+
+def nystrom(seed: sp.csr_matrix, evals, evecs, degrees, chunks):
+    """``nystrom`` (embedding.rs:194-267).  ``chunks`` yields normalised row blocks."""
+    evecs = evecs / np.sqrt(degrees)[:, None]          # :206-210
+    evecs = evecs / evals[None, :]                     # :211-215
+    proj = seed.T @ evecs                              # seed.T @ evecs                (:223)
+    out = []
+    for sample in chunks:
+        q = sample @ proj                              # :223
+        t = q.sum(axis=0) * evals                      # :224
+        d = q @ t.reshape((-1, 1))                     # :225
+        d[d <= 0] = np.min(d[d > 0])                   # :226
+        q = q / np.sqrt(d)                             # :227
+        out.append(q)
+    return evals.copy(), np.vstack(out)
+
+
+def orthogonalize(evals, evecs):
+    """``orthogonalize`` (tools/_embedding.py:397-413)."""
+    _, sigma, vt = np.linalg.svd(evecs, full_matrices=False)
+    v = vt.T
+    b = np.multiply(v.T, evals.reshape((1, -1))) @ v
+    b = b * sigma.reshape((-1, 1)) * sigma.reshape((1, -1))
+    evals_new, evecs_new = np.linalg.eig(b)
+    ix = evals_new.argsort()[::-1]
+    evals_new = evals_new[ix]
+    evecs_new = evecs_new[:, ix]
+    evecs_new = evecs_new / sigma.reshape((-1, 1))
+    return evals_new, evecs @ v @ evecs_new
+
+
+def spectral_embedding_nystrom(x, selected_features, n_components, landmarks, chunk_size,
+                               feature_weights=None, return_parts=False):
+    """``spectral_embedding_nystrom`` (embedding.rs:61-129) for a GIVEN landmark index list.
+
+    The reference draws the landmarks with Rust's ``rand::StdRng::seed_from_u64(2023)``
+    (:87-94), a stream that cannot be reproduced here; everything downstream of the draw
+    is restated.  IDF weights come from all cells (:76-84), the seed rows are normalised
+    with them (:95-103), ``spectral_mf(seed, k, 0)`` (:104), then ``nystrom`` over
+    ``chunk_size`` row blocks of the normalised data (:106-119).
+    """
+    mat = _select_columns(x, selected_features)
+    w = idf(mat) if feature_weights is None else np.asarray(feature_weights, dtype=np.float64)
+    seed = normalize(sp.csr_matrix(mat[np.asarray(landmarks)]), w)
+    v, u, d = spectral_mf(seed, n_components, 0)
+    chunks = (normalize(sp.csr_matrix(mat[i:i + chunk_size]), w) for i in range(0, mat.shape[0], chunk_size))
+    evals, q = nystrom(seed, v, u, d, chunks)
+    if return_parts:
+        return evals, q, w, d
+    return evals, q
+
+
+# --------------------------------------------------------------------------
 # a1: Python wrapper semantics                         _embedding.py:129-295
 # --------------------------------------------------------------------------
 def spectral(adata, n_comps=30, features="selected", random_state=0, sample_size=None,

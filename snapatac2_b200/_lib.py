@@ -20,6 +20,7 @@ SYMBOLS = [
     "snapb200_comm_unique_id", "snapb200_comm_init", "snapb200_load_csr",
     "snapb200_select_features", "snapb200_generate", "snapb200_shape", "snapb200_export_csr",
     "snapb200_set_feature_weights", "snapb200_prepare", "snapb200_view_norms",
+    "snapb200_prepare_projection", "snapb200_project",
     "snapb200_operator_apply", "snapb200_operator_time", "snapb200_eigsh", "snapb200_get_stats",
     "snapb200_get_stream", "snapb200_set_spmm_mode", "snapb200_set_block",
     "snapb200_dense_selftest", "snapb200_sym_eig",
@@ -72,6 +73,8 @@ def load() -> C.CDLL:
         "snapb200_set_feature_weights": [vp, vp, i64],
         "snapb200_prepare": [vp, vp, vp],
         "snapb200_view_norms": [vp, vp, vp],
+        "snapb200_prepare_projection": [vp, vp, vp],
+        "snapb200_project": [vp, i32, vp, i32, vp],
         "snapb200_operator_apply": [vp, vp, vp, i32],
         "snapb200_operator_time": [vp, i32, i32, i32, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)],
         "snapb200_eigsh": [vp, i32, i64, dbl, i32, i32, i32, vp, vp],

@@ -118,6 +118,7 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     c->Xt.clear();
     c->xt_built = false;
     c->XtT.clear();
+    c->proj_ready = false;
     X.nrows = n_local;
     X.ncols = m;
     X.ptr.alloc(n_local + 1);
@@ -290,6 +291,7 @@ int snapb200_generate(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_
         c->Xt.clear();
         c->xt_built = false;
         c->XtT.clear();
+        c->proj_ready = false;
         generate_rows(c, n_local, n_global, row0, m, nnz_row, n_clusters, seed, feat_cdf, cluster_cdf, block_start, alpha);
     });
 }
@@ -329,6 +331,7 @@ int snapb200_set_feature_weights(snapb200_ctx* c, const double* w, int64_t m) {
         if (w == nullptr) c->user_weights.clear();
         else c->user_weights.assign(w, w + m);
         c->prepared = false;
+        c->proj_ready = false;
     });
 }
 
@@ -338,6 +341,25 @@ int snapb200_prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
 
 int snapb200_view_norms(snapb200_ctx* c, double* idf_out, double* rho_out) {
     return guarded([&] { bind(c); view_norms(c, idf_out, rho_out); });
+}
+
+int snapb200_prepare_projection(snapb200_ctx* c, double* idf_out, double* rho_out) {
+    return guarded([&] {
+        bind(c);
+        prepare_projection(c);
+        if (idf_out) SB_CUDA(cudaMemcpyAsync(idf_out, c->w.p, sizeof(double) * c->m, cudaMemcpyDeviceToHost, c->stream));
+        if (rho_out && c->n_local > 0)
+            SB_CUDA(cudaMemcpyAsync(rho_out, c->rho.p, sizeof(double) * c->n_local, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+    });
+}
+
+int snapb200_project(snapb200_ctx* c, int transposed, const float* in, int k, float* out) {
+    return guarded([&] {
+        bind(c);
+        SB_CHECK(in != nullptr && out != nullptr, "project: null buffer");
+        project(c, transposed != 0, in, k, out);
+    });
 }
 
 int snapb200_operator_apply(snapb200_ctx* c, const float* V, float* Y, int b) {
@@ -415,6 +437,7 @@ int snapb200_set_spmm_mode(snapb200_ctx* c, int mode) {
         SB_CHECK(c != nullptr, "null context");
         SB_CHECK(mode >= 0 && mode <= 2, "set_spmm_mode: mode must be 0 (auto), 1 (csr) or 2 (tiled)");
         c->spmm_mode = mode;
+        c->proj_ready = false;
         c->prepared = false;
     });
 }

@@ -177,6 +177,9 @@ struct snapb200_ctx {
     snapb::DevBuf<float> w2;        // m   w^2 (f32)
     snapb::DevBuf<float> u1;        // n   sqrt(d)/||sqrt(d)||, trivial eigenvector
     double view_scale = 1.0;        // multi-view scale folded into w
+    snapb::DevBuf<float> w_f;       // m   w as f32      (projection products)
+    snapb::DevBuf<float> rhoinv_f;  // n   1/rho as f32
+    bool proj_ready = false;
 
     // operator workspaces
     snapb::DevBuf<float> Vr;        // n x b  r .* V
@@ -222,6 +225,8 @@ void ensure_xt(snapb200_ctx* c);   // builds the CSR feature-major copy c->Xt if
 void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local);
 void prepare(snapb200_ctx* c, double* idf_out, double* degree_out);
 void view_norms(snapb200_ctx* c, double* idf_out, double* rho_out);
+// IDF (or user) weights and weighted row norms of the loaded matrix into device buffers (no transpose)
+void weights_and_norms(snapb200_ctx* c, double* w_dev, double* rho_dev);
 
 // ---- spmm.cu
 // Y[n x b] (leading dim ldy) = X~ X~^T V - dinv .* V, V with leading dim ldv.
@@ -229,6 +234,10 @@ void view_norms(snapb200_ctx* c, double* idf_out, double* rho_out);
 // all-reduce, after pass 2.
 void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, int b,
                         cudaEvent_t* evs = nullptr);
+
+// products with Xhat = diag(1/rho) P diag(w) on k dense columns (Nystrom extension)
+void prepare_projection(snapb200_ctx* c);
+void project(snapb200_ctx* c, bool transposed, const float* in_host, int k, float* out_host);
 
 // ---- sell_build.cu / spmm_tiled.cu
 void sell_build(snapb200_ctx* c, const Csr& M, Sell& S, int b);

@@ -325,6 +325,7 @@ void select_features(snapb200_ctx* c, const uint8_t* keep_host, int64_t m) {
     X.ncols = m_new;
     c->m = m_new;
     c->prepared = false;
+    c->proj_ready = false;
     c->Xt.clear();
     c->xt_built = false;
     c->XtT.clear();
@@ -581,41 +582,65 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     c->stats.ms_prepare_wall = since(wall0);
     c->stats.ms_prepare = std::max(0.0, c->stats.ms_prepare_wall - c->stats.ms_transpose - ms_format);
     c->prepared = true;
+    c->proj_ready = false;
+}
+
+void weights_and_norms(snapb200_ctx* c, double* w_dev, double* rho_dev) {
+    Csr& X = c->X;
+    const int64_t m = c->m, n = c->n_local;
+    cudaStream_t st = c->stream;
+    if (!c->user_weights.empty()) {
+        SB_CHECK(static_cast<int64_t>(c->user_weights.size()) == m,
+                 "feature_weights length must equal the number of selected features");
+        SB_CUDA(cudaMemcpyAsync(w_dev, c->user_weights.data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    } else {
+        DevBuf<int32_t> cnt;
+        DevBuf<int64_t> df, mm;
+        cnt.alloc(m);
+        df.alloc(m);
+        mm.alloc(2);
+        SB_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int32_t) * m, st));
+        if (X.nnz > 0) {
+            int blocks = static_cast<int>(std::min<int64_t>(ceil_div(X.nnz, 256), static_cast<int64_t>(c->num_sms) * 32));
+            col_count_kernel<<<blocks, 256, 0, st>>>(X.idx.p, X.nnz, cnt.p);
+            SB_LAUNCH_CHECK();
+        }
+        i32_to_i64_kernel<<<grid1d(m), 256, 0, st>>>(cnt.p, df.p, m);
+        SB_LAUNCH_CHECK();
+        allreduce_i64(c, df.p, m);
+        df_minmax_kernel<<<1, 256, 0, st>>>(df.p, m, mm.p);
+        SB_LAUNCH_CHECK();
+        idf_kernel<<<grid1d(m), 256, 0, st>>>(df.p, mm.p, m, static_cast<double>(c->n_global), w_dev);
+        SB_LAUNCH_CHECK();
+        count_launch(c, 4);
+        SB_CUDA(cudaStreamSynchronize(st));   // temporaries
+    }
+    if (n > 0) {
+        spmv_f64_kernel<0><<<grid_for_rows(c, n), 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, w_dev, nullptr, 0.0, n, rho_dev);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
 }
 
 // Per-view statistics for multi_spectral (embedding.rs:413-416): IDF weights of the loaded
 // (and column-selected) view and the L2 norms of its IDF-weighted rows.  No transposition.
 void view_norms(snapb200_ctx* c, double* idf_out, double* rho_out) {
     SB_CHECK(c->loaded, "view_norms: no matrix loaded");
-    Csr& X = c->X;
     const int64_t m = c->m, n = c->n_local;
     cudaStream_t st = c->stream;
-    DevBuf<int32_t> cnt;
-    DevBuf<int64_t> df, mm;
     DevBuf<double> w, rho;
-    cnt.alloc(m);
-    df.alloc(m);
-    mm.alloc(2);
     w.alloc(m);
     rho.alloc(std::max<int64_t>(1, n));
-    SB_CUDA(cudaMemsetAsync(cnt.p, 0, sizeof(int32_t) * m, st));
-    if (X.nnz > 0) {
-        int blocks = static_cast<int>(std::min<int64_t>(ceil_div(X.nnz, 256), static_cast<int64_t>(c->num_sms) * 32));
-        col_count_kernel<<<blocks, 256, 0, st>>>(X.idx.p, X.nnz, cnt.p);
-        SB_LAUNCH_CHECK();
+    // the per-view statistics always use the view's own IDF (embedding.rs:413), never user weights
+    std::vector<double> saved;
+    saved.swap(c->user_weights);
+    try {
+        weights_and_norms(c, w.p, rho.p);
+    } catch (...) {
+        saved.swap(c->user_weights);
+        throw;
     }
-    i32_to_i64_kernel<<<grid1d(m), 256, 0, st>>>(cnt.p, df.p, m);
-    SB_LAUNCH_CHECK();
-    allreduce_i64(c, df.p, m);
-    df_minmax_kernel<<<1, 256, 0, st>>>(df.p, m, mm.p);
-    SB_LAUNCH_CHECK();
-    idf_kernel<<<grid1d(m), 256, 0, st>>>(df.p, mm.p, m, static_cast<double>(c->n_global), w.p);
-    SB_LAUNCH_CHECK();
-    if (n > 0) {
-        spmv_f64_kernel<0><<<grid_for_rows(c, n), 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, w.p, nullptr, 0.0, n, rho.p);
-        SB_LAUNCH_CHECK();
-    }
-    count_launch(c, 5);
+    saved.swap(c->user_weights);
     if (idf_out) SB_CUDA(cudaMemcpyAsync(idf_out, w.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     if (rho_out && n > 0) SB_CUDA(cudaMemcpyAsync(rho_out, rho.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));

@@ -11,6 +11,7 @@
 // Both passes are gathers (no atomics), so results are bitwise reproducible.
 // The only large traffic is the int32 index stream: 4 B/nnz per pass.
 #include "ctx.cuh"
+#include "dense.cuh"
 
 #include <algorithm>
 
@@ -193,6 +194,128 @@ void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, 
         case 16: apply_impl<16>(c, V, ldv, Y, ldy, evs); break;
         default: throw Error("operator: block width must be 4, 8 or 16");
     }
+}
+
+// --------------------------------------------------------------------------
+// Products with the row-normalised, feature-weighted matrix  Xhat = diag(1/rho) P diag(w)
+// on k dense columns (the Nystrom extension, embedding.rs:194-267:  q = sample @ (seed.T @ evecs)).
+//   project:    out[n x k] = Xhat   in[m x k]     (needs prepare_projection or prepare)
+//   project_t:  out[m x k] = Xhat^T in[n x k]     (needs prepare; all-reduced over the row shards)
+// The columns go through the same SpMM kernels as the operator, b at a time.
+// --------------------------------------------------------------------------
+namespace {
+
+// out[row, 0:B] = scale[row] * in[row * ld + col0 + (0:B)]   (columns past ncols read as zero)
+template <int B>
+__global__ void pack_scaled_kernel(const float* __restrict__ in, int64_t ld, int col0, int ncols,
+                                   const float* __restrict__ scale, int64_t rows, float* __restrict__ out) {
+    const int64_t t = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= rows * B) return;
+    const int64_t i = t / B;
+    const int k = static_cast<int>(t - i * B);
+    out[t] = (col0 + k < ncols) ? scale[i] * in[i * ld + col0 + k] : 0.f;
+}
+
+__global__ void to_float_kernel(const double* __restrict__ in, float* __restrict__ out, int64_t n, int recip) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = static_cast<float>(recip ? 1.0 / in[i] : in[i]);
+}
+
+template <int B>
+void product_block(snapb200_ctx* c, bool transposed, const float* in_b, float* out_b) {
+    const int64_t n = c->n_local, m = c->m;
+    cudaStream_t st = c->stream;
+    const bool tiled = use_tiled(c, B) && (transposed ? c->S1.built && c->S1.b == B : c->S2.built && c->S2.b == B);
+    if (!transposed) {
+        if (n == 0) return;
+        if (tiled) {
+            sell_spmm(c, c->S2, in_b, out_b, c->rhoinv_f.p, nullptr, nullptr, 0);
+        } else if (c->X.has_values()) {
+            gather_rows_kernel<B, true, false><<<grid_rows(c, n), 256, 0, st>>>(
+                c->X.ptr.p, c->X.idx.p, c->X.val.p, in_b, c->rhoinv_f.p, n, out_b, B, nullptr, nullptr, 0);
+        } else {
+            gather_rows_kernel<B, false, false><<<grid_rows(c, n), 256, 0, st>>>(
+                c->X.ptr.p, c->X.idx.p, nullptr, in_b, c->rhoinv_f.p, n, out_b, B, nullptr, nullptr, 0);
+        }
+    } else {
+        if (tiled) {
+            sell_spmm(c, c->S1, in_b, out_b, c->w_f.p, nullptr, nullptr, 0);
+        } else {
+            ensure_xt(c);
+            if (c->Xt.has_values())
+                gather_rows_kernel<B, true, false><<<grid_rows(c, m), 256, 0, st>>>(
+                    c->Xt.ptr.p, c->Xt.idx.p, c->Xt.val.p, in_b, c->w_f.p, m, out_b, B, nullptr, nullptr, 0);
+            else
+                gather_rows_kernel<B, false, false><<<grid_rows(c, m), 256, 0, st>>>(
+                    c->Xt.ptr.p, c->Xt.idx.p, nullptr, in_b, c->w_f.p, m, out_b, B, nullptr, nullptr, 0);
+        }
+        allreduce_f32(c, out_b, m * B);
+    }
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+}
+
+template <int B>
+void product_impl(snapb200_ctx* c, bool transposed, const float* in_host, int k, float* out_host) {
+    const int64_t n = c->n_local, m = c->m;
+    const int64_t rin = transposed ? n : m, rout = transposed ? m : n;
+    cudaStream_t st = c->stream;
+    DevBuf<float> din, dout, bin, bout;
+    din.alloc(std::max<int64_t>(1, rin * k));
+    dout.alloc(std::max<int64_t>(1, rout * k));
+    bin.alloc(std::max<int64_t>(1, rin * B));
+    bout.alloc(std::max<int64_t>(1, rout * B));
+    if (rin > 0) SB_CUDA(cudaMemcpyAsync(din.p, in_host, sizeof(float) * rin * k, cudaMemcpyHostToDevice, st));
+    const float* in_scale = transposed ? c->rhoinv_f.p : c->w_f.p;
+    for (int j0 = 0; j0 < k; j0 += B) {
+        const int nb = std::min(B, k - j0);
+        if (rin > 0) {
+            pack_scaled_kernel<B><<<static_cast<unsigned>(ceil_div(rin * B, 256)), 256, 0, st>>>(din.p, k, j0, k, in_scale, rin,
+                                                                                             bin.p);
+            SB_LAUNCH_CHECK();
+        }
+        product_block<B>(c, transposed, bin.p, bout.p);
+        if (rout > 0) copy_cols(c, bout.p, B, dout.p + j0, k, rout, nb);
+    }
+    if (rout > 0) SB_CUDA(cudaMemcpyAsync(out_host, dout.p, sizeof(float) * rout * k, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace
+
+void prepare_projection(snapb200_ctx* c) {
+    SB_CHECK(c->loaded, "prepare_projection: no matrix loaded");
+    const int64_t n = c->n_local, m = c->m;
+    cudaStream_t st = c->stream;
+    if (!c->prepared) {
+        // IDF (or user) weights and row norms only; no transpose (view_norms leaves them on the device)
+        c->w.alloc(m);
+        c->rho.alloc(std::max<int64_t>(1, n));
+        weights_and_norms(c, c->w.p, c->rho.p);
+        c->S1.clear();
+        c->S2.clear();
+        if (use_tiled(c, c->block)) sell_build(c, c->X, c->S2, c->block);
+    }
+    c->w_f.alloc(m);
+    c->rhoinv_f.alloc(std::max<int64_t>(1, n));
+    to_float_kernel<<<static_cast<unsigned>(ceil_div(m, 256)), 256, 0, st>>>(c->w.p, c->w_f.p, m, 0);
+    SB_LAUNCH_CHECK();
+    if (n > 0) {
+        to_float_kernel<<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, st>>>(c->rho.p, c->rhoinv_f.p, n, 1);
+        SB_LAUNCH_CHECK();
+    }
+    SB_CUDA(cudaStreamSynchronize(st));
+    c->proj_ready = true;
+}
+
+void project(snapb200_ctx* c, bool transposed, const float* in_host, int k, float* out_host) {
+    SB_CHECK(k >= 1, "project: k must be positive");
+    SB_CHECK(!transposed || c->prepared, "project_t: call prepare first");
+    if (!c->proj_ready) prepare_projection(c);
+    // column blocks of the width the tiled copies were built for (8 on the CSR path)
+    const int b = (c->S2.built && (c->S2.b == 4 || c->S2.b == 8)) ? c->S2.b : 8;
+    if (b == 4) product_impl<4>(c, transposed, in_host, k, out_host);
+    else product_impl<8>(c, transposed, in_host, k, out_host);
 }
 
 }  // namespace snapb

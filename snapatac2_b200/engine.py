@@ -154,6 +154,30 @@ class Engine:
         _lib.check(self._lib.snapb200_view_norms(self._ctx, _lib.ptr(idf), _lib.ptr(rho)))
         return idf, rho
 
+    def prepare_projection(self, want_outputs=True):
+        """What :meth:`project` needs (weights, row norms, cell-major tiled copy), without the
+        transpose.  Returns ``(w[m], rho[n_local])`` (or None, None)."""
+        w = np.empty(self.m, dtype=np.float64) if want_outputs else None
+        rho = np.empty(self.n_local, dtype=np.float64) if want_outputs else None
+        _lib.check(self._lib.snapb200_prepare_projection(self._ctx, _lib.ptr(w), _lib.ptr(rho)))
+        return w, rho
+
+    def project(self, M):
+        """``Xhat @ M`` for the feature-weighted, row-normalised matrix (M: m x k) -> n_local x k."""
+        M = np.ascontiguousarray(M, dtype=np.float32)
+        assert M.ndim == 2 and M.shape[0] == self.m
+        out = np.empty((self.n_local, M.shape[1]), dtype=np.float32)
+        _lib.check(self._lib.snapb200_project(self._ctx, 0, _lib.ptr(M), int(M.shape[1]), _lib.ptr(out)))
+        return out
+
+    def project_t(self, U):
+        """``Xhat.T @ U`` (U: n_local x k) -> m x k, summed over the row shards; needs prepare()."""
+        U = np.ascontiguousarray(U, dtype=np.float32)
+        assert U.ndim == 2 and U.shape[0] == self.n_local
+        out = np.empty((self.m, U.shape[1]), dtype=np.float32)
+        _lib.check(self._lib.snapb200_project(self._ctx, 1, _lib.ptr(U), int(U.shape[1]), _lib.ptr(out)))
+        return out
+
     def operator_apply(self, V):
         V = np.ascontiguousarray(V, dtype=np.float32)
         assert V.ndim == 2 and V.shape[0] == self.n_local

@@ -104,6 +104,84 @@ def spectral_embedding(engine: Engine, X, selected_features, n_components, rando
     return evals, evecs
 
 
+def orthogonalize(evals, evecs):
+    """``orthogonalize`` of the reference wrapper (tools/_embedding.py:397-413): turns the Nystrom
+    extension into an orthogonal eigenbasis (k x k algebra after one thin SVD; host side)."""
+    _, sigma, vt = np.linalg.svd(evecs, full_matrices=False)
+    v = vt.T
+    b = np.multiply(v.T, evals.reshape((1, -1))) @ v
+    b = b * sigma.reshape((-1, 1)) * sigma.reshape((1, -1))
+    evals_new, evecs_new = np.linalg.eig(b)
+    ix = evals_new.argsort()[::-1]
+    evals_new = evals_new[ix]
+    evecs_new = evecs_new[:, ix] / sigma.reshape((-1, 1))
+    return evals_new, evecs @ v @ evecs_new
+
+
+def spectral_embedding_nystrom(engine: Engine, X, selected_features, n_components, sample_size,
+                               weighted_by_degree, chunk_size, feature_weights=None, *, landmarks=None,
+                               seed_engine: Engine | None = None, tol=0.0, block=0, return_parts=False):
+    """Counterpart of ``internal.spectral_embedding_nystrom`` (embedding.rs:61-129): spectral
+    embedding of ``sample_size`` landmark cells, extended to every cell (``nystrom``, :194-267).
+
+    Device work: IDF weights and row norms of all cells, the embedding of the landmark
+    matrix (a second context on the same GPU: load / prepare / eigsh with the global
+    weights), ``seed.T @ evecs`` (``snapb200_project`` transposed) and ``sample @ (...)`` for
+    every cell (``snapb200_project``).  The per-chunk degree normalisation (:224-227, over
+    ``chunk_size`` row blocks exactly as the reference streams them) is n x k algebra on
+    the host.  Landmarks: the reference draws them with Rust's ``StdRng::seed_from_u64(2023)``
+    (:87-94); that stream is not reproduced -- numpy's ``default_rng(2023)`` is used instead
+    (pass ``landmarks`` to fix them).  Single GPU."""
+    if dist.world()[1] > 1:
+        raise NotImplementedError("the Nystrom path runs on a single GPU")
+    mask, fw = _feature_mask(selected_features, X.shape[1], feature_weights)
+    n = X.shape[0]
+    engine.load_csr(X)
+    if mask is not None:
+        engine.select_features(mask)
+    engine.set_feature_weights(fw)
+    degree = None
+    if landmarks is None and weighted_by_degree:
+        _, degree = engine.prepare()                        # compute_degrees (:328-360)
+    w, _rho = engine.prepare_projection()                   # idf over all cells (:76-84) + row norms
+    if landmarks is None:
+        rng = np.random.default_rng(2023)
+        if weighted_by_degree:                              # compute_probs (:362-365)
+            p = 1.0 / degree
+            landmarks = rng.choice(n, size=sample_size, replace=False, p=p / p.sum())
+        else:
+            landmarks = rng.choice(n, size=sample_size, replace=False)
+    landmarks = np.asarray(landmarks, dtype=np.int64)
+
+    # landmark rows (host slice, :95-99), embedded on a second context with the global weights
+    Xs = X[landmarks]
+    if mask is not None:
+        Xs = Xs[:, np.flatnonzero(mask)]
+    own_seed = seed_engine is None
+    seed = Engine(engine.device) if own_seed else seed_engine
+    try:
+        seed.load_csr(sp.csr_matrix(Xs))
+        seed.set_feature_weights(w)
+        _, d = seed.prepare()
+        v, u = seed.eigsh(n_components, seed=0, tol=tol, block=block)   # spectral_mf(seed, k, 0) (:104)
+        u = u / np.sqrt(d)[:, None]                          # :206-210
+        u = u / v[None, :]                                   # :211-215
+        proj = seed.project_t(u)                             # seed.T @ evecs
+    finally:
+        if own_seed:
+            seed.close()
+    q = engine.project(proj).astype(np.float64)              # sample @ (seed.T @ evecs), every cell
+    for i in range(0, n, chunk_size):                        # :224-227, per streamed chunk
+        qc = q[i:i + chunk_size]
+        t = qc.sum(axis=0) * v
+        dd = qc @ t
+        dd[dd <= 0] = np.min(dd[dd > 0])
+        qc /= np.sqrt(dd)[:, None]
+    if return_parts:
+        return v, q, w, d, landmarks
+    return v, q
+
+
 def spectral(
     adata,
     n_comps: int = 30,
@@ -159,17 +237,19 @@ def spectral(
             raise ValueError("when sample_size is a float, it should be > 0 and <= 1")
         sample_size = int(sample_size * n_sample)
 
-    if sample_size < n_sample:
-        raise NotImplementedError(
-            "the Nystrom approximation (sample_size < n_obs) is not part of the B200 path: the full "
-            "matrix-free operator is used instead; pass sample_size=None")
     if distance_metric != "cosine":
         raise NotImplementedError("only distance_metric='cosine' (the matrix-free path) runs on the GPU")
 
     eng = engine if engine is not None else default_engine()
     X = _get_csr(adata)
-    evals, evecs = spectral_embedding(eng, X, features, n_comps, random_state, feature_weights,
-                                      n_global=n_global, row0=row0, tol=tol, block=block)   # :249
+    if sample_size < n_sample:                                      # :257-265
+        logging.getLogger(__name__).info("Perform spectral embedding using the Nystrom algorithm...")
+        v, u = spectral_embedding_nystrom(eng, X, features, n_comps, sample_size, sample_method != "random",
+                                          chunk_size, feature_weights, tol=tol, block=block)
+        evals, evecs = orthogonalize(v, u)
+    else:
+        evals, evecs = spectral_embedding(eng, X, features, n_comps, random_state, feature_weights,
+                                          n_global=n_global, row0=row0, tol=tol, block=block)   # :249
     logging.getLogger(__name__).info("spectral: %s", eng.stats())
 
     if weighted_by_sd:                                              # :286-289

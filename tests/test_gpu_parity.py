@@ -230,3 +230,37 @@ def test_second_context_lifetime(engine):
     third = Engine(engine.device)
     third.generate(spec)
     third.close()
+
+
+@pytest.mark.parametrize("valued", [False, True])
+def test_nystrom_matches_oracle_given_landmarks(engine, valued):
+    """spectral_embedding_nystrom (embedding.rs:61-129, 194-267) with the landmark draw fixed:
+    IDF over all cells, landmark degrees, eigenvalues and the extended vectors against the oracle;
+    then the public sample_size path end to end (its own landmark draw) for shape and sanity."""
+    spec = synth.make_spec(6000, 30000, 400, n_clusters=16, seed=5)
+    engine.generate(spec)
+    X = engine.export_csr().astype(np.float64)
+    feats = None
+    if valued:
+        rng = np.random.default_rng(8)
+        X.data = rng.integers(1, 4, size=X.nnz).astype(np.float64)
+        feats = rng.random(X.shape[1]) < 0.8
+    lm = np.random.default_rng(1).choice(6000, 1500, replace=False)
+    k = 12
+    ev_o, q_o, w_o, d_o = oracle.spectral_embedding_nystrom(X, feats, k, lm, 2000, return_parts=True)
+    ev, q, w, d, lm2 = tl.spectral_embedding_nystrom(engine, X, feats, k, 1500, False, 2000, landmarks=lm,
+                                                     return_parts=True)
+    np.testing.assert_array_equal(lm2, lm)
+    np.testing.assert_allclose(w, w_o, rtol=1e-5)
+    np.testing.assert_allclose(d, d_o, rtol=1e-5)
+    np.testing.assert_allclose(ev, ev_o, rtol=1e-4)
+    assert q.shape == q_o.shape
+    assert eigvec_agreement(ev_o, q_o, q).min() >= 0.999
+    # row scaling (the per-chunk degree normalisation) agrees too, not only directions
+    np.testing.assert_allclose(np.linalg.norm(q, axis=0), np.linalg.norm(q_o, axis=0), rtol=1e-3)
+
+    ad = MiniAnnData(sp.csr_matrix(X))
+    evals, emb = tl.spectral(ad, n_comps=k, features=feats, sample_size=1500, chunk_size=2000, inplace=False,
+                             engine=engine)
+    assert emb.shape[0] == 6000 and emb.shape[1] == evals.shape[0] <= k
+    assert np.all(np.isfinite(emb)) and np.all(np.diff(evals) <= 1e-12)

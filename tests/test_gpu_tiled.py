@@ -129,3 +129,39 @@ def test_tiled_eigsh_parity_config1(engine, block):
     finally:
         engine.set_spmm_mode("auto")
         engine.set_block(4)
+
+
+@pytest.mark.parametrize("valued,block", [(False, 4), (True, 8)])
+def test_projection_products_tiled_and_csr(engine, valued, block):
+    """snapb200_project (the Nystrom extension's two products) through the tiled copies and through
+    the CSR kernels against scipy: Xhat @ M and Xhat.T @ U for k not a multiple of the block width."""
+    spec = synth.make_spec(27000, 30000, 200, n_clusters=20, seed=23)
+    engine.generate(spec)
+    X = engine.export_csr().astype(np.float64)
+    rng = np.random.default_rng(4)
+    if valued:
+        X.data = rng.integers(1, 6, size=X.nnz).astype(np.float64)
+    w = oracle.idf(sp.csr_matrix(X))
+    xhat = oracle.normalize(sp.csr_matrix(X), w)
+    k = 13
+    M = rng.standard_normal((30000, k)).astype(np.float32)
+    U = rng.standard_normal((27000, k)).astype(np.float32)
+    want = xhat @ M.astype(np.float64)
+    want_t = xhat.T @ U.astype(np.float64)
+    engine.set_block(block)
+    try:
+        for mode in ("csr", "tiled"):
+            engine.set_spmm_mode(mode)
+            engine.load_csr(X, binarized=not valued)
+            engine.set_feature_weights(None)
+            w_dev, rho = engine.prepare_projection()          # no transpose needed for Xhat @ M
+            np.testing.assert_allclose(w_dev, w, rtol=1e-5)
+            got = engine.project(M)
+            assert np.abs(got - want).max() / np.abs(want).max() < 2e-5, mode
+            engine.prepare()
+            got_t = engine.project_t(U)
+            assert np.abs(got_t - want_t).max() / np.abs(want_t).max() < 2e-5, mode
+            np.testing.assert_array_equal(engine.project(M), got)   # after the full prepare as well
+    finally:
+        engine.set_spmm_mode("auto")
+        engine.set_block(4)

@@ -86,9 +86,22 @@ def test_wrapper_argument_errors_before_any_gpu_work():
     with pytest.raises(ValueError):
         tl.spectral(ad, features=None, sample_size=1.5)      # :243
     with pytest.raises(NotImplementedError):
-        tl.spectral(ad, features=None, sample_size=10)
-    with pytest.raises(NotImplementedError):
         tl.spectral(ad, features=None, distance_metric="jaccard")
+    with pytest.raises(NotImplementedError):
+        tl.spectral(ad, features=None, sample_size=10, distance_metric="jaccard")
+
+
+def test_orthogonalize_matches_the_reference_statement():
+    import oracle
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal((400, 7))
+    v = np.sort(rng.uniform(0.01, 1.0, 7))[::-1]
+    ev, evec = tl.orthogonalize(v, u)
+    ev_o, evec_o = oracle.orthogonalize(v, u)
+    np.testing.assert_allclose(ev, ev_o, rtol=1e-12)
+    np.testing.assert_allclose(np.abs(evec), np.abs(evec_o), rtol=1e-9, atol=1e-12)
+    # columns are orthonormal and diagonalise the projected operator
+    np.testing.assert_allclose(evec.T @ evec, np.eye(7), atol=1e-9)
 
 
 def test_feature_mask_and_weight_permutation():
