@@ -1,3 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tiled.py -m gpu -x -q -k "nystrom or projection" 2>&1 | tail -25
+timeout 900 python scripts/bench_nystrom.py c2 20000 2>&1 | tail -1 | tee gpurun_out/bench_nystrom_c2.json
