@@ -103,6 +103,20 @@ void staged_copy(snapb200_ctx* c, const void* src, size_t elem, int64_t count, b
     SB_CUDA(cudaStreamSynchronize(c->stream));
 }
 
+// bad |= 2 if a row's column indices are not strictly increasing (the transpose and the tiled
+// format build rely on sorted, duplicate-free rows); one warp per row, coalesced
+__global__ void rows_sorted_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t nrows,
+                                   int* __restrict__ bad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    bool wrong = false;
+    for (int64_t r = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; r < nrows; r += nwarps) {
+        const int64_t s = ptr[r], e = ptr[r + 1];
+        for (int64_t p = s + lane; p + 1 < e; p += 32) wrong = wrong || (idx[p] >= idx[p + 1]);
+    }
+    if (wrong) atomicOr(bad, 2);
+}
+
 void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, int64_t m, const void* indptr,
               int indptr_bits, const void* indices, int indices_bits, const void* values, int value_kind,
               int on_device) {
@@ -195,11 +209,18 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
         SB_CUDA(cudaStreamSynchronize(st));
         if (!h) X.val.release();   // binarised input: pattern-only kernels
     }
+    if (nnz > 0 && n_local > 0) {
+        const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_local, 8), static_cast<int64_t>(c->num_sms) * 16));
+        rows_sorted_kernel<<<blocks, 256, 0, st>>>(X.ptr.p, X.idx.p, n_local, bad.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
     int hbad = 0;
     SB_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaEventRecord(c->ev1, st));
     SB_CUDA(cudaStreamSynchronize(st));
-    SB_CHECK(!hbad, "load_csr: column index out of range");
+    SB_CHECK(!(hbad & 1), "load_csr: column index out of range");
+    SB_CHECK(!(hbad & 2), "load_csr: column indices must be strictly increasing within every row (sorted, no duplicates)");
     float ms = 0.f;
     cudaEventElapsedTime(&ms, c->ev0, c->ev1);
     c->stats.ms_load = ms;

@@ -82,8 +82,9 @@ class Engine:
             X = sp.csr_matrix(np.asarray(X))
         if X.format != "csr":
             raise ValueError("X must be a CSR matrix (the reference rejects CSC input as well)")
-        if not X.has_sorted_indices:
-            X = X.sorted_indices()
+        if not X.has_canonical_format:      # sorted, duplicate-free rows are part of the C ABI contract
+            X = X.copy()
+            X.sum_duplicates()
         indptr = np.ascontiguousarray(X.indptr)
         indices = np.ascontiguousarray(X.indices)
         values = None

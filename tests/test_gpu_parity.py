@@ -264,3 +264,20 @@ def test_nystrom_matches_oracle_given_landmarks(engine, valued):
                              engine=engine)
     assert emb.shape[0] == 6000 and emb.shape[1] == evals.shape[0] <= k
     assert np.all(np.isfinite(emb)) and np.all(np.diff(evals) <= 1e-12)
+
+
+def test_unsorted_or_duplicate_rows_are_rejected(engine):
+    """The C ABI wants strictly increasing column indices per row; the raw entry point checks it
+    (the scipy-level loader canonicalises instead)."""
+    indptr = np.array([0, 3, 5], dtype=np.int64)
+    good = np.array([1, 4, 7, 0, 2], dtype=np.int32)
+    engine.load_arrays(indptr, good, None, 2, 8)
+    for bad in (np.array([4, 1, 7, 0, 2], dtype=np.int32), np.array([1, 4, 4, 0, 2], dtype=np.int32)):
+        with pytest.raises(RuntimeError, match="strictly increasing"):
+            engine.load_arrays(indptr, bad, None, 2, 8)
+    with pytest.raises(RuntimeError, match="out of range"):
+        engine.load_arrays(indptr, np.array([1, 4, 8, 0, 2], dtype=np.int32), None, 2, 8)
+    # scipy-level loader: duplicates are summed, order restored
+    X = sp.csr_matrix((np.ones(6), np.array([4, 1, 1, 7, 2, 0]), np.array([0, 4, 6])), shape=(2, 8))
+    engine.load_csr(X)
+    assert engine.shape() == (2, 8, 5)
