@@ -42,6 +42,14 @@ def allgather_ints(value: int) -> list[int]:
     return [int(v) for v in out]
 
 
+def allgather_objects(obj) -> list:
+    """Every rank's (picklable, small) object, in rank order."""
+    import torch.distributed as td
+    out = [None] * td.get_world_size()
+    td.all_gather_object(out, obj)
+    return out
+
+
 def shard_offsets(n_locals: list[int]) -> list[int]:
     """Global row offset of every rank's shard from the list of shard sizes."""
     offs, run = [], 0

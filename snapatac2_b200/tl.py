@@ -286,29 +286,40 @@ def multi_spectral_embedding(engine: Engine, xs, selected_features, weights, n_c
     the ordinary load/prepare/eigsh path with the concatenated IDF weights as
     feature weights and ``c_v / rho_v,i`` folded into the stored values, so the
     stacked rows already have unit norm exactly as in ``spectral_mf`` (:447).
+    Under ``torchrun`` every rank passes its block of cells of every view; the
+    sampled rows for the normaliser are exchanged over ``torch.distributed``.
     """
-    if dist.world()[1] > 1:
-        raise NotImplementedError("multi_spectral is single-GPU in this build")
+    rank, world = dist.world()
+    n_local = xs[0].shape[0]
+    if world > 1:      # every rank passes its own contiguous block of cells, the same block of every view
+        n_locals = dist.allgather_ints(n_local)
+        n_global, row0 = sum(n_locals), dist.shard_offsets(n_locals)[rank]
+    else:
+        n_global, row0 = n_local, 0
     views, idfs, norms = [], [], []
     for X, sel in zip(xs, selected_features):
         if not sp.issparse(X) or X.format != "csr":
             X = sp.csr_matrix(X)
+        if X.shape[0] != n_local:
+            raise ValueError("all views must hold the same cells")
         mask, _ = _feature_mask(sel, X.shape[1], None)
-        engine.load_csr(X)
+        engine.load_csr(X, n_global=n_global, row0=row0)
         if mask is not None:
             engine.select_features(mask)
             X = X[:, mask]
-        idf, rho = engine.view_norms()
+        idf, rho = engine.view_norms()          # document frequencies are all-reduced over the shards
         Xs = sp.csr_matrix(X, dtype=np.float64)
-        n = Xs.shape[0]
-        if n <= 2000:
-            rows = np.arange(n)
+        if n_global <= 2000:
+            rows = np.arange(n_global)
         elif sample_rows is not None:
-            rows = np.asarray(sample_rows)
+            rows = np.sort(np.asarray(sample_rows))
         else:
-            rows = np.sort(np.random.RandomState(2023).choice(n, 2000, replace=False))
-        xhat_s = sp.diags(1.0 / rho[rows]) @ (Xs[rows] @ sp.diags(idf))
-        norms.append(_frobenius_offdiag(sp.csr_matrix(xhat_s)))
+            rows = np.sort(np.random.RandomState(2023).choice(n_global, 2000, replace=False))
+        mine = rows[(rows >= row0) & (rows < row0 + n_local)] - row0
+        xhat_s = sp.csr_matrix(sp.diags(1.0 / rho[mine]) @ (Xs[mine] @ sp.diags(idf)))
+        if world > 1:   # the sampled unit rows of all shards, in global row order, on every rank
+            xhat_s = sp.csr_matrix(sp.vstack(dist.allgather_objects(xhat_s), format="csr"))
+        norms.append(_frobenius_offdiag(xhat_s))
         views.append((Xs, rho))
         idfs.append(idf)
     ws = [w / nrm for w, nrm in zip(weights, norms)]
@@ -317,7 +328,7 @@ def multi_spectral_embedding(engine: Engine, xs, selected_features, weights, n_c
     stacked = sp.csr_matrix(sp.hstack(scaled, format="csr"))
     stacked.sort_indices()
     fw = np.concatenate(idfs)
-    out = spectral_embedding(engine, stacked, None, n_components, random_state, fw,
+    out = spectral_embedding(engine, stacked, None, n_components, random_state, fw, n_global=n_global, row0=row0,
                              tol=tol, block=block, return_parts=return_parts)
     if return_parts:
         return out + (norms,)
@@ -337,7 +348,10 @@ def multi_spectral(adatas, n_comps: int = 30, features="selected", weights=None,
         features = [_resolve_features(a, f) for a, f in zip(adatas, features)]
     if weights is None:                                                     # :530-531
         weights = [1.0 for _ in adatas]
-    n_comps = min(min(a.n_obs for a in adatas) - 1, n_comps)
+    n_obs = min(a.n_obs for a in adatas)
+    if dist.world()[1] > 1:
+        n_obs = sum(dist.allgather_ints(n_obs))
+    n_comps = min(n_obs - 1, n_comps)
     eng = engine if engine is not None else default_engine()
     evals, evecs = multi_spectral_embedding(eng, [_get_csr(a) for a in adatas], features, weights,
                                             n_comps, random_state, sample_rows=sample_rows)   # :533

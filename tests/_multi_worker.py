@@ -58,6 +58,31 @@ if rank == 0:
     assert abs(np.linalg.norm(evec_all[:, 3]) - 1.0) < 1e-5
     print(f"MULTI_OK world={world} mode={mode} n_ops={stats['n_ops']} ms_comm={stats['ms_comm']:.3f} min_cos={cos.min():.8f}")
     solo.close()
+
+# ---- multi-view (tl.multi_spectral, embedding.rs:388-452) on row shards: every rank passes its
+#      block of both views; the result must match the CPU oracle on the full views
+spec_b = synth.make_spec(spec.n, 4000, 150, n_clusters=40, seed=4)
+eng.set_feature_weights(None)
+eng.generate(spec_b, row0=r0, n_local=r1 - r0)
+XB_local = eng.export_csr().astype(np.float64)
+XB_local.data = 1.0 + (XB_local.indices % 3)          # counts: a function of the column, shard independent
+rows = np.sort(np.random.RandomState(7).choice(spec.n, 2000, replace=False))
+km = 12
+ev_m, emb_m = tl.multi_spectral([MiniAnnData(X_local), MiniAnnData(XB_local)], n_comps=km, features=None,
+                                weights=[1.0, 0.5], weighted_by_sd=False, engine=eng, sample_rows=rows)
+parts_m = [None] * world
+td.gather_object(emb_m, parts_m if rank == 0 else None, dst=0)
+if rank == 0:
+    import oracle
+    from conftest import eigvec_agreement
+    XA = synth.generate_csr(spec, dtype=np.float64)
+    XB = synth.generate_csr(spec_b, dtype=np.float64)
+    XB.data = 1.0 + (XB.indices % 3)
+    ev_o, evec_o = oracle.multi_spectral_embedding([XA, XB], [None, None], [1.0, 0.5], km, 0, sample_rows=rows)
+    emb_all = np.concatenate(parts_m, axis=0)
+    np.testing.assert_allclose(ev_m, ev_o, rtol=1e-4)
+    assert eigvec_agreement(ev_o, evec_o, emb_all).min() >= 0.999
+    print(f"MULTIVIEW_OK world={world}")
 td.barrier()
 eng.close()
 td.destroy_process_group()

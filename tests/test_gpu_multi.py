@@ -27,3 +27,4 @@ def test_shard_invariance(mode):
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "MULTI_OK" in res.stdout
+    assert "MULTIVIEW_OK" in res.stdout
