@@ -148,6 +148,13 @@ df = torch.from_numpy(np.bincount(mine.indices, minlength=spec.m).astype(np.int6
 td.all_reduce(df)
 full = synth.generate_csr(spec)
 assert np.array_equal(df.numpy(), np.bincount(full.indices, minlength=spec.m))
+# multi_spectral's exchange of the sampled rows: shard pieces stacked in rank order = the global rows
+import scipy.sparse as sp
+rows = np.sort(np.random.RandomState(3).choice(spec.n, 40, replace=False))
+r0 = int(bounds[rank])
+local = rows[(rows >= r0) & (rows < r0 + mine.shape[0])] - r0
+stacked = sp.vstack(dist.allgather_objects(sp.csr_matrix(mine[local])), format="csr")
+assert (stacked != full[rows]).nnz == 0
 td.barrier()
 td.destroy_process_group()
 print("ok", rank)
