@@ -120,7 +120,8 @@ def orthogonalize(evals, evecs):
 
 def spectral_embedding_nystrom(engine: Engine, X, selected_features, n_components, sample_size,
                                weighted_by_degree, chunk_size, feature_weights=None, *, landmarks=None,
-                               seed_engine: Engine | None = None, tol=0.0, block=0, return_parts=False):
+                               seed_engine: Engine | None = None, tol=0.0, block=0, return_parts=False,
+                               stream: bool | None = None):
     """Counterpart of ``internal.spectral_embedding_nystrom`` (embedding.rs:61-129): spectral
     embedding of ``sample_size`` landmark cells, extended to every cell (``nystrom``, :194-267).
 
@@ -131,19 +132,50 @@ def spectral_embedding_nystrom(engine: Engine, X, selected_features, n_component
     ``chunk_size`` row blocks exactly as the reference streams them) is n x k algebra on
     the host.  Landmarks: the reference draws them with Rust's ``StdRng::seed_from_u64(2023)``
     (:87-94); that stream is not reproduced -- numpy's ``default_rng(2023)`` is used instead
-    (pass ``landmarks`` to fix them).  Single GPU."""
+    (pass ``landmarks`` to fix them).  Single GPU.
+
+    ``stream=True`` keeps only one ``chunk_size`` block of cells on the device at a time, the
+    way the reference iterates a backed AnnData (:76-84, :109-118): document frequencies are
+    accumulated chunk by chunk, then every chunk is loaded, normalised and projected on its
+    own.  Default: stream when the matrix would not fit next to its tiled copy (> 6e9 stored
+    entries).  Degree-weighted landmark sampling needs the degrees of all cells and is only
+    available without streaming."""
     if dist.world()[1] > 1:
         raise NotImplementedError("the Nystrom path runs on a single GPU")
     mask, fw = _feature_mask(selected_features, X.shape[1], feature_weights)
     n = X.shape[0]
-    engine.load_csr(X)
-    if mask is not None:
-        engine.select_features(mask)
-    engine.set_feature_weights(fw)
+    cols = None if mask is None else np.flatnonzero(mask)
+    if stream is None:
+        stream = X.nnz > 6_000_000_000
     degree = None
-    if landmarks is None and weighted_by_degree:
-        _, degree = engine.prepare()                        # compute_degrees (:328-360)
-    w, _rho = engine.prepare_projection()                   # idf over all cells (:76-84) + row norms
+    if stream:
+        if landmarks is None and weighted_by_degree:
+            raise NotImplementedError("degree-weighted landmarks need the whole matrix on the device (stream=False)")
+        if fw is not None:
+            w = np.asarray(fw, dtype=np.float64)
+        else:                                               # idf_from_chunks (:288-312)
+            m_sel = X.shape[1] if cols is None else cols.size
+            df = np.zeros(m_sel, dtype=np.int64)
+            for i in range(0, n, chunk_size):
+                Xc = X[i:i + chunk_size]
+                if cols is not None:
+                    Xc = Xc[:, cols]
+                df += np.bincount(Xc.indices, minlength=m_sel)
+            if np.all(df == df[0]):
+                w = np.ones(m_sel, dtype=np.float64)
+            else:
+                d = df.astype(np.float64)
+                d[d == 0] = 1.0
+                d[d == n] = n - 1.0
+                w = np.log(n / d)
+    else:
+        engine.load_csr(X)
+        if mask is not None:
+            engine.select_features(mask)
+        engine.set_feature_weights(fw)
+        if landmarks is None and weighted_by_degree:
+            _, degree = engine.prepare()                    # compute_degrees (:328-360)
+        w, _rho = engine.prepare_projection()               # idf over all cells (:76-84) + row norms
     if landmarks is None:
         rng = np.random.default_rng(2023)
         if weighted_by_degree:                              # compute_probs (:362-365)
@@ -170,7 +202,17 @@ def spectral_embedding_nystrom(engine: Engine, X, selected_features, n_component
     finally:
         if own_seed:
             seed.close()
-    q = engine.project(proj).astype(np.float64)              # sample @ (seed.T @ evecs), every cell
+    if stream:                                               # sample @ (seed.T @ evecs), chunk by chunk
+        q = np.empty((n, proj.shape[1]), dtype=np.float64)
+        for i in range(0, n, chunk_size):
+            Xc = X[i:i + chunk_size]
+            if cols is not None:
+                Xc = Xc[:, cols]
+            engine.load_csr(sp.csr_matrix(Xc))
+            engine.set_feature_weights(w)
+            q[i:i + chunk_size] = engine.project(proj)
+    else:
+        q = engine.project(proj).astype(np.float64)          # ... or for every cell at once
     for i in range(0, n, chunk_size):                        # :224-227, per streamed chunk
         qc = q[i:i + chunk_size]
         t = qc.sum(axis=0) * v

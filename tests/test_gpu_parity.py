@@ -258,6 +258,10 @@ def test_nystrom_matches_oracle_given_landmarks(engine, valued):
     assert eigvec_agreement(ev_o, q_o, q).min() >= 0.999
     # row scaling (the per-chunk degree normalisation) agrees too, not only directions
     np.testing.assert_allclose(np.linalg.norm(q, axis=0), np.linalg.norm(q_o, axis=0), rtol=1e-3)
+    # chunk-streamed variant (one chunk_size block of cells on the device at a time): same numbers
+    ev_s, q_s = tl.spectral_embedding_nystrom(engine, X, feats, k, 1500, False, 2000, landmarks=lm, stream=True)
+    np.testing.assert_allclose(ev_s, ev, rtol=1e-9)
+    assert np.abs(q_s - q).max() <= 1e-4 * np.abs(q).max()
 
     ad = MiniAnnData(sp.csr_matrix(X))
     evals, emb = tl.spectral(ad, n_comps=k, features=feats, sample_size=1500, chunk_size=2000, inplace=False,
