@@ -285,3 +285,14 @@ def test_unsorted_or_duplicate_rows_are_rejected(engine):
     X = sp.csr_matrix((np.ones(6), np.array([4, 1, 1, 7, 2, 0]), np.array([0, 4, 6])), shape=(2, 8))
     engine.load_csr(X)
     assert engine.shape() == (2, 8, 5)
+
+
+def test_nystrom_golden_fixture(engine):
+    X, z = load_golden("nystrom_500x3000")
+    k, chunk, lm = int(z["k"]), int(z["chunk_size"]), z["landmarks"]
+    ev, q, w, d, _ = tl.spectral_embedding_nystrom(engine, X, None, k, lm.size, False, chunk, landmarks=lm,
+                                                   return_parts=True)
+    np.testing.assert_allclose(w, z["idf"], rtol=TOL_VEC)
+    np.testing.assert_allclose(d, z["degree"], rtol=TOL_VEC)
+    np.testing.assert_allclose(ev, z["evals"], rtol=TOL_EVAL)
+    assert eigvec_agreement(z["evals"], z["q"], q).min() >= MIN_COS

@@ -87,3 +87,25 @@ def test_multi_view_restatement_runs():
     a, b = synth.generate_csr(s1, dtype=np.float64), synth.generate_csr(s2, dtype=np.float64)
     ev, evec = oracle.multi_spectral_embedding([a, b], [None, None], [1.0, 1.0], 4, 0)
     assert ev.shape == (4,) and evec.shape == (150, 4) and ev[0] == pytest.approx(1.0, abs=1e-10)
+
+
+def test_nystrom_golden_and_its_structure():
+    """Oracle restatement of the Nystrom path against the committed fixture (itself cross-checked
+    with a dense eigh statement by make_golden.py), plus two structural properties: landmark cells
+    are extended exactly like any other cell, and the result depends on chunk_size only through the
+    per-chunk degree normalisation."""
+    X, z = load_golden("nystrom_500x3000")
+    k, chunk, lm = int(z["k"]), int(z["chunk_size"]), z["landmarks"]
+    ev, q, w, d = oracle.spectral_embedding_nystrom(X, None, k, lm, chunk, return_parts=True)
+    np.testing.assert_allclose(w, z["idf"], rtol=1e-12)
+    np.testing.assert_allclose(d, z["degree"], rtol=1e-10)
+    np.testing.assert_allclose(ev, z["evals"], rtol=1e-9)
+    assert eigvec_agreement(z["evals"], z["q"], q).min() > 1 - 1e-8
+    # one chunk = all rows: directions per row group change only by the chunk-wise scaling
+    ev1, q1 = oracle.spectral_embedding_nystrom(X, None, k, lm, X.shape[0])
+    ratio = q1[:chunk] / q[:chunk]
+    np.testing.assert_allclose(ratio, np.repeat(ratio[:, :1], k, axis=1), rtol=1e-8)
+    # orthogonalize: orthonormal columns, eigenvalues sorted descending
+    evo, qo = oracle.orthogonalize(ev, q)
+    np.testing.assert_allclose(np.real(qo).T @ np.real(qo), np.eye(k), atol=1e-8)
+    assert np.all(np.diff(np.real(evo)) <= 1e-12)
