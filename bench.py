@@ -294,7 +294,11 @@ def run_ours(args):
     tf = ROOT / "profiles" / "spmm_traffic.json"
     if tf.exists():
         try:
-            traffic = json.loads(tf.read_text()).get("dram_bytes_per_application")
+            tj = json.loads(tf.read_text())
+            traffic = tj.get("dram_bytes_per_application")
+            if traffic is not None and tj.get("nnz_of_capture"):
+                # the ncu capture was taken on one GPU at C3; DRAM traffic is proportional to the stored entries
+                traffic = float(traffic) * nnz_local / float(tj["nnz_of_capture"])
         except Exception:
             traffic = None
     roofline = {
