@@ -1,7 +1,13 @@
 """Numpy/scipy restatement of SnapATAC2's matrix-free spectral embedding.
 
-TEST INFRASTRUCTURE (see ``oracle/__init__.py``); parity unpinned by reference
-golden vectors (none exist), pinned by ``dense_check`` and ``matrix_free_twin``.
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  PINNED against outputs of the
+reference's own code executed in the build container
+(``tests/golden/make_ref_golden.py`` -> ``tests/golden/*_ref.npz``): the pure-Python
+``SpectralMatrixFree.fit``/``_eigen``/``orthogonalize``/``spectral`` of
+``tools/_embedding.py`` run unmodified, and the Python snippet embedded in
+``frobenius_norm`` (embedding.rs:456-460) executed on both scipy containers.  What
+stays restatement-only: the Rust IDF (embedding.rs:269-286, a closed form checked
+separately) and the Rust RNG draws (landmarks, multi-view row sample).
 
 Every function names the reference lines it follows.  Paths are relative to
 ``/root/reference``; ``embedding.rs`` = ``snapatac2-python/src/embedding.rs`` and
@@ -254,15 +260,43 @@ def spectral(adata, n_comps=30, features="selected", random_state=0, sample_size
 # --------------------------------------------------------------------------
 # a8: multi-view                                         embedding.rs:367-477
 # --------------------------------------------------------------------------
-def _frobenius_norm(xhat: sp.csr_matrix) -> float:
-    """``sqrt(sum((X X^T)^2) - n)`` (embedding.rs:454-471)."""
-    s = (xhat @ xhat.T)
-    total = float(s.multiply(s).sum())
+def _frobenius_snippet(X):
+    """The Python snippet embedded in ``frobenius_norm`` (embedding.rs:456-460), verbatim."""
+    import numpy as np
+    return np.power(X @ X.T, 2).sum()
+
+
+def _frobenius_norm(xhat: sp.csr_matrix, container: str = "csr_matrix") -> float:
+    """``frobenius_norm`` (embedding.rs:454-471): ``sqrt(snippet(X) - n)``.
+
+    What the snippet computes depends on the scipy container it is handed, because
+    ``np.power`` on a scipy sparse object falls through to the object's ``__pow__``:
+
+    * ``csr_matrix`` (the ``spmatrix`` interface): ``__pow__`` is the MATRIX power, so the
+      snippet returns ``sum((X X^T) @ (X X^T)) = || (X X^T) 1 ||^2``;
+    * ``csr_array`` (the ``sparray`` interface): ``__pow__`` is element-wise, so the snippet
+      returns ``|| X X^T ||_F^2`` -- what the function name promises.
+
+    The reference passes ``PyArrayData::from(ArrayData::from(x))`` (embedding.rs:467);
+    pyanndata is pinned to kaizhang/anndata-rs rev 0d27ac4 (snapatac2-python/Cargo.toml:22)
+    and is not vendored under /root/reference.  Its CSR -> Python conversion builds
+    ``scipy.sparse.csr_matrix`` (recalled from the published source of that crate; it cannot
+    be checked offline), so ``container="csr_matrix"`` is the default here and in the CUDA
+    path; both readings are pinned against the executed snippet
+    (tests/golden/frobenius_snippet_ref.npz).
+    """
+    if container == "csr_matrix":
+        X = sp.csr_matrix(xhat)
+    elif container == "csr_array":
+        X = sp.csr_array(xhat)
+    else:
+        raise ValueError("container must be 'csr_matrix' or 'csr_array'")
+    total = float(_frobenius_snippet(X))
     return float(np.sqrt(total - xhat.shape[0]))
 
 
 def multi_spectral_embedding(xs, selected_features, weights, n_components, random_state,
-                             sample_rows=None, return_parts=False):
+                             sample_rows=None, return_parts=False, container="csr_matrix"):
     """``multi_spectral_embedding`` (embedding.rs:388-452).
 
     Per view: slice, IDF, normalise (:404-416); Frobenius norm of the
@@ -280,11 +314,11 @@ def multi_spectral_embedding(xs, selected_features, weights, n_components, rando
         mat = _select_columns(x, sel)
         xhat = normalize(mat, idf(mat))
         if xhat.shape[0] <= 2000:
-            nrm = _frobenius_norm(xhat)
+            nrm = _frobenius_norm(xhat, container)
         else:
             if sample_rows is None:
                 raise ValueError("n > 2000: pass sample_rows (the reference's Rust RNG is not reproducible here)")
-            nrm = _frobenius_norm(xhat[np.asarray(sample_rows)])
+            nrm = _frobenius_norm(xhat[np.asarray(sample_rows)], container)
         mats.append(xhat)
         norms.append(nrm)
     ws = [w / nrm for w, nrm in zip(weights, norms)]
@@ -298,7 +332,7 @@ def multi_spectral_embedding(xs, selected_features, weights, n_components, rando
 
 
 def multi_spectral(adatas, n_comps=30, features="selected", weights=None, random_state=0,
-                   weighted_by_sd=True, sample_rows=None):
+                   weighted_by_sd=True, sample_rows=None, container="csr_matrix"):
     """Wrapper semantics of ``snap.tl.multi_spectral`` (_embedding.py:483-540)."""
     np.random.seed(random_state)
     if features is None or isinstance(features, str):
@@ -308,7 +342,7 @@ def multi_spectral(adatas, n_comps=30, features="selected", weights=None, random
     if weights is None:
         weights = [1.0 for _ in adatas]
     evals, evecs = multi_spectral_embedding([a.X for a in adatas], features, weights,
-                                            n_comps, random_state, sample_rows=sample_rows)
+                                            n_comps, random_state, sample_rows=sample_rows, container=container)
     if weighted_by_sd:
         keep = [i for i in range(evals.shape[0]) if evals[i] > 0]
         evals = evals[keep]

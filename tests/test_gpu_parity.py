@@ -59,6 +59,29 @@ def test_golden_vectors(engine, name):
     assert np.all(np.diff(evals) <= 0)                      # argsort()[::-1]
 
 
+@pytest.mark.parametrize("name", ["tile_600x4000", "counts_300x1000", "masked_400x3000"])
+def test_reference_executed_vectors(engine, name):
+    """CUDA path against vectors produced by running the reference's own Python code
+    (SpectralMatrixFree.fit/_eigen, tools/_embedding.py:434-481; tests/golden/make_ref_golden.py)."""
+    from conftest import GOLDEN
+    X, z = load_golden(name)
+    r = np.load(GOLDEN / f"{name}_ref.npz")
+    feats = z["features"] if "features" in z else None
+    fw = z["feature_weights"] if "feature_weights" in z else None
+    evals, evecs, idf, deg = tl.spectral_embedding(engine, X, feats, int(z["k"]), 0, fw, return_parts=True)
+    np.testing.assert_allclose(idf, r["weights"], rtol=TOL_VEC)
+    np.testing.assert_allclose(deg, r["degree"], rtol=TOL_VEC)
+    _check_against(r["evals"], r["evecs"], evals, evecs)
+    # wrapper post-processing against the reference's spectral() run unmodified
+    ad = MiniAnnData(X)
+    ev_w, emb_w = tl.spectral(ad, n_comps=int(z["k"]), features=feats, feature_weights=fw, inplace=False, engine=engine)
+    np.testing.assert_allclose(ev_w, r["wrapped_evals"], rtol=TOL_EVAL)
+    cos = eigvec_agreement(r["wrapped_evals"], r["wrapped_evecs"], emb_w)
+    assert cos.min() >= MIN_COS, cos
+    scale = np.linalg.norm(emb_w, axis=0) / np.linalg.norm(r["wrapped_evecs"], axis=0)
+    np.testing.assert_allclose(scale, 1.0, rtol=1e-4)
+
+
 def test_golden_dense_50x100_exhausts_krylov_space(engine):
     # the reference's own test input shape (tests/test_tools.py:95-110): n=50, k=30
     X, z = load_golden("dense_50x100")
