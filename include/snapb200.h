@@ -61,6 +61,9 @@ typedef struct snapb200_stats {
     double ms_prepare_wall; /* host wall clock of the whole prepare call        */
     double ms_pool;        /* host time spent in cudaMalloc/cudaFree by the caching allocator (cumulative) */
     int64_t pool_mallocs;  /* driver allocations so far (cumulative; a steady state adds none)             */
+    int64_t converged;     /* last eigsh: 1 = every pair met the tolerance (or the Krylov space was exhausted),
+                              0 = max_ops reached first (scipy's eigsh raises ArpackNoConvergence there)   */
+    int64_t n_spec_ops;    /* operator applications enqueued ahead of the convergence check and discarded  */
 } snapb200_stats;
 
 /* Library / error plumbing. */
@@ -179,6 +182,9 @@ int  snapb200_get_stream(snapb200_ctx* ctx, void** stream);
  * Rayleigh-Ritz eigensolver (a: n x n row-major, destroyed; eigenvalues
  * ascending in w, eigenvectors in the columns of a) and needs no GPU. */
 int  snapb200_dense_selftest(snapb200_ctx* ctx, int64_t n, int ncq, int p, double* max_rel_err);
+/* ortho_selftest builds an orthonormal basis of `ncols` columns from random blocks of width `block`
+ * with the eigensolver's fused orthogonalisation kernels and returns max |Q^T Q - I|. */
+int  snapb200_ortho_selftest(snapb200_ctx* ctx, int64_t n, int ncols, int block, double* max_err);
 int  snapb200_sym_eig(int n, double* a, double* w);
 
 #ifdef __cplusplus

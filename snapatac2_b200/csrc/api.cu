@@ -126,9 +126,18 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     SB_CHECK(indices_bits == 32 || indices_bits == 64, "load_csr: indices_bits must be 32 or 64");
     SB_CHECK(indptr != nullptr, "load_csr: null indptr");
     cudaStream_t st = c->stream;
-    SB_CUDA(cudaEventRecord(c->ev0, st));
     const bool dev = on_device != 0;
+    // device-resident input was produced on the caller's stream(s), which this library's private
+    // non-blocking stream does not order with: wait for the device before reading it
+    if (dev) SB_CUDA(cudaDeviceSynchronize());
+    SB_CUDA(cudaEventRecord(c->ev0, st));
     Csr& X = c->X;
+    // the context holds no usable matrix until this load has passed validation
+    c->loaded = false;
+    c->prepared = false;
+    c->nnz_mode = -1;
+    c->S1.clear();
+    c->S2.clear();
     c->Xt.clear();
     c->xt_built = false;
     c->XtT.clear();
@@ -479,6 +488,10 @@ int snapb200_get_stream(snapb200_ctx* c, void** stream) {
 }
 
 // ---- test hooks (not part of the reference-facing surface) -----------------
+int snapb200_ortho_selftest(snapb200_ctx* c, int64_t n, int ncols, int block, double* max_err) {
+    return guarded([&] { bind(c); *max_err = ortho_selftest(c, n, ncols, block); });
+}
+
 int snapb200_dense_selftest(snapb200_ctx* c, int64_t n, int ncq, int p, double* max_rel_err) {
     return guarded([&] { bind(c); *max_rel_err = dense_selftest(c, n, ncq, p); });
 }

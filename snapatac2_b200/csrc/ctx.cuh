@@ -159,6 +159,10 @@ struct snapb200_ctx {
     snapb::Sell S2;  // tiled copy of X  (pass 2: gathers W rows by feature)
     snapb::Sell S1;  // tiled copy of Xt (pass 1: gathers r.*V rows by cell)
     int spmm_mode = 0;   // 0 = auto, 1 = CSR gather from L2, 2 = shared-memory tiled SELL
+    // stored entries per rank averaged over the communicator (set by prepare / prepare_projection,
+    // -1 = unknown): the automatic kernel choice must be the same on every rank, or the ranks would
+    // disagree on block widths and all-reduce counts
+    int64_t nnz_mode = -1;
     // default Lanczos block width (prepare builds the tiled copies for it).  4: a dense row is one
     // 16-byte bank group, half the shared-memory traffic per entry of b = 8; the solver needs ~1.6x the
     // operator applications but each costs less than half.
@@ -232,8 +236,9 @@ void weights_and_norms(snapb200_ctx* c, double* w_dev, double* rho_dev);
 // Y[n x b] (leading dim ldy) = X~ X~^T V - dinv .* V, V with leading dim ldv.
 // evs (optional, 4 events): recorded before pass 1, after pass 1, after the
 // all-reduce, after pass 2.
+// vr_ready: c->Vr already holds r .* V (the eigensolver's append kernel writes it), skip the scaling kernel.
 void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, int b,
-                        cudaEvent_t* evs = nullptr);
+                        cudaEvent_t* evs = nullptr, bool vr_ready = false);
 
 // products with Xhat = diag(1/rho) P diag(w) on k dense columns (Nystrom extension)
 void prepare_projection(snapb200_ctx* c);
@@ -253,6 +258,8 @@ void sell_spmm(snapb200_ctx* c, const Sell& S, const float* in, float* out, cons
 void sell_spmv64(snapb200_ctx* c, const Sell& S, const double* x, int mode, const double* scale, double shift,
                  double* out);
 bool use_tiled(const snapb200_ctx* c, int b);
+// agree on the stored-entry count the automatic kernel choice looks at (collective over the ranks)
+void decide_spmm_mode(snapb200_ctx* c);
 // (re)build S1/S2 for block width b if they are missing or sized for another width
 void ensure_tiled(snapb200_ctx* c, int b);
 

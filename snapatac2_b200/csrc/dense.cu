@@ -24,8 +24,66 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // --------------------------------------------------------------------------
-// Gram: partial[cta][ncq x B] = Q[rows of cta, 0:ncq]^T Z[rows of cta, 0:B]
-// grid = (row chunks, column groups of 64); 8 warps per CTA.
+// Fixed-order reduction of per-CTA partial sums by the LAST CTA of a grid to finish (ticket from
+// an atomic counter that the last CTA resets): out[e] = sum_p partial[p][e], p ascending.  Only the
+// identity of the reducing CTA depends on timing, never the order of the additions, so the result
+// is bitwise reproducible -- and the separate reduce launch of the first version is gone.
+// Returns true on the reducing CTA (after the result is written).
+// --------------------------------------------------------------------------
+constexpr int kLastRedSlots = 3072;   // doubles of shared memory for the slice sums
+
+__device__ bool last_cta_reduce(const double* __restrict__ partial, int n_parts, int len, double* __restrict__ out,
+                                unsigned* __restrict__ counter, unsigned n_ctas, double* red /* kLastRedSlots */) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == n_ctas - 1;
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    if (len <= kLastRedSlots) {
+        // len x S work items: slice s of the partials for element e; slices combined in order afterwards
+        const int S = max(1, min(8, min(kLastRedSlots / len, n_parts)));
+        for (int item = threadIdx.x; item < len * S; item += blockDim.x) {
+            const int e = item % len, sl = item / len;
+            const int p0 = static_cast<int>(static_cast<int64_t>(n_parts) * sl / S);
+            const int p1 = static_cast<int>(static_cast<int64_t>(n_parts) * (sl + 1) / S);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int p = p0;
+            for (; p + 3 < p1; p += 4) {
+                a0 += __ldcg(partial + static_cast<int64_t>(p) * len + e);
+                a1 += __ldcg(partial + static_cast<int64_t>(p + 1) * len + e);
+                a2 += __ldcg(partial + static_cast<int64_t>(p + 2) * len + e);
+                a3 += __ldcg(partial + static_cast<int64_t>(p + 3) * len + e);
+            }
+            for (; p < p1; ++p) a0 += __ldcg(partial + static_cast<int64_t>(p) * len + e);
+            red[item] = (a0 + a1) + (a2 + a3);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < len; e += blockDim.x) {
+            double t = 0.0;
+            for (int sl = 0; sl < S; ++sl) t += red[sl * len + e];
+            out[e] = t;
+        }
+    } else {
+        for (int e = threadIdx.x; e < len; e += blockDim.x) {
+            double t = 0.0;
+            for (int p = 0; p < n_parts; ++p) t += __ldcg(partial + static_cast<int64_t>(p) * len + e);
+            out[e] = t;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *counter = 0u;
+    return true;
+}
+
+// --------------------------------------------------------------------------
+// Gram: H[(ncq + nzx) x B] = [Q[:, 0:ncq] | Zx[:, 0:nzx]]^T Z[:, 0:B]
+// The optional extension block Zx (usually Z itself) rides along as extra basis columns, so
+// one pass gives the projection coefficients Q^T Z AND the block's own Gram Z^T Z -- one kernel
+// and one all-reduce instead of two of each.
+// grid = (row chunks, column groups of 64); 8 warps per CTA; per-CTA partials, summed in a fixed
+// order by the last CTA (last_cta_reduce).
 // DMMA roles: m = 8 basis columns, n = 8 block columns, k = 4 rows.
 // Column permutation inside a 32-column group so that one float4 load feeds
 // four tiles: tile t, fragment row mi  <->  column 32*(t/4) + 4*mi + (t%4).
@@ -35,14 +93,17 @@ constexpr int kGramCols = 64;  // basis columns per CTA (8 tiles)
 
 template <int B>
 __global__ void __launch_bounds__(kGramWarps * 32)
-gram_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const float* __restrict__ Z, int64_t ldz, int64_t n,
-            double* __restrict__ partial) {
+gram_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const float* __restrict__ Zx, int64_t ldzx, int nzx,
+            const float* __restrict__ Z, int64_t ldz, int64_t n, double* __restrict__ partial,
+            double* __restrict__ out, unsigned* __restrict__ counter) {
     constexpr int NT = (B + 7) / 8;
     __shared__ double red[kGramWarps][NT][64];
+    __shared__ double lastred[kLastRedSlots];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int mi = lane >> 2, ki = lane & 3;
     const int c_base = blockIdx.y * kGramCols;
+    const int ncx = ncq + nzx;
 
     int64_t chunk = (n + gridDim.x - 1) / gridDim.x;
     chunk = (chunk + 3) / 4 * 4;
@@ -55,9 +116,12 @@ gram_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const float* __re
 #pragma unroll
         for (int u = 0; u < NT; ++u) acc[t][u][0] = acc[t][u][1] = 0.0;
 
-    // which of the two 32-column groups of this CTA have columns < ncq
-    const bool g0 = (c_base + 4 * mi) < ncq;
-    const bool g1 = (c_base + 32 + 4 * mi) < ncq;
+    // the two float4 column groups of this lane: from the basis, from the extension block, or none
+    const int cg0 = c_base + 4 * mi, cg1 = c_base + 32 + 4 * mi;
+    const float* p0 = nullptr; int64_t ld0 = 0;
+    const float* p1 = nullptr; int64_t ld1 = 0;
+    if (cg0 < ncq) { p0 = Q + cg0; ld0 = ldq; } else if (cg0 < ncx) { p0 = Zx + (cg0 - ncq); ld0 = ldzx; }
+    if (cg1 < ncq) { p1 = Q + cg1; ld1 = ldq; } else if (cg1 < ncx) { p1 = Zx + (cg1 - ncq); ld1 = ldzx; }
 
     for (int64_t r = r_lo + 4 * warp; r < r_hi; r += 4 * kGramWarps) {
         const int64_t row = r + ki;
@@ -69,8 +133,8 @@ gram_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const float* __re
             bf[u] = (valid && col < B) ? static_cast<double>(Z[row * ldz + col]) : 0.0;
         }
         float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-        if (valid && g0) a0 = *reinterpret_cast<const float4*>(Q + row * ldq + c_base + 4 * mi);
-        if (valid && g1) a1 = *reinterpret_cast<const float4*>(Q + row * ldq + c_base + 32 + 4 * mi);
+        if (valid && p0) a0 = *reinterpret_cast<const float4*>(p0 + row * ld0);
+        if (valid && p1) a1 = *reinterpret_cast<const float4*>(p1 + row * ld1);
         const double av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
 #pragma unroll
         for (int t = 0; t < 8; ++t)
@@ -79,7 +143,7 @@ gram_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const float* __re
     }
 
     // fixed-order reduction over the CTA's warps, one tile row at a time
-    double* out = partial + static_cast<int64_t>(blockIdx.x) * ncq * B;
+    double* outp = partial + static_cast<int64_t>(blockIdx.x) * ncx * B;
 #pragma unroll
     for (int t = 0; t < 8; ++t) {
 #pragma unroll
@@ -97,46 +161,28 @@ gram_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const float* __re
             const int fl = f >> 1, fmi = fl >> 2, fni = (fl & 3) * 2 + (f & 1);
             const int col = c_base + 32 * (t >> 2) + 4 * fmi + (t & 3);   // basis column (H row)
             const int bc = u * 8 + fni;                                    // block column (H col)
-            if (col < ncq && bc < B) out[static_cast<int64_t>(col) * B + bc] = s;
+            if (col < ncx && bc < B) outp[static_cast<int64_t>(col) * B + bc] = s;
         }
         __syncthreads();
     }
-}
-
-// H[e] = sum over CTAs (fixed order) of partial[cta][e]
-__global__ void reduce_partials_kernel(const double* __restrict__ partial, int n_parts, int64_t len,
-                                       double* __restrict__ out) {
-    int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (e >= len) return;
-    double s = 0.0;
-    for (int p = 0; p < n_parts; ++p) s += partial[static_cast<int64_t>(p) * len + e];
-    out[e] = s;
+    last_cta_reduce(partial, gridDim.x, ncx * B, out, counter, gridDim.x * gridDim.y, lastred);
 }
 
 // --------------------------------------------------------------------------
-// Cholesky of the B x B Gram matrix, G = R^T R (R upper), plus R^-1.
-// A pivot below 1e-24 * max diagonal marks a dependent (or zero) column: its
-// output column is zeroed and flagged.  One thread; B <= 16.
-// out layout (doubles): R[B*B], Rinv[B*B], Rtot[B*B], flags[B]
-// Rtot = R * Rprev (Rprev = previous round's Rtot, or identity when first).
+// Cholesky of a B x B Gram matrix, G = R^T R (R upper), plus R^-1; one thread, B <= 16.
+// A pivot below 1e-24 * max diagonal marks a dependent (or zero) column: its column of R^-1 is
+// zeroed (the block column becomes 0) and dep[j] is set.  ref_diag (optional, B x B, the Gram of
+// the block before projection): a column whose squared norm collapsed by more than 1e10 under the
+// projection lies in the span of the basis and is dropped as well.
 // --------------------------------------------------------------------------
 template <int B>
-__global__ void chol_kernel(const double* __restrict__ G, const double* __restrict__ ref_diag,
-                            double* __restrict__ out, int first) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double R[B][B], Ri[B][B];
-    double* Rg = out;
-    double* Rig = out + B * B;
-    double* Rt = out + 2 * B * B;
-    double* flags = out + 3 * B * B;
+__device__ void chol_device(const double* G, const double* ref_diag, double (*R)[B], double (*Ri)[B], bool* dep) {
     double dmax = 0.0;
     for (int j = 0; j < B; ++j) dmax = fmax(dmax, G[j * B + j]);
     for (int i = 0; i < B; ++i)
         for (int j = 0; j < B; ++j) { R[i][j] = 0.0; Ri[i][j] = 0.0; }
-    bool dep[B];
     for (int j = 0; j < B; ++j) {
-        // column j of R: R[i][j] for i <= j
-        for (int i = 0; i < j; ++i) {
+        for (int i = 0; i < j; ++i) {   // column j of R: R[i][j] for i <= j
             double s = G[i * B + j];
             for (int k = 0; k < i; ++k) s -= R[k][i] * R[k][j];
             R[i][j] = dep[i] ? 0.0 : s / R[i][i];
@@ -144,13 +190,11 @@ __global__ void chol_kernel(const double* __restrict__ G, const double* __restri
         double d = G[j * B + j];
         for (int k = 0; k < j; ++k) d -= R[k][j] * R[k][j];
         dep[j] = !(d > 1e-24 * dmax) || !(dmax > 0.0);
-        // column norm collapsed by >1e5 under projection: it lies in the span of the basis
         if (ref_diag && !(d > 1e-10 * ref_diag[j * B + j])) dep[j] = true;
         R[j][j] = dep[j] ? 1.0 : sqrt(d);
         if (dep[j]) for (int i = 0; i < j; ++i) R[i][j] = 0.0;
     }
-    // inverse of upper-triangular R by back substitution, column by column
-    for (int j = 0; j < B; ++j) {
+    for (int j = 0; j < B; ++j) {       // inverse of upper-triangular R by back substitution
         Ri[j][j] = 1.0 / R[j][j];
         for (int i = j - 1; i >= 0; --i) {
             double s = 0.0;
@@ -163,38 +207,198 @@ __global__ void chol_kernel(const double* __restrict__ G, const double* __restri
             for (int i = 0; i < B; ++i) Ri[i][j] = 0.0;   // zero the dependent output column
             R[j][j] = 0.0;                                 // and its coupling
         }
-    double prev[B][B];
-    for (int i = 0; i < B; ++i)
-        for (int j = 0; j < B; ++j) prev[i][j] = first ? (i == j ? 1.0 : 0.0) : Rt[i * B + j];
-    for (int i = 0; i < B; ++i)
-        for (int j = 0; j < B; ++j) {
-            double s = 0.0;
-            for (int k = 0; k < B; ++k) s += R[i][k] * prev[k][j];
-            Rg[i * B + j] = R[i][j];
-            Rig[i * B + j] = Ri[i][j];
-            Rt[i * B + j] = s;
-        }
-    for (int j = 0; j < B; ++j) flags[j] = first ? (dep[j] ? 1.0 : 0.0) : fmax(flags[j], dep[j] ? 1.0 : 0.0);
 }
 
-// dst[i, 0:B] = Z[i, 0:B] * Rinv   (fp64 math, fp32 storage)
+// --------------------------------------------------------------------------
+// Second Gram-Schmidt pass fused with the first CholQR round:
+//     Z <- fl32( (Z - Q H) R1^-1 ),   R1 = chol(G' - H^T H),   G3 = Z_new^T Z_new
+// Hext = [H ; G'] ((ncq + B) x B) is the output of gram_kernel on [Q | Z]: H = Q^T Z and
+// G' = Z^T Z of the block as stored.  Since H = Q^T Z holds exactly for the stored vectors,
+// (Z - QH)^T (Z - QH) = G' - H^T H up to the departure of Q from orthonormality times |H|^2
+// (H is the tiny second-pass correction), so the Gram of the projected block needs no pass of
+// its own.  Every CTA repeats the B x B factorisation in its prologue (B <= 16; nothing to
+// synchronise on); CTA 0 publishes R1 and the dependence flags.  The Gram of the result --
+// input of the second CholQR round -- is accumulated on the way out (per-CTA partials, fixed-order
+// sum by the last CTA).
+// Projection on the FP64 tensor cores: m = 8 rows, n = 8 block columns, k = 4 basis columns
+// (layout of tall_gemm_kernel).
+// --------------------------------------------------------------------------
+constexpr int kPcaWarps = 8;
+
 template <int B>
-__global__ void apply_rinv_kernel(const float* __restrict__ Z, int64_t ldz, const double* __restrict__ Rinv,
-                                  int64_t n, float* __restrict__ dst, int64_t ldd) {
-    __shared__ double Ri[B * B];
-    for (int e = threadIdx.x; e < B * B; e += blockDim.x) Ri[e] = Rinv[e];
+__global__ void __launch_bounds__(kPcaWarps * 32)
+project_chol_apply_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const double* __restrict__ Hext,
+                          const double* __restrict__ G0, float* __restrict__ Z, int64_t n,
+                          double* __restrict__ chol1_out, double* __restrict__ partial, double* __restrict__ G3,
+                          unsigned* __restrict__ counter) {
+    constexpr int NT = (B + 7) / 8;
+    constexpr int BB = B * B;
+    extern __shared__ __align__(16) double pca_smem[];
+    double* sH = pca_smem;                                   // ncq x B
+    double* sG = sH + static_cast<size_t>(ncq) * B;          // B x B   (G'', then scratch)
+    double* sRi = sG + BB;                                   // B x B   R1^-1
+    double* tile = sRi + BB;                                 // warps x 8 x B   projected rows (fp64)
+    double* tile2 = tile + kPcaWarps * 8 * B;                // warps x 8 x B   rows as stored (fp32 values)
+    double* sred = tile2 + kPcaWarps * 8 * B;                // warps x BB      per-warp Gram sums
+    __shared__ double lastred[kLastRedSlots];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mi = lane >> 2, ki = lane & 3;
+
+    // ---- prologue: stage H, G'' = G' - H^T H, factorise
+    for (int e = tid; e < ncq * B; e += blockDim.x) sH[e] = Hext[e];
     __syncthreads();
-    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (int e = tid; e < BB; e += blockDim.x) {
+        const int i = e / B, j = e % B;
+        double s = Hext[static_cast<size_t>(ncq) * B + e];
+        for (int c = 0; c < ncq; ++c) s -= sH[c * B + i] * sH[c * B + j];
+        sG[e] = s;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double R[B][B], Ri[B][B];
+        bool dep[B];
+        chol_device<B>(sG, G0, R, Ri, dep);
+        for (int i = 0; i < B; ++i)
+            for (int j = 0; j < B; ++j) sRi[i * B + j] = Ri[i][j];
+        if (blockIdx.x == 0) {
+            for (int i = 0; i < B; ++i)
+                for (int j = 0; j < B; ++j) chol1_out[i * B + j] = R[i][j];
+            for (int j = 0; j < B; ++j) chol1_out[BB + j] = dep[j] ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+
+    double* my_tile = tile + warp * 8 * B;
+    double* my_tile2 = tile2 + warp * 8 * B;
+    constexpr int NP = (BB + 31) / 32;   // Gram pairs per lane
+    double g[NP];
+#pragma unroll
+    for (int q = 0; q < NP; ++q) g[q] = 0.0;
+
+    const int64_t gwarp = static_cast<int64_t>(blockIdx.x) * kPcaWarps + warp;
+    const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kPcaWarps;
+    for (int64_t r0 = gwarp * 8; r0 < n; r0 += nwarps * 8) {
+        const int64_t row = r0 + mi;
+        const bool valid = row < n;
+        double acc[NT][2];
+#pragma unroll
+        for (int u = 0; u < NT; ++u) acc[u][0] = acc[u][1] = 0.0;
+        for (int kb = 0; kb < ncq; kb += 16) {
+            const int c = kb + 4 * ki;
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && c < ncq) a = *reinterpret_cast<const float4*>(Q + row * ldq + c);
+            const double av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int s4 = 0; s4 < 4; ++s4) {
+                const int kc = c + s4;
+#pragma unroll
+                for (int u = 0; u < NT; ++u) {
+                    const int oc = u * 8 + mi;
+                    const double bfrag = (kc < ncq && oc < B) ? sH[kc * B + oc] : 0.0;
+                    dmma884(acc[u][0], acc[u][1], av[s4], bfrag);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NT; ++u) {
+            const int oc = u * 8 + ki * 2;
+            if (oc < B) {
+                double z0 = 0.0, z1 = 0.0;
+                if (valid) {
+                    const float2 zz = *reinterpret_cast<const float2*>(Z + row * B + oc);
+                    z0 = static_cast<double>(zz.x) - acc[u][0];
+                    z1 = static_cast<double>(zz.y) - acc[u][1];
+                }
+                my_tile[mi * B + oc] = z0;
+                my_tile[mi * B + oc + 1] = z1;
+            }
+        }
+        __syncwarp();
+        // rows times R1^-1, rounded to the stored precision
+        for (int o = lane; o < 8 * B; o += 32) {
+            const int rr = o / B, j = o % B;
+            double sum = 0.0;
+            for (int k2 = 0; k2 <= j; ++k2) sum = fma(my_tile[rr * B + k2], sRi[k2 * B + j], sum);
+            const float f = static_cast<float>(sum);
+            const bool ok = r0 + rr < n;
+            if (ok) Z[(r0 + rr) * B + j] = f;
+            my_tile2[o] = ok ? static_cast<double>(f) : 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+            const int pidx = lane + 32 * q;
+            if (pidx < BB) {
+                const int i = pidx / B, j = pidx % B;
+                double sum = g[q];
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) sum = fma(my_tile2[rr * B + i], my_tile2[rr * B + j], sum);
+                g[q] = sum;
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+        const int pidx = lane + 32 * q;
+        if (pidx < BB) sred[warp * BB + pidx] = g[q];
+    }
+    __syncthreads();
+    for (int e = tid; e < BB; e += blockDim.x) {
+        double t = 0.0;
+        for (int w = 0; w < kPcaWarps; ++w) t += sred[w * BB + e];
+        partial[static_cast<int64_t>(blockIdx.x) * BB + e] = t;
+    }
+    last_cta_reduce(partial, gridDim.x, BB, G3, counter, gridDim.x, lastred);
+}
+
+// --------------------------------------------------------------------------
+// Second CholQR round fused with the append:  R2 = chol(G3);  dst = fl32(Z R2^-1)  (the new basis
+// block) and, when rscale is given, Vr = rscale .* dst (the operator's scaled input for the next
+// step, so that no separate scaling kernel runs).  CTA 0 publishes Rtot = R2 R1 and the flags of
+// both rounds: out = {Rtot[B*B], flags[B]}.  rows_too == 0: factorisation only (the caller needs
+// the flags before it knows where the block goes, i.e. before a thick restart).
+// --------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(256)
+chol_append_kernel(const double* __restrict__ G3, const double* __restrict__ chol1, const float* __restrict__ Z,
+                   int64_t n, float* __restrict__ dst, int64_t ldd, const float* __restrict__ rscale,
+                   float* __restrict__ Vr, double* __restrict__ out, int rows_too) {
+    constexpr int BB = B * B;
+    __shared__ double sRi[BB];
+    if (threadIdx.x == 0) {
+        double R[B][B], Ri[B][B];
+        bool dep[B];
+        chol_device<B>(G3, nullptr, R, Ri, dep);
+        for (int i = 0; i < B; ++i)
+            for (int j = 0; j < B; ++j) sRi[i * B + j] = Ri[i][j];
+        if (blockIdx.x == 0) {
+            for (int i = 0; i < B; ++i)
+                for (int j = 0; j < B; ++j) {
+                    double s = 0.0;
+                    for (int k = 0; k < B; ++k) s += R[i][k] * chol1[k * B + j];
+                    out[i * B + j] = s;
+                }
+            for (int j = 0; j < B; ++j) out[BB + j] = fmax(chol1[BB + j], dep[j] ? 1.0 : 0.0);
+        }
+    }
+    __syncthreads();
+    if (!rows_too) return;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double z[B];
 #pragma unroll
-    for (int k = 0; k < B; ++k) z[k] = static_cast<double>(Z[i * ldz + k]);
+    for (int k = 0; k < B; ++k) z[k] = static_cast<double>(Z[i * B + k]);
+    const float rs = rscale ? rscale[i] : 0.f;
 #pragma unroll
     for (int j = 0; j < B; ++j) {
         double s = 0.0;
 #pragma unroll
-        for (int k = 0; k <= j; ++k) s = fma(z[k], Ri[k * B + j], s);
-        dst[i * ldd + j] = static_cast<float>(s);
+        for (int k = 0; k <= j; ++k) s = fma(z[k], sRi[k * B + j], s);
+        const float f = static_cast<float>(s);
+        dst[i * ldd + j] = f;
+        if (rscale) Vr[i * B + j] = rs * f;
     }
 }
 
@@ -307,6 +511,9 @@ __global__ void ref_tall_kernel(const float* Q, int64_t ldq, int ncq, const doub
 inline int row_chunks(snapb200_ctx* c, int64_t n) {
     return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c->num_sms * 2, ceil_div(n, 256))));
 }
+inline int pca_blocks(snapb200_ctx* c, int64_t n) {
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(c->num_sms * 2, ceil_div(n, kPcaWarps * 8))));
+}
 
 }  // namespace
 
@@ -315,41 +522,57 @@ inline int row_chunks(snapb200_ctx* c, int64_t n) {
 // ==========================================================================
 template <int B>
 void DenseOps<B>::reserve(snapb200_ctx* c, int64_t n, int ld) {
-    partial.ensure(static_cast<int64_t>(row_chunks(c, n)) * ld * B);
+    partial.ensure(static_cast<int64_t>(row_chunks(c, n)) * (ld + B) * B);
+    partial_g.ensure(static_cast<int64_t>(pca_blocks(c, n)) * B * B);
+    if (!counters.p) {
+        counters.alloc(4);
+        SB_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned), c->stream));
+    }
 }
 
 template <int B>
-void DenseOps<B>::gram(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Z, int64_t ldz, int64_t n,
-                       double* H) {
-    SB_CHECK(ncq % 4 == 0 && ldq % 4 == 0, "gram: basis width must be a multiple of 4");
+void DenseOps<B>::gram_ext(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Zx, int64_t ldzx, int nzx,
+                           const float* Z, int64_t ldz, int64_t n, double* H) {
+    SB_CHECK(ncq % 4 == 0 && ldq % 4 == 0 && nzx % 4 == 0 && ldzx % 4 == 0, "gram: widths must be multiples of 4");
+    const int ncx = ncq + nzx;
     const int parts = row_chunks(c, n);
-    const int64_t len = static_cast<int64_t>(ncq) * B;
-    partial.ensure(static_cast<int64_t>(parts) * len);
-    dim3 grid(parts, static_cast<unsigned>(ceil_div(ncq, kGramCols)));
-    gram_kernel<B><<<grid, kGramWarps * 32, 0, c->stream>>>(Q, ldq, ncq, Z, ldz, n, partial.p);
-    SB_LAUNCH_CHECK();
-    reduce_partials_kernel<<<static_cast<unsigned>(ceil_div(len, 128)), 128, 0, c->stream>>>(partial.p, parts, len, H);
-    SB_LAUNCH_CHECK();
-    count_launch(c, 2);
-}
-
-template <int B>
-void DenseOps<B>::zz(snapb200_ctx* c, const float* Z, int64_t ldz, int64_t n, double* G) {
-    gram(c, Z, ldz, B, Z, ldz, n, G);   // Z^T Z through the same DMMA kernel
-}
-
-template <int B>
-void DenseOps<B>::chol(snapb200_ctx* c, const double* G, const double* ref_diag, double* out, bool first) {
-    chol_kernel<B><<<1, 32, 0, c->stream>>>(G, ref_diag, out, first ? 1 : 0);
+    reserve(c, n, 0);
+    partial.ensure(static_cast<int64_t>(parts) * ncx * B);
+    dim3 grid(parts, static_cast<unsigned>(ceil_div(ncx, kGramCols)));
+    gram_kernel<B><<<grid, kGramWarps * 32, 0, c->stream>>>(Q, ldq, ncq, Zx, ldzx, nzx, Z, ldz, n, partial.p, H,
+                                                            counters.p);
     SB_LAUNCH_CHECK();
     count_launch(c);
 }
 
 template <int B>
-void DenseOps<B>::apply_rinv(snapb200_ctx* c, const float* Z, int64_t ldz, const double* Rinv, int64_t n, float* dst,
-                             int64_t ldd) {
-    if (n == 0) return;
-    apply_rinv_kernel<B><<<static_cast<unsigned>(ceil_div(n, 256)), 256, 0, c->stream>>>(Z, ldz, Rinv, n, dst, ldd);
+void DenseOps<B>::gram(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Z, int64_t ldz, int64_t n,
+                       double* H) {
+    gram_ext(c, Q, ldq, ncq, nullptr, 4, 0, Z, ldz, n, H);
+}
+
+template <int B>
+void DenseOps<B>::project_chol_apply(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const double* Hext,
+                                     const double* G0, float* Z, int64_t n, double* chol1, double* G3) {
+    SB_CHECK(ncq % 4 == 0 && ldq % 4 == 0, "project: basis width must be a multiple of 4");
+    const int blocks = pca_blocks(c, n);
+    reserve(c, n, 0);
+    const size_t smem = sizeof(double) * (static_cast<size_t>(ncq) * B + 2 * B * B + 2 * kPcaWarps * 8 * B + kPcaWarps * B * B);
+    auto k = project_chol_apply_kernel<B>;
+    if (smem > static_cast<size_t>(pca_smem_set)) {
+        SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        pca_smem_set = static_cast<int>(smem);
+    }
+    k<<<blocks, kPcaWarps * 32, smem, c->stream>>>(Q, ldq, ncq, Hext, G0, Z, n, chol1, partial_g.p, G3, counters.p + 1);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+}
+
+template <int B>
+void DenseOps<B>::chol_append(snapb200_ctx* c, const double* G3, const double* chol1, const float* Z, int64_t n,
+                              float* dst, int64_t ldd, const float* rscale, float* Vr, double* out, bool rows_too) {
+    const unsigned blocks = (rows_too && n > 0) ? static_cast<unsigned>(ceil_div(n, 256)) : 1u;
+    chol_append_kernel<B><<<blocks, 256, 0, c->stream>>>(G3, chol1, Z, n, dst, ldd, rscale, Vr, out, rows_too ? 1 : 0);
     SB_LAUNCH_CHECK();
     count_launch(c);
 }
@@ -406,6 +629,60 @@ void copy_cols(snapb200_ctx* c, const float* src, int64_t lds, float* dst, int64
 template struct DenseOps<4>;
 template struct DenseOps<8>;
 template struct DenseOps<16>;
+
+// Self test of the fused orthogonalisation chain (gram_ext -> project_out -> gram_ext ->
+// project_chol_apply -> chol_append) on its own: builds an orthonormal basis of `ncols` columns
+// from random blocks, exactly as the eigensolver appends Krylov blocks, and returns
+// max |Q^T Q - I| measured with plain fp64 loops (fp32 storage: ~1e-7 expected).
+template <int B>
+static double ortho_selftest_impl(snapb200_ctx* c, int64_t n, int ncols) {
+    const int ld = ncols + 8;
+    DenseOps<B> ops;
+    ops.reserve(c, n, ld);
+    DevBuf<float> Q, Z, Vr, ones;
+    DevBuf<double> H1, H2, chol1, G3, out, QtQ;
+    Q.alloc(n * ld); Z.alloc(n * B); Vr.alloc(n * B); ones.alloc(n);
+    H1.alloc((ld + B) * B); H2.alloc((ld + B) * B); chol1.alloc(B * B + B); G3.alloc(B * B); out.alloc(B * B + B);
+    SB_CUDA(cudaMemsetAsync(Q.p, 0, sizeof(float) * n * ld, c->stream));
+    fill_f32(c, ones.p, 1.f, n);
+    double worst = 0.0;
+    std::vector<double> hout(B * B + B);
+    for (int nb = 0; nb + B <= ncols; nb += B) {
+        ops.random_block(c, Z.p, B, n, 77, 1000 + nb);
+        const int nbq = std::max(nb, 4);   // the kernels want at least one float4 column group of basis
+        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, H1.p);
+        ops.project_out(c, Q.p, ld, nbq, H1.p, n, Z.p, B);
+        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, H2.p);
+        ops.project_chol_apply(c, Q.p, ld, nbq, H2.p, H1.p + static_cast<int64_t>(nbq) * B, Z.p, n, chol1.p, G3.p);
+        ops.chol_append(c, G3.p, chol1.p, Z.p, n, Q.p + nb, ld, ones.p, Vr.p, out.p, true);
+        SB_CUDA(cudaMemcpyAsync(hout.data(), out.p, sizeof(double) * (B * B + B), cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int j = 0; j < B; ++j)
+            if (hout[B * B + j] != 0.0) worst = std::max(worst, 1.0);   // a random block must not be flagged dependent
+    }
+    // Q^T Q, one block of B columns at a time, plain loops
+    QtQ.alloc(static_cast<int64_t>(ncols) * B);
+    std::vector<double> h(static_cast<size_t>(ncols) * B);
+    for (int j0 = 0; j0 + B <= ncols; j0 += B) {
+        ref_gram_kernel<<<static_cast<unsigned>(ceil_div(ncols * B, 64)), 64, 0, c->stream>>>(Q.p, ld, ncols, Q.p + j0, ld, B, n, QtQ.p);
+        SB_LAUNCH_CHECK();
+        SB_CUDA(cudaMemcpyAsync(h.data(), QtQ.p, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        for (int i = 0; i < ncols; ++i)
+            for (int j = 0; j < B; ++j) worst = std::max(worst, fabs(h[static_cast<size_t>(i) * B + j] - (i == j0 + j ? 1.0 : 0.0)));
+    }
+    return worst;
+}
+
+double ortho_selftest(snapb200_ctx* c, int64_t n, int ncols, int block) {
+    SB_CHECK(n >= 64 && ncols >= block && ncols % block == 0 && ncols <= 256, "ortho selftest: bad sizes");
+    switch (block) {
+        case 4: return ortho_selftest_impl<4>(c, n, ncols);
+        case 8: return ortho_selftest_impl<8>(c, n, ncols);
+        case 16: return ortho_selftest_impl<16>(c, n, ncols);
+        default: throw Error("ortho selftest: block width must be 4, 8 or 16");
+    }
+}
 
 // Self test: DMMA kernels against plain fp64 loops on random data.
 double dense_selftest(snapb200_ctx* c, int64_t n, int ncq, int p) {

@@ -9,21 +9,28 @@ namespace snapb {
 // fp32 row-major with leading dimension ldq; small matrices are fp64.
 template <int B>
 struct DenseOps {
-    DevBuf<double> partial;   // per-CTA partial sums (fixed-order reduction)
-    // size `partial` once for a basis of up to ld columns (no reallocation inside the solver loop)
+    DevBuf<double> partial;     // per-CTA partial sums of the Gram kernel (fixed-order reduction)
+    DevBuf<double> partial_g;   // per-CTA partial B x B Grams of project_chol_apply
+    DevBuf<unsigned> counters;  // tickets of the last-CTA reductions (self-resetting)
+    int pca_smem_set = 0;
+    // size the partial buffers once for a basis of up to ld columns (no reallocation inside the solver loop)
     void reserve(snapb200_ctx* c, int64_t n, int ld);
 
+    // H[(ncq + nzx) x B] = [Q[:, 0:ncq] | Zx[:, 0:nzx]]^T Z   (one kernel; Zx = Z gives Q^T Z and Z^T Z at once)
+    void gram_ext(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Zx, int64_t ldzx, int nzx,
+                  const float* Z, int64_t ldz, int64_t n, double* H);
     // H[ncq x B] = Q[:, 0:ncq]^T Z
     void gram(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Z, int64_t ldz, int64_t n, double* H);
-    // G[B x B] = Z^T Z
-    void zz(snapb200_ctx* c, const float* Z, int64_t ldz, int64_t n, double* G);
-    // out = {R, Rinv, Rtot, flags}; G = R^T R.  ref_diag (optional B x B Gram of the block before
-    // projection) lets columns whose norm collapsed be flagged as dependent.
-    void chol(snapb200_ctx* c, const double* G, const double* ref_diag, double* out, bool first);
-    // dst = Z * Rinv
-    void apply_rinv(snapb200_ctx* c, const float* Z, int64_t ldz, const double* Rinv, int64_t n, float* dst, int64_t ldd);
     // Z -= Q[:, 0:ncq] H
     void project_out(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const double* H, int64_t n, float* Z, int64_t ldz);
+    // Z (packed n x B) <- (Z - Q H) R1^-1 with R1 = chol(G' - H^T H), Hext = [H ; G'];  chol1 = {R1[B*B], flags[B]};
+    // G3 = Gram of the result.  G0 (optional): Gram of the block before any projection (dependence test).
+    void project_chol_apply(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const double* Hext, const double* G0,
+                            float* Z, int64_t n, double* chol1, double* G3);
+    // R2 = chol(G3); dst = Z R2^-1 (leading dimension ldd), Vr = rscale .* dst (if rscale);
+    // out = {Rtot = R2 R1 [B*B], flags[B]}.  rows_too = false: factorisation and `out` only.
+    void chol_append(snapb200_ctx* c, const double* G3, const double* chol1, const float* Z, int64_t n, float* dst,
+                     int64_t ldd, const float* rscale, float* Vr, double* out, bool rows_too);
     void random_block(snapb200_ctx* c, float* Z, int64_t ldz, int64_t n, uint64_t seed, uint64_t stream);
 };
 
@@ -34,6 +41,7 @@ void tall_gemm_f64(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const 
                    double* out, int64_t ldo);
 void copy_cols(snapb200_ctx* c, const float* src, int64_t lds, float* dst, int64_t ldd, int64_t n, int ncols);
 double dense_selftest(snapb200_ctx* c, int64_t n, int ncq, int p);
+double ortho_selftest(snapb200_ctx* c, int64_t n, int ncols, int block);
 
 // Symmetric eigen-decomposition on the host (Householder + implicit QL).
 // a: n x n row-major (destroyed); on return w ascending, a holds eigenvectors

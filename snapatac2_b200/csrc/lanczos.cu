@@ -21,6 +21,7 @@
 #include "ctx.cuh"
 #include "dense.cuh"
 
+#include <stdlib.h>
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -169,6 +170,22 @@ struct Ritz {
     std::vector<int> by_mag;     // indices into theta, |theta| descending
 };
 
+// One block step on the device = the operator + ortho_block():
+//   K1  Hext1 = [Q | Z]^T Z                 (projection coefficients and the block's Gram G0 at once)
+//   AR  all-reduce Hext1                    (one small fp64 all-reduce)
+//   P1  Z -= Q H1
+//   K1  Hext2 = [Q | Z]^T Z                 (second Gram-Schmidt pass + Gram G' of the projected block)
+//   AR
+//   K3  Z <- (Z - Q H2) R1^-1, R1 = chol(G' - H2^T H2);  G3 = Z^T Z          (project_chol_apply)
+//   AR  all-reduce G3
+//   K4  R2 = chol(G3);  Q[:, nb:nb+B] = Z R2^-1;  Vr = r .* (new block)      (chol_append)
+// 5 launches and 3 tiny all-reduces, no host round trip; the first version took 16 launches,
+// 6 all-reduces and a stream synchronisation per step.  What the host needs (T's new columns
+// H1 + H2, Rtot = R2 R1, the dependence flags) comes back in ONE asynchronous copy into a pinned
+// slot and is looked at one step late: the host enqueues step j + 1 before it reads step j, so the
+// GPU never waits for the Rayleigh-Ritz check.  The price is one speculative step when the check
+// says "converged"; near convergence (worst residual ratio below `kSyncRatio`) the loop therefore
+// switches to checking before it enqueues.
 template <int B>
 void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis, int max_ops, double* evals,
                 double* evecs) {
@@ -182,54 +199,56 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
     ld = std::max(ld, keep + 2 * B + 8);
     if (max_ops <= 0) max_ops = 1000;
     if (!(tol > 0.0)) tol = 1e-5;
+    double sync_ratio = 30.0;
+    if (const char* e = getenv("SNAPB200_SYNC_RATIO")) sync_ratio = atof(e);
+    const bool debug = getenv("SNAPB200_DEBUG") != nullptr;
 
     DenseOps<B> ops;
     ops.reserve(c, n, ld);
     DevBuf<float> Q, Z, Qtmp;
-    DevBuf<double> dH, dG0, dG, dChol, dS, dEvec;
+    DevBuf<double> dStep, dChol1, dG3, dS, dEvec;
     Q.alloc(std::max<int64_t>(1, n * ld));
     Z.alloc(std::max<int64_t>(1, n * B));
-    const int chol_len = 3 * B * B + B;
-    dH.alloc(2 * static_cast<int64_t>(ld) * B);
-    dG0.alloc(B * B);
-    dG.alloc(B * B);
-    dChol.alloc(chol_len);
-    // pinned staging for the small per-step matrices lives in the context (cudaMallocHost /
-    // cudaFreeHost per call cost hundreds of milliseconds on a device with ~100 GB mapped)
-    c->pinned.ensure(static_cast<int64_t>(sizeof(double)) * (2 * static_cast<int64_t>(ld) * B + chol_len));
-    double* hbuf = reinterpret_cast<double*>(c->pinned.p);
-    double* hH1 = hbuf;
-    double* hH2 = hbuf + static_cast<int64_t>(ld) * B;
-    double* hChol = hbuf + 2 * static_cast<int64_t>(ld) * B;
-    double* dH1 = dH.p;
-    double* dH2 = dH.p + static_cast<int64_t>(ld) * B;
+    c->Vr.ensure(std::max<int64_t>(1, n * B));
+    // device step buffer, copied to the host in one piece: Hext1 | Hext2 | Rtot | flags
+    const int64_t LB = static_cast<int64_t>(ld + B) * B;
+    const int64_t step_len = 2 * LB + B * B + B;
+    dStep.alloc(step_len);
+    dChol1.alloc(B * B + B);
+    dG3.alloc(B * B);
+    double* dH1 = dStep.p;
+    double* dH2 = dStep.p + LB;
+    double* dOut = dStep.p + 2 * LB;
+    // pinned staging lives in the context (cudaMallocHost / cudaFreeHost per call cost hundreds of
+    // milliseconds on a device with ~100 GB mapped); two slots: step j is read while j + 1 runs
+    c->pinned.ensure(static_cast<int64_t>(sizeof(double)) * 2 * step_len);
+    double* hslot[2] = {reinterpret_cast<double*>(c->pinned.p), reinterpret_cast<double*>(c->pinned.p) + step_len};
 
     std::vector<double> T(static_cast<size_t>(ld) * ld, 0.0);
     std::vector<char> valid(ld, 0);
     auto Tm = [&](int i, int j) -> double& { return T[static_cast<size_t>(i) * ld + j]; };
 
-    cudaEvent_t evs[6];
-    for (auto& e : evs) SB_CUDA(cudaEventCreate(&e));
+    cudaEvent_t evs[2][7];
+    for (auto& es : evs)
+        for (auto& e : es) SB_CUDA(cudaEventCreate(&e));
     double ms_spmm = 0.0, ms_comm = 0.0, ms_ortho = 0.0, ms_host = 0.0;
 
-    // orthogonalise Z against Q[:, 0:nb] twice; optionally keep H1/H2
-    auto orthogonalise = [&](int nb) {
-        ops.gram(c, Q.p, ld, nb, Z.p, B, n, dH1);
-        allreduce_f64(c, dH1, static_cast<int64_t>(nb) * B);
-        ops.project_out(c, Q.p, ld, nb, dH1, n, Z.p, B);
-        ops.gram(c, Q.p, ld, nb, Z.p, B, n, dH2);
-        allreduce_f64(c, dH2, static_cast<int64_t>(nb) * B);
-        ops.project_out(c, Q.p, ld, nb, dH2, n, Z.p, B);
+    // everything after the operator, up to (and, if `append_at` >= 0, including) the append
+    auto ortho_block = [&](int nbq, int append_at) {
+        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, dH1);
+        allreduce_f64(c, dH1, static_cast<int64_t>(nbq + B) * B);
+        ops.project_out(c, Q.p, ld, nbq, dH1, n, Z.p, B);
+        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, dH2);
+        allreduce_f64(c, dH2, static_cast<int64_t>(nbq + B) * B);
+        ops.project_chol_apply(c, Q.p, ld, nbq, dH2, dH1 + static_cast<int64_t>(nbq) * B, Z.p, n, dChol1.p, dG3.p);
+        allreduce_f64(c, dG3.p, B * B);
+        if (append_at >= 0)
+            ops.chol_append(c, dG3.p, dChol1.p, Z.p, n, Q.p + append_at, ld, c->r.p, c->Vr.p, dOut, true);
+        else
+            ops.chol_append(c, dG3.p, dChol1.p, Z.p, n, nullptr, 0, nullptr, nullptr, dOut, false);
     };
-    // CholQR2 of Z: first round applied in place, second round's R^-1 left in dChol
-    auto cholqr = [&](const double* ref) {
-        ops.zz(c, Z.p, B, n, dG.p);
-        allreduce_f64(c, dG.p, B * B);
-        ops.chol(c, dG.p, ref, dChol.p, true);
-        ops.apply_rinv(c, Z.p, B, dChol.p + B * B, n, Z.p, B);
-        ops.zz(c, Z.p, B, n, dG.p);
-        allreduce_f64(c, dG.p, B * B);
-        ops.chol(c, dG.p, nullptr, dChol.p, false);
+    auto append_block = [&](int at) {
+        ops.chol_append(c, dG3.p, dChol1.p, Z.p, n, Q.p + at, ld, c->r.p, c->Vr.p, dOut, true);
     };
 
     // ---- basis block 0 = [u1, 0 ... 0]
@@ -241,12 +260,10 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
 
     // ---- first Krylov block from a counter-hash random start
     ops.random_block(c, Z.p, B, n, static_cast<uint64_t>(seed), 0);
-    orthogonalise(nb);
-    cholqr(nullptr);
-    SB_CUDA(cudaMemcpyAsync(hChol, dChol.p, sizeof(double) * chol_len, cudaMemcpyDeviceToHost, st));
+    ortho_block(nb, nb);
+    SB_CUDA(cudaMemcpyAsync(hslot[0], dStep.p, sizeof(double) * step_len, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
-    ops.apply_rinv(c, Z.p, B, dChol.p + B * B, n, Q.p + nb, ld);
-    for (int j = 0; j < B; ++j) valid[nb + j] = hChol[3 * B * B + j] == 0.0;
+    for (int j = 0; j < B; ++j) valid[nb + j] = hslot[0][2 * LB + B * B + j] == 0.0;
     nb += B;
 
     Ritz ritz;
@@ -269,37 +286,63 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
         ms_host += hc.ms();
     };
 
-    int64_t n_ops = 0, n_restarts = 0;
-    int last_check = 0;
-    double max_res = 0.0, last_ratio = 1e300;
-    bool have_ritz = false;
-    const int min_check = (k + B - 1) / B + 2;
+    struct Step {
+        int nb = 0;           // basis width the step was orthogonalised against
+        int slot = 0;
+        bool appended = false;   // the new block is already in Q[:, nb : nb + B]
+    };
+    int64_t n_enqueued = 0;
+    auto enqueue_step = [&](int nbq) {
+        Step s;
+        s.nb = nbq;
+        s.slot = static_cast<int>(n_enqueued++ & 1);
+        cudaEvent_t* ev = evs[s.slot];
+        operator_apply_dev(c, Q.p + (nbq - B), ld, Z.p, B, B, ev, /*vr_ready=*/true);
+        SB_CUDA(cudaEventRecord(ev[4], st));
+        s.appended = nbq + B <= ld;          // room for the new block: no thick restart before the append
+        ortho_block(nbq, s.appended ? nbq : -1);
+        SB_CUDA(cudaEventRecord(ev[5], st));
+        SB_CUDA(cudaMemcpyAsync(hslot[s.slot], dStep.p, sizeof(double) * step_len, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaEventRecord(ev[6], st));
+        return s;
+    };
 
+    int64_t n_ops = 0, n_restarts = 0, n_spec = 0;
+    double max_res = 0.0, last_ratio = 1e300;
+    bool have_ritz = false, converged = false, exhausted = false;
+    const int min_check = (k + B - 1) / B + 2;
+    int nb_final = nb;
+
+    Step cur = enqueue_step(nb);
     while (true) {
-        const int last0 = nb - B;   // first column of the newest block
-        // ---- Z = A Q_last
-        operator_apply_dev(c, Q.p + last0, ld, Z.p, B, B, evs);
-        SB_CUDA(cudaEventRecord(evs[4], st));
-        ops.zz(c, Z.p, B, n, dG0.p);
-        allreduce_f64(c, dG0.p, B * B);
-        orthogonalise(nb);
-        cholqr(dG0.p);
-        SB_CUDA(cudaEventRecord(evs[5], st));
-        SB_CUDA(cudaMemcpyAsync(hH1, dH1, sizeof(double) * nb * B, cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaMemcpyAsync(hH2, dH2, sizeof(double) * nb * B, cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaMemcpyAsync(hChol, dChol.p, sizeof(double) * chol_len, cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaStreamSynchronize(st));
+        // speculate: enqueue the next step before looking at this one (see the comment above)
+        const bool may_spec = cur.appended && last_ratio > sync_ratio && n_ops + 2 < max_ops;
+        Step next;
+        bool have_next = false;
+        if (may_spec) {
+            next = enqueue_step(cur.nb + B);
+            have_next = true;
+        }
+        // ---- read step `cur`
+        SB_CUDA(cudaEventSynchronize(evs[cur.slot][6]));
         ++n_ops;
         {
             float a = 0.f, b2 = 0.f, c2 = 0.f, d2 = 0.f;
-            cudaEventElapsedTime(&a, evs[0], evs[1]);
-            cudaEventElapsedTime(&b2, evs[1], evs[2]);
-            cudaEventElapsedTime(&c2, evs[2], evs[3]);
-            cudaEventElapsedTime(&d2, evs[4], evs[5]);
+            cudaEvent_t* ev = evs[cur.slot];
+            cudaEventElapsedTime(&a, ev[0], ev[1]);
+            cudaEventElapsedTime(&b2, ev[1], ev[2]);
+            cudaEventElapsedTime(&c2, ev[2], ev[3]);
+            cudaEventElapsedTime(&d2, ev[4], ev[5]);
             ms_spmm += a + c2;
             ms_comm += b2;
             ms_ortho += d2;
         }
+        const double* hH1 = hslot[cur.slot];
+        const double* hH2 = hslot[cur.slot] + LB;
+        const double* Rtot = hslot[cur.slot] + 2 * LB;
+        const double* flags = Rtot + B * B;
+        nb = cur.nb;
+        const int last0 = nb - B;   // first column of the block the operator was applied to
         // ---- T[:, last block] = H1 + H2 (explicit projection), symmetric fill
         for (int i = 0; i < nb; ++i)
             for (int j = 0; j < B; ++j) {
@@ -310,26 +353,23 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
         bool new_valid[B];
         bool any_new = false;
         for (int j = 0; j < B; ++j) {
-            new_valid[j] = hChol[3 * B * B + j] == 0.0;
+            new_valid[j] = flags[j] == 0.0;
             any_new = any_new || new_valid[j];
         }
         int nv_now = 0;
         for (int i = 0; i < nb; ++i) nv_now += valid[i] ? 1 : 0;
 
         const bool must_restart = any_new && (nb + B > ld);
-        const bool forced = !any_new || n_ops >= max_ops;
-        const int stride = (last_ratio < 1e3) ? 1 : 2;
-        const bool due = nv_now > k && n_ops >= min_check && (n_ops - last_check) >= stride;
-        bool converged = false;
+        const bool out_of_ops = n_ops >= max_ops;
+        const bool forced = !any_new || out_of_ops;
+        const bool due = nv_now > k && n_ops >= min_check;
         have_ritz = false;
         if (due || forced || must_restart) {
             solve_ritz(nb);
             have_ritz = true;
-            last_check = static_cast<int>(n_ops);
             const int nv = static_cast<int>(ritz.idx.size());
             if (nv >= k) {
                 // residual estimates || Rtot s_last ||
-                const double* Rtot = hChol + 2 * B * B;
                 std::vector<int> lastpos(B, -1);
                 for (int a = 0; a < nv; ++a)
                     if (ritz.idx[a] >= last0) lastpos[ritz.idx[a] - last0] = a;
@@ -339,10 +379,10 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
                     const int col = ritz.by_mag[q];
                     double r2 = 0.0;
                     for (int i = 0; i < B; ++i) {
-                        double s = 0.0;
+                        double sum = 0.0;
                         for (int j = 0; j < B; ++j)
-                            if (lastpos[j] >= 0) s += Rtot[i * B + j] * ritz.S[static_cast<size_t>(lastpos[j]) * nv + col];
-                        r2 += s * s;
+                            if (lastpos[j] >= 0) sum += Rtot[i * B + j] * ritz.S[static_cast<size_t>(lastpos[j]) * nv + col];
+                        r2 += sum * sum;
                     }
                     const double res = std::sqrt(r2);
                     max_res = std::max(max_res, res);
@@ -350,12 +390,20 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
                 }
                 last_ratio = worst_ratio;
                 converged = worst_ratio <= 1.0;
+                if (debug) fprintf(stderr, "[snapb200] step %lld nb=%d worst residual ratio %.3e%s\n",
+                                   static_cast<long long>(n_ops), nb, worst_ratio, have_next ? " (next step in flight)" : "");
             }
         }
-        if (converged || forced) break;
+        if (converged || forced) {
+            exhausted = !any_new;
+            nb_final = nb;
+            if (have_next) ++n_spec;   // its device work is discarded
+            break;
+        }
 
+        int at = nb;   // where the new block goes
         if (must_restart) {
-            // ---- thick restart: keep the `keep` largest-|theta| Ritz vectors
+            // ---- thick restart: keep the `keep` largest-|theta| Ritz vectors (never speculated past)
             const int nv = static_cast<int>(ritz.idx.size());
             const int p = std::min(keep, nv);
             const int p8 = round_up8(p);
@@ -376,14 +424,15 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
                 Tm(q, q) = ritz.theta[ritz.by_mag[q]];
                 valid[q] = 1;
             }
-            nb = p8;
+            at = p8;
             ++n_restarts;
         }
-        // ---- append the new block  Q[:, nb:nb+B] = Z R2^-1
-        ops.apply_rinv(c, Z.p, B, dChol.p + B * B, n, Q.p + nb, ld);
-        for (int j = 0; j < B; ++j) valid[nb + j] = new_valid[j];
-        nb += B;
+        if (!cur.appended) append_block(at);   // Q[:, at : at + B] = Z R2^-1
+        for (int j = 0; j < B; ++j) valid[at + j] = new_valid[j];
+        nb = at + B;
+        cur = have_next ? next : enqueue_step(nb);
     }
+    nb = nb_final;
 
     // ---- final Ritz extraction: k largest |theta|, sorted by descending value
     if (!have_ritz) solve_ritz(nb);
@@ -405,7 +454,8 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
         SB_CUDA(cudaMemcpyAsync(evecs, dEvec.p, sizeof(double) * n * k, cudaMemcpyDeviceToHost, st));
     }
     SB_CUDA(cudaStreamSynchronize(st));
-    for (auto& e : evs) cudaEventDestroy(e);
+    for (auto& es : evs)
+        for (auto& e : es) cudaEventDestroy(e);
 
     c->stats.ms_eigsh = wall.ms();
     c->stats.ms_spmm = ms_spmm;
@@ -417,6 +467,11 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
     c->stats.n_restarts = n_restarts;
     c->stats.basis_cols = nb;
     c->stats.block = B;
+    c->stats.n_spec_ops = n_spec;
+    // converged: every wanted pair met the tolerance, or the Krylov space is exhausted (the Ritz
+    // pairs are then exact).  Not converged: max_ops reached first -- scipy's eigsh raises
+    // ArpackNoConvergence there; the Python mirror does the same from this flag.
+    c->stats.converged = (converged || exhausted) ? 1 : 0;
 }
 
 }  // namespace

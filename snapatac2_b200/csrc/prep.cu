@@ -329,6 +329,9 @@ void select_features(snapb200_ctx* c, const uint8_t* keep_host, int64_t m) {
     c->Xt.clear();
     c->xt_built = false;
     c->XtT.clear();
+    c->S1.clear();
+    c->S2.clear();
+    c->nnz_mode = -1;
     c->stats.nnz_local = nnz;
 }
 
@@ -420,6 +423,7 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     auto since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
+    decide_spmm_mode(c);
     const bool tiled = use_tiled(c, c->block);
     const bool user_w = !c->user_weights.empty();
     if (user_w)

@@ -110,13 +110,13 @@ gather_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ 
 
 // Shared-memory tiled path (b = 4 or 8): both passes run over the sliced-ELL copies.
 template <int B>
-void apply_tiled(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, cudaEvent_t* evs) {
+void apply_tiled(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, cudaEvent_t* evs, bool vr_ready) {
     SB_CHECK(ldy == B, "tiled operator: Y must be packed (leading dimension b)");
     const int64_t n = c->n_local, m = c->m;
     cudaStream_t st = c->stream;
     c->Vr.ensure(std::max<int64_t>(1, n * B));
     c->W.ensure(m * B);
-    if (n > 0) {
+    if (n > 0 && !vr_ready) {
         scale_rows_kernel<B><<<static_cast<unsigned>(ceil_div(n * B, 256)), 256, 0, st>>>(V, ldv, c->r.p, n, c->Vr.p);
         SB_LAUNCH_CHECK();
         count_launch(c);
@@ -137,12 +137,12 @@ inline int grid_rows(snapb200_ctx* c, int64_t nrows) {
 }
 
 template <int B>
-void apply_impl(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, cudaEvent_t* evs) {
+void apply_impl(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, cudaEvent_t* evs, bool vr_ready) {
     const int64_t n = c->n_local, m = c->m;
     cudaStream_t st = c->stream;
     c->Vr.ensure(std::max<int64_t>(1, n * B));
     c->W.ensure(m * B);
-    if (n > 0) {
+    if (n > 0 && !vr_ready) {
         scale_rows_kernel<B><<<static_cast<unsigned>(ceil_div(n * B, 256)), 256, 0, st>>>(V, ldv, c->r.p, n, c->Vr.p);
         SB_LAUNCH_CHECK();
         count_launch(c);
@@ -177,21 +177,22 @@ void apply_impl(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t 
 
 }  // namespace
 
-void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, int b, cudaEvent_t* evs) {
+void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, int b, cudaEvent_t* evs,
+                        bool vr_ready) {
     SB_CHECK(c->prepared, "operator: call prepare first");
     SB_CHECK(ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "operator: Y must be 16-byte aligned");
     if (use_tiled(c, b)) {
         ensure_tiled(c, b);   // no-op when prepare() already built the copies for this width
         c->stats.spmm_tiled = 1;
-        if (b == 8) apply_tiled<8>(c, V, ldv, Y, ldy, evs);
-        else apply_tiled<4>(c, V, ldv, Y, ldy, evs);
+        if (b == 8) apply_tiled<8>(c, V, ldv, Y, ldy, evs, vr_ready);
+        else apply_tiled<4>(c, V, ldv, Y, ldy, evs, vr_ready);
         return;
     }
     c->stats.spmm_tiled = 0;
     switch (b) {
-        case 4: apply_impl<4>(c, V, ldv, Y, ldy, evs); break;
-        case 8: apply_impl<8>(c, V, ldv, Y, ldy, evs); break;
-        case 16: apply_impl<16>(c, V, ldv, Y, ldy, evs); break;
+        case 4: apply_impl<4>(c, V, ldv, Y, ldy, evs, vr_ready); break;
+        case 8: apply_impl<8>(c, V, ldv, Y, ldy, evs, vr_ready); break;
+        case 16: apply_impl<16>(c, V, ldv, Y, ldy, evs, vr_ready); break;
         default: throw Error("operator: block width must be 4, 8 or 16");
     }
 }
@@ -288,6 +289,7 @@ void prepare_projection(snapb200_ctx* c) {
     const int64_t n = c->n_local, m = c->m;
     cudaStream_t st = c->stream;
     if (!c->prepared) {
+        decide_spmm_mode(c);
         // IDF (or user) weights and row norms only; no transpose (view_norms leaves them on the device)
         c->w.alloc(m);
         c->rho.alloc(std::max<int64_t>(1, n));

@@ -456,7 +456,22 @@ bool use_tiled(const snapb200_ctx* c, int b) {
     if (b != 8 && b != 4) return false;
     if (c->spmm_mode == 1) return false;
     if (c->spmm_mode == 2) return true;
-    return c->X.nnz >= (1ll << 25);   // small problems: the CSR kernel avoids staging tiles at all
+    const int64_t nnz = c->nnz_mode >= 0 ? c->nnz_mode : c->X.nnz;
+    return nnz >= (1ll << 25);   // small problems: the CSR kernel avoids staging tiles at all
+}
+
+void decide_spmm_mode(snapb200_ctx* c) {
+    int64_t nnz = c->X.nnz;
+    if (c->nranks > 1) {
+        DevBuf<int64_t> t;
+        t.alloc(1);
+        SB_CUDA(cudaMemcpyAsync(t.p, &nnz, sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        allreduce_i64(c, t.p, 1);
+        SB_CUDA(cudaMemcpyAsync(&nnz, t.p, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+        nnz /= c->nranks;
+    }
+    c->nnz_mode = nnz;
 }
 
 void ensure_tiled(snapb200_ctx* c, int b) {

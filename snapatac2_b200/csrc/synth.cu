@@ -190,6 +190,8 @@ void generate_rows(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t r
     c->m = m;
     c->loaded = true;
     c->prepared = false;
+    c->proj_ready = false;
+    c->nnz_mode = -1;
     c->stats.nnz_local = nnz;
 }
 

@@ -197,6 +197,13 @@ class Engine:
         evecs = np.empty((self.n_local, k), dtype=np.float64) if out_evecs is None else out_evecs
         _lib.check(self._lib.snapb200_eigsh(self._ctx, int(k), int(seed), float(tol), int(block),
                                             int(max_basis), int(max_ops), _lib.ptr(evals), _lib.ptr(evecs)))
+        st = self.stats()
+        if not st["converged"]:
+            # scipy's eigsh, which the reference calls (embedding.rs:166-167), raises here as well
+            from scipy.sparse.linalg import ArpackNoConvergence
+            raise ArpackNoConvergence(
+                f"block Lanczos: no convergence after {st['n_ops']} block operator applications "
+                f"(worst residual {st['max_residual']:.3e})", evals, evecs)
         return evals, evecs
 
     def stats(self) -> dict:
@@ -218,6 +225,11 @@ class Engine:
         h = C.c_void_p()
         _lib.check(self._lib.snapb200_get_stream(self._ctx, C.byref(h)))
         return int(h.value or 0)
+
+    def ortho_selftest(self, n=5000, ncols=64, block=4) -> float:
+        err = C.c_double()
+        _lib.check(self._lib.snapb200_ortho_selftest(self._ctx, int(n), int(ncols), int(block), C.byref(err)))
+        return err.value
 
     def dense_selftest(self, n=4099, ncq=136, p=30) -> float:
         err = C.c_double()

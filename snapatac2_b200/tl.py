@@ -8,8 +8,10 @@ exceptions.  Where the reference calls ``internal.spectral_embedding``
 (``_embedding.py:249`` -> ``snapatac2-python/src/embedding.rs:24-59``) this
 module drives ``libsnapb200.so`` through ctypes instead.
 
-There is no CPU fallback: the jaccard metric and the Nystrom ``sample_size``
-path of the reference are outside this build and raise NotImplementedError.
+``sample_size`` selects the Nystrom path exactly as in the reference
+(``internal.spectral_embedding_nystrom``, embedding.rs:61-129, followed by
+``orthogonalize``, _embedding.py:397-413).  There is no CPU fallback: the jaccard
+metric (a dense similarity matrix, outside this build) raises NotImplementedError.
 """
 
 from __future__ import annotations
@@ -24,6 +26,19 @@ from . import dist
 from .engine import Engine
 
 _engine: Engine | None = None
+
+
+def _check_engine(eng: Engine) -> Engine:
+    """Under torch.distributed an engine must span the world: a context that never joined the
+    communicator would silently treat its shard as the whole matrix (all-reduces are no-ops)."""
+    rank, ws = dist.world()
+    if ws > 1 and (eng.nranks != ws or eng.rank != rank):
+        if eng.nranks == 1:
+            dist.attach_engine_comm(eng)
+        else:
+            raise RuntimeError(f"engine belongs to a communicator of {eng.nranks} ranks (rank {eng.rank}); "
+                               f"torch.distributed world is {ws} (rank {rank})")
+    return eng
 
 
 def default_engine() -> Engine:
@@ -282,12 +297,13 @@ def spectral(
     if distance_metric != "cosine":
         raise NotImplementedError("only distance_metric='cosine' (the matrix-free path) runs on the GPU")
 
-    eng = engine if engine is not None else default_engine()
+    eng = _check_engine(engine) if engine is not None else default_engine()
     X = _get_csr(adata)
     if sample_size < n_sample:                                      # :257-265
         logging.getLogger(__name__).info("Perform spectral embedding using the Nystrom algorithm...")
+        # like the reference (:263), the Nystrom call does not receive feature_weights: IDF from all cells
         v, u = spectral_embedding_nystrom(eng, X, features, n_comps, sample_size, sample_method != "random",
-                                          chunk_size, feature_weights, tol=tol, block=block)
+                                          chunk_size, tol=tol, block=block)
         evals, evecs = orthogonalize(v, u)
     else:
         evals, evecs = spectral_embedding(eng, X, features, n_comps, random_state, feature_weights,
@@ -394,7 +410,7 @@ def multi_spectral(adatas, n_comps: int = 30, features="selected", weights=None,
     if dist.world()[1] > 1:
         n_obs = sum(dist.allgather_ints(n_obs))
     n_comps = min(n_obs - 1, n_comps)
-    eng = engine if engine is not None else default_engine()
+    eng = _check_engine(engine) if engine is not None else default_engine()
     evals, evecs = multi_spectral_embedding(eng, [_get_csr(a) for a in adatas], features, weights,
                                             n_comps, random_state, sample_rows=sample_rows)   # :533
     if weighted_by_sd:                                                      # :535-538

@@ -32,6 +32,13 @@ def test_dense_tensor_core_kernels_selftest(engine):
         assert engine.dense_selftest(n, ncq, p) < 1e-11
 
 
+def test_fused_orthogonalisation_chain_selftest(engine):
+    # gram_ext -> project_out -> gram_ext -> project_chol_apply -> chol_append, as the eigensolver chains
+    # them: orthonormal basis from random blocks, max |Q^T Q - I| at fp32 storage precision
+    for n, ncols, block in ((5000, 64, 4), (4099, 96, 8), (3001, 64, 16), (70001, 168, 4)):
+        assert engine.ortho_selftest(n, ncols, block) < 5e-6
+
+
 def test_generator_is_bit_identical_to_host(engine):
     spec = synth.make_spec(700, 30000, 900, n_clusters=16, seed=6)
     engine.generate(spec)
