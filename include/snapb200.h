@@ -64,6 +64,9 @@ typedef struct snapb200_stats {
     int64_t converged;     /* last eigsh: 1 = every pair met the tolerance (or the Krylov space was exhausted),
                               0 = max_ops reached first (scipy's eigsh raises ArpackNoConvergence there)   */
     int64_t n_spec_ops;    /* operator applications enqueued ahead of the convergence check and discarded  */
+    double ms_d2h;         /* last eigsh: final rotation + copy of the eigenvectors to the host            */
+    int64_t bytes_h2d;     /* last load_csr: bytes that crossed PCIe (indptr + int32 indices [+ f32 values]) */
+    int64_t host_threads;  /* last load_csr: size of the host staging team                                 */
 } snapb200_stats;
 
 /* Library / error plumbing. */
@@ -84,8 +87,12 @@ int  snapb200_comm_init(snapb200_ctx* ctx, int rank, int nranks, const char id[1
  * embedding.rs:36-41).  `indptr` has n_local+1 entries (relative to the
  * shard), `indices` are column ids < m, sorted within a row.  *_bits is 32 or
  * 64.  `values` may be NULL (binarised pattern: every stored entry is 1);
- * otherwise value_kind selects 1=f32, 2=f64, 3=u32, 4=i32, 5=i64, 6=u64 and
- * the values are converted to f32.  `on_device` != 0 means the pointers are
+ * otherwise value_kind selects 1=f32, 2=f64, 3=u32, 4=i32, 5=i64, 6=u64,
+ * 7=u8 (also numpy bool), 8=i8, 9=u16, 10=i16 and the values are converted to f32; an
+ * all-ones value array is recognised (host arrays: by a threaded scan before anything is
+ * shipped) and dropped.  Host arrays may be pageable: a team of host threads
+ * (SNAPB200_THREADS, default min(16, cores / local ranks)) narrows 64-bit indices to 32 bits
+ * into a ring of pinned buffers and issues the DMAs chunk by chunk.  `on_device` != 0 means the pointers are
  * device pointers on this context's GPU (e.g. torch CUDA tensors). */
 int  snapb200_load_csr(snapb200_ctx* ctx, int64_t n_local, int64_t n_global, int64_t row0,
                        int64_t m, const void* indptr, int indptr_bits,
@@ -126,6 +133,28 @@ int  snapb200_prepare(snapb200_ctx* ctx, double* idf_out, double* degree_out);
  * (rho_out, n_local entries).  The caller scales and concatenates the views
  * (embedding.rs:428-443) and runs the ordinary load/prepare/eigsh on the result. */
 int  snapb200_view_norms(snapb200_ctx* ctx, double* idf_out, double* rho_out);
+
+/* Multi-view embedding as a VIRTUAL column concatenation (multi_spectral_embedding,
+ * embedding.rs:388-452; hstack :367-385): one context per view on the same GPU.
+ *   attach_view    the view context adopts the main context's stream and communicator (call before
+ *                  loading the view; the main context must outlive its views);
+ *   [load_csr / select_features / prepare on every view context -- the ordinary single-view calls]
+ *   view_frobenius the value of the Python snippet inside frobenius_norm (embedding.rs:456-460) on the
+ *                  unit-norm rows `sample_rows` (this rank's local ids) of a prepared view, as the
+ *                  snippet evaluates on a scipy.sparse.csr_matrix: sum((X X^T) @ (X X^T)); the
+ *                  caller forms norm = sqrt(value - n_sample) and the view scales
+ *                  c_v = sqrt((weight_v / norm_v) / sum) (embedding.rs:423-442);
+ *   combine_views  views[0] = main; combined degrees d = sum_v c_v^2 (d_v + 1) - 1, D^-1, the
+ *                  trivial eigenvector and every view's operator row scale; afterwards
+ *                  snapb200_eigsh / operator_apply on the main context use
+ *                  A = sum_v X~_v X~_v^T - D^-1 without the concatenated matrix ever existing.
+ * get_vector copies a prepared context's fp64 vectors to the host: which = 0 feature weights (m),
+ * 1 row norms (n_local), 2 degrees (n_local), 3 column sums (m). */
+int  snapb200_attach_view(snapb200_ctx* main_ctx, snapb200_ctx* view);
+int  snapb200_view_frobenius(snapb200_ctx* ctx, const int64_t* sample_rows, int64_t n_sample_local, double* snippet_sum);
+int  snapb200_combine_views(snapb200_ctx* main_ctx, snapb200_ctx** views, const double* view_scale, int n_views,
+                            double* degree_out);
+int  snapb200_get_vector(snapb200_ctx* ctx, int which, double* out);
 
 /* Nystrom extension (spectral_embedding_nystrom / nystrom, embedding.rs:61-129, 194-267): products
  * with the feature-weighted, row-normalised matrix  Xhat = diag(1/rho) P diag(w)  on k dense

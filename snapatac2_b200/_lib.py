@@ -20,6 +20,7 @@ SYMBOLS = [
     "snapb200_comm_unique_id", "snapb200_comm_init", "snapb200_load_csr",
     "snapb200_select_features", "snapb200_generate", "snapb200_shape", "snapb200_export_csr",
     "snapb200_set_feature_weights", "snapb200_prepare", "snapb200_view_norms",
+    "snapb200_attach_view", "snapb200_view_frobenius", "snapb200_combine_views", "snapb200_get_vector",
     "snapb200_prepare_projection", "snapb200_project",
     "snapb200_operator_apply", "snapb200_operator_time", "snapb200_eigsh", "snapb200_get_stats",
     "snapb200_get_stream", "snapb200_set_spmm_mode", "snapb200_set_block",
@@ -37,7 +38,8 @@ class Stats(C.Structure):
         ("ms_format", C.c_double), ("spmm_tiled", C.c_int64),
         ("ms_prepare_wall", C.c_double),
         ("ms_pool", C.c_double), ("pool_mallocs", C.c_int64),
-        ("converged", C.c_int64), ("n_spec_ops", C.c_int64),
+        ("converged", C.c_int64), ("n_spec_ops", C.c_int64), ("ms_d2h", C.c_double),
+        ("bytes_h2d", C.c_int64), ("host_threads", C.c_int64),
     ]
 
     def as_dict(self):
@@ -74,6 +76,10 @@ def load() -> C.CDLL:
         "snapb200_set_feature_weights": [vp, vp, i64],
         "snapb200_prepare": [vp, vp, vp],
         "snapb200_view_norms": [vp, vp, vp],
+        "snapb200_attach_view": [vp, vp],
+        "snapb200_view_frobenius": [vp, vp, i64, C.POINTER(dbl)],
+        "snapb200_combine_views": [vp, vp, vp, i32, vp],
+        "snapb200_get_vector": [vp, i32, vp],
         "snapb200_prepare_projection": [vp, vp, vp],
         "snapb200_project": [vp, i32, vp, i32, vp],
         "snapb200_operator_apply": [vp, vp, vp, i32],
@@ -113,6 +119,8 @@ def ptr(a):
 _VALUE_KINDS = {
     np.dtype(np.float32): 1, np.dtype(np.float64): 2, np.dtype(np.uint32): 3,
     np.dtype(np.int32): 4, np.dtype(np.int64): 5, np.dtype(np.uint64): 6,
+    np.dtype(np.uint8): 7, np.dtype(np.bool_): 7, np.dtype(np.int8): 8,
+    np.dtype(np.uint16): 9, np.dtype(np.int16): 10,
 }
 
 

@@ -19,7 +19,7 @@ CSRC = HERE / "csrc"
 BUILD = HERE / "_build"
 LIB = HERE / "libsnapb200.so"
 
-SOURCES = ["api.cu", "pool.cu", "comm.cu", "util.cu", "synth.cu", "prep.cu", "transpose_tiled.cu", "spmm.cu", "sell_build.cu", "spmm_tiled.cu", "dense.cu", "lanczos.cu"]
+SOURCES = ["api.cu", "ingest.cu", "pool.cu", "comm.cu", "util.cu", "synth.cu", "prep.cu", "transpose_tiled.cu", "spmm.cu", "sell_build.cu", "spmm_tiled.cu", "dense.cu", "lanczos.cu"]
 
 
 def _nccl_paths():
@@ -35,7 +35,7 @@ def _flags():
     inc, _ = _nccl_paths()
     return [
         "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-        "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-I", str(inc), "-I", str(HERE.parent / "include"),
+        "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-Xcompiler", "-mavx2", "-Xcompiler", "-pthread", "-I", str(inc), "-I", str(HERE.parent / "include"),
     ]
 
 

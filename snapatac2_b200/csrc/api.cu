@@ -5,6 +5,7 @@
 
 #include <string.h>
 #include <algorithm>
+#include <chrono>
 #include <vector>
 
 namespace snapb {
@@ -76,31 +77,9 @@ int stream_blocks(snapb200_ctx* c, int64_t n) {
 size_t value_size(int kind) {
     switch (kind) {
         case 1: return 4; case 2: return 8; case 3: return 4; case 4: return 4; case 5: return 8; case 6: return 8;
+        case 7: case 8: return 1; case 9: case 10: return 2;
         default: throw Error("load_csr: unknown value_kind");
     }
-}
-
-// Copy `count` elements of `elem` bytes from src (host or device) into a device
-// staging buffer in chunks and hand every chunk to `consume(dev_ptr, offset, len)`.
-template <typename F>
-void staged_copy(snapb200_ctx* c, const void* src, size_t elem, int64_t count, bool on_device, F&& consume) {
-    if (count == 0) return;
-    if (on_device) {
-        consume(src, 0, count);
-        return;
-    }
-    const int64_t chunk = std::min<int64_t>(count, (256ll << 20) / static_cast<int64_t>(elem));
-    DevBuf<unsigned char> stage[2];
-    stage[0].alloc(chunk * elem);
-    stage[1].alloc(chunk * elem);
-    int which = 0;
-    for (int64_t off = 0; off < count; off += chunk, which ^= 1) {
-        const int64_t len = std::min(chunk, count - off);
-        SB_CUDA(cudaMemcpyAsync(stage[which].p, static_cast<const unsigned char*>(src) + off * elem, len * elem,
-                                cudaMemcpyHostToDevice, c->stream));
-        consume(stage[which].p, off, len);
-    }
-    SB_CUDA(cudaStreamSynchronize(c->stream));
 }
 
 // bad |= 2 if a row's column indices are not strictly increasing (the transpose and the tiled
@@ -126,6 +105,7 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     SB_CHECK(indices_bits == 32 || indices_bits == 64, "load_csr: indices_bits must be 32 or 64");
     SB_CHECK(indptr != nullptr, "load_csr: null indptr");
     cudaStream_t st = c->stream;
+    const auto wall0 = std::chrono::steady_clock::now();
     const bool dev = on_device != 0;
     // device-resident input was produced on the caller's stream(s), which this library's private
     // non-blocking stream does not order with: wait for the device before reading it
@@ -135,6 +115,7 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     // the context holds no usable matrix until this load has passed validation
     c->loaded = false;
     c->prepared = false;
+    c->views.clear();
     c->nnz_mode = -1;
     c->S1.clear();
     c->S2.clear();
@@ -174,49 +155,62 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     bad.alloc(1);
     SB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
     // ---- column indices: int32 on the device, range-checked
-    if (indices_bits == 32) {
-        if (nnz > 0) {
-            SB_CUDA(cudaMemcpyAsync(X.idx.p, indices, sizeof(int32_t) * nnz, kind, st));
-            check_i32_kernel<<<stream_blocks(c, nnz), 256, 0, st>>>(X.idx.p, nnz, m, bad.p);
+    if (nnz > 0) {
+        if (!dev) {
+            // host arrays (pageable or pinned): narrowed / copied chunk by chunk through the pinned ring
+            if (!stage_indices(c, indices, indices_bits, nnz, X.idx.p)) throw Error("load_csr: column index out of range");
+        } else if (indices_bits == 32) {
+            SB_CUDA(cudaMemcpyAsync(X.idx.p, indices, sizeof(int32_t) * nnz, cudaMemcpyDeviceToDevice, st));
+        } else {
+            narrow_i64_kernel<<<stream_blocks(c, nnz), 256, 0, st>>>(static_cast<const int64_t*>(indices), X.idx.p, nnz, m, bad.p);
             SB_LAUNCH_CHECK();
             count_launch(c);
         }
-    } else {
-        staged_copy(c, indices, 8, nnz, dev, [&](const void* p, int64_t off, int64_t len) {
-            narrow_i64_kernel<<<stream_blocks(c, len), 256, 0, st>>>(static_cast<const int64_t*>(p), X.idx.p + off, len, m, bad.p);
-            SB_LAUNCH_CHECK();
-            count_launch(c);
-        });
+        check_i32_kernel<<<stream_blocks(c, nnz), 256, 0, st>>>(X.idx.p, nnz, m, bad.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
     }
-    // ---- values (optional): f32 on the device; an all-ones array is dropped
+    // ---- values (optional): f32 on the device; an all-ones array is dropped (binarised input runs
+    //      the pattern-only kernels).  Host values are scanned on the host first, so a binarised
+    //      matrix never ships them.
     X.val.release();
     if (values != nullptr && nnz > 0) {
-        X.val.alloc(nnz);
-        const size_t es = value_size(value_kind);
-        staged_copy(c, values, es, nnz, dev, [&](const void* p, int64_t off, int64_t len) {
-            const int g = stream_blocks(c, len);
-            float* out = X.val.p + off;
+        value_size(value_kind);
+        if (!dev) {
+            if (!host_values_all_ones(c, values, value_kind, nnz)) {
+                X.val.alloc(nnz);
+                stage_values(c, values, value_kind, nnz, X.val.p);
+            }
+        } else {
+            X.val.alloc(nnz);
+            const int g = stream_blocks(c, nnz);
+            float* out = X.val.p;
+            const void* p = values;
             switch (value_kind) {
-                case 1: SB_CUDA(cudaMemcpyAsync(out, p, sizeof(float) * len, cudaMemcpyDeviceToDevice, st)); break;
-                case 2: to_f32_kernel<double><<<g, 256, 0, st>>>(static_cast<const double*>(p), out, len); break;
-                case 3: to_f32_kernel<uint32_t><<<g, 256, 0, st>>>(static_cast<const uint32_t*>(p), out, len); break;
-                case 4: to_f32_kernel<int32_t><<<g, 256, 0, st>>>(static_cast<const int32_t*>(p), out, len); break;
-                case 5: to_f32_kernel<int64_t><<<g, 256, 0, st>>>(static_cast<const int64_t*>(p), out, len); break;
-                case 6: to_f32_kernel<uint64_t><<<g, 256, 0, st>>>(static_cast<const uint64_t*>(p), out, len); break;
+                case 1: SB_CUDA(cudaMemcpyAsync(out, p, sizeof(float) * nnz, cudaMemcpyDeviceToDevice, st)); break;
+                case 2: to_f32_kernel<double><<<g, 256, 0, st>>>(static_cast<const double*>(p), out, nnz); break;
+                case 3: to_f32_kernel<uint32_t><<<g, 256, 0, st>>>(static_cast<const uint32_t*>(p), out, nnz); break;
+                case 4: to_f32_kernel<int32_t><<<g, 256, 0, st>>>(static_cast<const int32_t*>(p), out, nnz); break;
+                case 5: to_f32_kernel<int64_t><<<g, 256, 0, st>>>(static_cast<const int64_t*>(p), out, nnz); break;
+                case 6: to_f32_kernel<uint64_t><<<g, 256, 0, st>>>(static_cast<const uint64_t*>(p), out, nnz); break;
+                case 7: to_f32_kernel<uint8_t><<<g, 256, 0, st>>>(static_cast<const uint8_t*>(p), out, nnz); break;
+                case 8: to_f32_kernel<int8_t><<<g, 256, 0, st>>>(static_cast<const int8_t*>(p), out, nnz); break;
+                case 9: to_f32_kernel<uint16_t><<<g, 256, 0, st>>>(static_cast<const uint16_t*>(p), out, nnz); break;
+                case 10: to_f32_kernel<int16_t><<<g, 256, 0, st>>>(static_cast<const int16_t*>(p), out, nnz); break;
             }
             SB_LAUNCH_CHECK();
             count_launch(c);
-        });
-        DevBuf<int> not_one;
-        not_one.alloc(1);
-        SB_CUDA(cudaMemsetAsync(not_one.p, 0, sizeof(int), st));
-        ones_check_kernel<<<stream_blocks(c, nnz), 256, 0, st>>>(X.val.p, nnz, not_one.p);
-        SB_LAUNCH_CHECK();
-        count_launch(c);
-        int h = 0;
-        SB_CUDA(cudaMemcpyAsync(&h, not_one.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        SB_CUDA(cudaStreamSynchronize(st));
-        if (!h) X.val.release();   // binarised input: pattern-only kernels
+            DevBuf<int> not_one;
+            not_one.alloc(1);
+            SB_CUDA(cudaMemsetAsync(not_one.p, 0, sizeof(int), st));
+            ones_check_kernel<<<stream_blocks(c, nnz), 256, 0, st>>>(X.val.p, nnz, not_one.p);
+            SB_LAUNCH_CHECK();
+            count_launch(c);
+            int h = 0;
+            SB_CUDA(cudaMemcpyAsync(&h, not_one.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            SB_CUDA(cudaStreamSynchronize(st));
+            if (!h) X.val.release();
+        }
     }
     if (nnz > 0 && n_local > 0) {
         const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_local, 8), static_cast<int64_t>(c->num_sms) * 16));
@@ -230,9 +224,9 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     SB_CUDA(cudaStreamSynchronize(st));
     SB_CHECK(!(hbad & 1), "load_csr: column index out of range");
     SB_CHECK(!(hbad & 2), "load_csr: column indices must be strictly increasing within every row (sorted, no duplicates)");
-    float ms = 0.f;
-    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-    c->stats.ms_load = ms;
+    c->stats.ms_load = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    c->stats.bytes_h2d = dev ? 0 : static_cast<int64_t>((indptr_bits / 8) * (n_local + 1) + 4 * nnz + (X.has_values() ? 4 * nnz : 0));
+    c->stats.host_threads = dev ? 0 : host_threads(c);
     c->n_local = n_local;
     c->n_global = n_global;
     c->row0 = row0;
@@ -280,9 +274,22 @@ int snapb200_destroy(snapb200_ctx* c) {
         if (!c) return;
         cudaSetDevice(c->device);
         cudaStreamSynchronize(c->stream);
+        if (c->borrowed) {   // a view context: stream and communicator belong to its main context
+            c->comm = nullptr;
+            cudaStream_t shared = c->stream;
+            if (c->ev0) cudaEventDestroy(c->ev0);
+            if (c->ev1) cudaEventDestroy(c->ev1);
+            for (auto& e : c->ring_events) cudaEventDestroy(e);
+            c->ring_events.clear();
+            pool_set_stream(shared);   // its buffers return to the pool ordered on the shared stream
+            delete c;
+            return;
+        }
         comm_destroy(c);
         if (c->ev0) cudaEventDestroy(c->ev0);
         if (c->ev1) cudaEventDestroy(c->ev1);
+        for (auto& e : c->ring_events) cudaEventDestroy(e);
+        c->ring_events.clear();
         cudaStream_t st = c->stream;
         // everything on the stream is done: the context's buffers go back to the pool as quiesced
         // blocks (no event), and blocks parked earlier must stop referring to the stream
@@ -367,6 +374,58 @@ int snapb200_set_feature_weights(snapb200_ctx* c, const double* w, int64_t m) {
 
 int snapb200_prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     return guarded([&] { bind(c); prepare(c, idf_out, degree_out); });
+}
+
+int snapb200_attach_view(snapb200_ctx* main_ctx, snapb200_ctx* view) {
+    return guarded([&] {
+        bind(main_ctx);
+        SB_CHECK(view != nullptr && view != main_ctx, "attach_view: need a second context");
+        SB_CHECK(view->device == main_ctx->device, "attach_view: contexts must live on the same device");
+        if (view->stream == main_ctx->stream) return;
+        SB_CHECK(!view->borrowed, "attach_view: the context is already attached to another one");
+        SB_CUDA(cudaStreamSynchronize(view->stream));
+        comm_destroy(view);
+        cudaStream_t old = view->stream;
+        pool_forget_stream(old);
+        if (old) cudaStreamDestroy(old);
+        view->stream = main_ctx->stream;
+        view->comm = main_ctx->comm;
+        view->rank = main_ctx->rank;
+        view->nranks = main_ctx->nranks;
+        view->borrowed = true;
+        main_ctx->views.clear();
+    });
+}
+
+int snapb200_view_frobenius(snapb200_ctx* c, const int64_t* sample_rows, int64_t n_sample_local, double* snippet_sum) {
+    return guarded([&] {
+        bind(c);
+        SB_CHECK(snippet_sum != nullptr, "view_frobenius: null output");
+        *snippet_sum = view_frobenius(c, sample_rows, n_sample_local);
+    });
+}
+
+int snapb200_combine_views(snapb200_ctx* main_ctx, snapb200_ctx** views, const double* view_scale, int n_views,
+                           double* degree_out) {
+    return guarded([&] { bind(main_ctx); combine_views(main_ctx, views, view_scale, n_views, degree_out); });
+}
+
+int snapb200_get_vector(snapb200_ctx* c, int which, double* out) {
+    return guarded([&] {
+        bind(c);
+        SB_CHECK(c->prepared || (which <= 1 && c->proj_ready), "get_vector: call prepare first");
+        const double* src = nullptr;
+        int64_t len = 0;
+        switch (which) {
+            case 0: src = c->w.p; len = c->m; break;
+            case 1: src = c->rho.p; len = c->n_local; break;
+            case 2: src = c->degree.p; len = c->n_local; break;
+            case 3: src = c->csum.p; len = c->m; break;
+            default: throw Error("get_vector: which must be 0 (weights), 1 (row norms), 2 (degrees) or 3 (column sums)");
+        }
+        if (len > 0) SB_CUDA(cudaMemcpyAsync(out, src, sizeof(double) * len, cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+    });
 }
 
 int snapb200_view_norms(snapb200_ctx* c, double* idf_out, double* rho_out) {

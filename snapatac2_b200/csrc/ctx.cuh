@@ -194,6 +194,14 @@ struct snapb200_ctx {
     // scratch
     snapb::DevBuf<unsigned char> scratch;
     snapb::PinBuf<unsigned char> pinned;
+    snapb::PinBuf<unsigned char> ring;          // pinned ring of the host staging team (ingest.cu)
+    std::vector<cudaEvent_t> ring_events;
+
+    // multi-view (multi_spectral): further views chained behind this context by combine_views();
+    // they share this context's stream and communicator (attach_view) and are owned by the caller
+    std::vector<snapb200_ctx*> views;
+    snapb::DevBuf<float> neg_one;   // n  (accumulating pass 2 of the views after the first)
+    bool borrowed = false;          // stream / communicator belong to another context
 
     snapb200_stats stats{};
 
@@ -209,6 +217,13 @@ void comm_destroy(snapb200_ctx* c);
 void allreduce_f32(snapb200_ctx* c, float* buf, int64_t count);
 void allreduce_f64(snapb200_ctx* c, double* buf, int64_t count);
 void allreduce_i64(snapb200_ctx* c, int64_t* buf, int64_t count);
+
+// ---- ingest.cu: threaded staging between pageable host arrays and the device
+int host_threads(const snapb200_ctx* c);
+bool stage_indices(snapb200_ctx* c, const void* src, int bits, int64_t count, int32_t* dst_dev);
+bool host_values_all_ones(snapb200_ctx* c, const void* values, int kind, int64_t count);
+void stage_values(snapb200_ctx* c, const void* src, int kind, int64_t count, float* dst_dev);
+void copy_to_host(snapb200_ctx* c, void* dst, const void* src_dev, size_t bytes);
 
 // ---- synth.cu
 void generate_rows(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, int64_t m,
@@ -229,6 +244,8 @@ void ensure_xt(snapb200_ctx* c);   // builds the CSR feature-major copy c->Xt if
 void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local);
 void prepare(snapb200_ctx* c, double* idf_out, double* degree_out);
 void view_norms(snapb200_ctx* c, double* idf_out, double* rho_out);
+double view_frobenius(snapb200_ctx* c, const int64_t* sample_rows, int64_t ns_local);
+void combine_views(snapb200_ctx* main, snapb200_ctx** views, const double* cv, int n_views, double* degree_out);
 // IDF (or user) weights and weighted row norms of the loaded matrix into device buffers (no transpose)
 void weights_and_norms(snapb200_ctx* c, double* w_dev, double* rho_dev);
 

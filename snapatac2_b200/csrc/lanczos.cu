@@ -451,7 +451,9 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
     if (n > 0) {
         dEvec.alloc(n * k);
         tall_gemm_f64(c, Q.p, ld, nb, dS.p, k8, k, n, dEvec.p, k);
-        SB_CUDA(cudaMemcpyAsync(evecs, dEvec.p, sizeof(double) * n * k, cudaMemcpyDeviceToHost, st));
+        HostClock hx;
+        copy_to_host(c, evecs, dEvec.p, sizeof(double) * static_cast<size_t>(n) * k);   // pageable numpy memory: threaded staging
+        c->stats.ms_d2h = hx.ms();
     }
     SB_CUDA(cudaStreamSynchronize(st));
     for (auto& es : evs)

@@ -423,6 +423,7 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out) {
     auto since = [](std::chrono::steady_clock::time_point t0) {
         return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     };
+    c->views.clear();   // a new prepare invalidates a multi-view combination
     decide_spmm_mode(c);
     const bool tiled = use_tiled(c, c->block);
     const bool user_w = !c->user_weights.empty();
@@ -648,6 +649,195 @@ void view_norms(snapb200_ctx* c, double* idf_out, double* rho_out) {
     if (idf_out) SB_CUDA(cudaMemcpyAsync(idf_out, w.p, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
     if (rho_out && n > 0) SB_CUDA(cudaMemcpyAsync(rho_out, rho.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
+}
+
+// ==========================================================================
+// Multi-view embedding on the device (multi_spectral_embedding, embedding.rs:388-452) as a
+// VIRTUAL column concatenation: every view keeps its own context (pattern, tiled copies, IDF
+// weights, row norms) and the views only share the dense block V and the degree vector,
+//     A V = sum_v X~_v (X~_v^T V) - D^-1 V,   X~_v = diag(r_v) P_v diag(w_v),
+//     r_v,i = sqrt(1/d_i) c_v / rho_v,i,      c_v = sqrt((weight_v / norm_v) / sum)   (:428-442)
+// -- exactly the operator of the hstack-ed matrix (:443, :367-385) without ever forming it, and a
+// binarised view keeps its 2-byte pattern-only entries next to a valued one.  The stacked rows
+// have unit norm (sum_v c_v^2 = 1), so  d_i = sum_v c_v^2 (d_v,i + 1) - 1  with d_v the degrees
+// the ordinary single-view prepare() computes for view v.
+// ==========================================================================
+namespace {
+
+__global__ void sample_mask_kernel(const int64_t* __restrict__ rows, int64_t ns, const double* __restrict__ rho,
+                                   double* __restrict__ msk) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < ns) msk[rows[i]] = 1.0 / rho[rows[i]];
+}
+__global__ void sumsq_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ part) {
+    __shared__ double ss[256];
+    double s = 0.0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) s += v[i] * v[i];
+    ss[threadIdx.x] = s;
+    __syncthreads();
+    for (int k = blockDim.x / 2; k > 0; k >>= 1) {
+        if (threadIdx.x < k) ss[threadIdx.x] += ss[threadIdx.x + k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = ss[0];
+}
+// d (in: first view's degrees) <- c0^2 (d + 1) - 1   or   d += cv^2 (dv + 1)
+__global__ void combine_degree_kernel(double* __restrict__ d, const double* __restrict__ dv, double c2, int first, int64_t n) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (first) d[i] = c2 * (d[i] + 1.0) - 1.0;
+    else d[i] += c2 * (dv[i] + 1.0);
+}
+__global__ void view_rowscale_kernel(const double* __restrict__ d, const double* __restrict__ rho, double cv, int64_t n,
+                                     float* __restrict__ r) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) r[i] = static_cast<float>(sqrt(1.0 / d[i]) * cv / rho[i]);
+}
+
+// out_cols[m] = scale_cols .* (P^T x_rows)   through whichever feature-major copy the context has
+void col_product(snapb200_ctx* c, const double* x_rows, const double* scale_cols, double* out_cols) {
+    if (c->S1.built) {
+        sell_spmv64(c, c->S1, x_rows, 1, scale_cols, 0.0, out_cols);
+    } else {
+        ensure_xt(c);
+        spmv_f64_kernel<1><<<grid_for_rows(c, c->m), 256, 0, c->stream>>>(c->Xt.ptr.p, c->Xt.idx.p, c->Xt.val.p, x_rows,
+                                                                           scale_cols, 0.0, c->m, out_cols);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
+}
+// out_rows[n] = scale_rows .* (P x_cols) + shift
+void row_product(snapb200_ctx* c, const double* x_cols, const double* scale_rows, double shift, double* out_rows) {
+    if (c->n_local == 0) return;
+    if (c->S2.built) {
+        sell_spmv64(c, c->S2, x_cols, 1, scale_rows, shift, out_rows);
+    } else {
+        spmv_f64_kernel<1><<<grid_for_rows(c, c->n_local), 256, 0, c->stream>>>(c->X.ptr.p, c->X.idx.p, c->X.val.p, x_cols,
+                                                                                 scale_rows, shift, c->n_local, out_rows);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
+}
+
+double sum_of_squares(snapb200_ctx* c, const double* v, int64_t n) {
+    const int nb = 256;
+    DevBuf<double> part;
+    part.alloc(nb);
+    sumsq_kernel<<<nb, 256, 0, c->stream>>>(v, n, part.p);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+    std::vector<double> h(nb);
+    SB_CUDA(cudaMemcpyAsync(h.data(), part.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, c->stream));
+    SB_CUDA(cudaStreamSynchronize(c->stream));
+    double t = 0.0;
+    for (double x : h) t += x;
+    if (c->nranks > 1) {
+        DevBuf<double> d;
+        d.alloc(1);
+        SB_CUDA(cudaMemcpyAsync(d.p, &t, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        allreduce_f64(c, d.p, 1);
+        SB_CUDA(cudaMemcpyAsync(&t, d.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        SB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return t;
+}
+
+}  // namespace
+
+// The value the Python snippet inside frobenius_norm (embedding.rs:456-460) returns for the unit-norm
+// rows `sample_rows` (local ids, this rank's part of the sample) when it is handed a
+// scipy.sparse.csr_matrix:  np.power(S, 2) is then the MATRIX square of S = Xs Xs^T, whose sum is
+// || S 1 ||^2 = sum_i ( xhat_i . sum_{i' in sample} xhat_i' )^2  -- two fp64 SpMVs over the
+// prepared view, no Gram matrix.  Collective over the row shards.
+double view_frobenius(snapb200_ctx* c, const int64_t* sample_rows, int64_t ns_local) {
+    SB_CHECK(c->prepared, "view_frobenius: call prepare first");
+    const int64_t n = c->n_local, m = c->m;
+    cudaStream_t st = c->stream;
+    DevBuf<double> msk, cs, wc, y;
+    DevBuf<int64_t> rows;
+    msk.alloc(n + 2);
+    cs.alloc(m);
+    wc.alloc(m + 2);
+    y.alloc(std::max<int64_t>(1, n));
+    SB_CUDA(cudaMemsetAsync(msk.p, 0, sizeof(double) * (n + 2), st));
+    if (ns_local > 0) {
+        for (int64_t i = 0; i < ns_local; ++i) SB_CHECK(sample_rows[i] >= 0 && sample_rows[i] < n, "view_frobenius: sample row out of range");
+        rows.alloc(ns_local);
+        SB_CUDA(cudaMemcpyAsync(rows.p, sample_rows, sizeof(int64_t) * ns_local, cudaMemcpyHostToDevice, st));
+        sample_mask_kernel<<<grid1d(ns_local), 256, 0, st>>>(rows.p, ns_local, c->rho.p, msk.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c);
+    }
+    col_product(c, msk.p, c->w.p, cs.p);                       // sum of the sampled unit rows
+    allreduce_f64(c, cs.p, m);
+    mul_kernel<<<grid1d(m), 256, 0, st>>>(c->w.p, cs.p, wc.p, m);
+    SB_LAUNCH_CHECK();
+    count_launch(c);
+    SB_CUDA(cudaMemsetAsync(y.p, 0, sizeof(double) * std::max<int64_t>(1, n), st));
+    row_product(c, wc.p, msk.p, 0.0, y.p);                     // (S 1)_i on the sampled rows, 0 elsewhere
+    const double total = sum_of_squares(c, y.p, n);
+    SB_CUDA(cudaStreamSynchronize(st));                        // `rows` came from a host temporary
+    return total;
+}
+
+// Chain `n_views` prepared view contexts behind `main` (views[0] must be main itself) with the view
+// scales c_v: combined degrees, D^-1, the trivial eigenvector and every view's operator row scale.
+void combine_views(snapb200_ctx* main, snapb200_ctx** views, const double* cv, int n_views, double* degree_out) {
+    SB_CHECK(n_views >= 1 && views[0] == main, "combine_views: views[0] must be the main context");
+    const int64_t n = main->n_local;
+    cudaStream_t st = main->stream;
+    for (int v = 0; v < n_views; ++v) {
+        snapb200_ctx* x = views[v];
+        SB_CHECK(x->prepared, "combine_views: every view must be prepared");
+        SB_CHECK(x->n_local == n && x->n_global == main->n_global && x->row0 == main->row0, "combine_views: views must hold the same cells");
+        SB_CHECK(x->stream == st && x->device == main->device, "combine_views: attach the view contexts first");
+    }
+    for (int v = 0; v < n_views; ++v) {
+        if (n > 0) {
+            combine_degree_kernel<<<grid1d(n), 256, 0, st>>>(main->degree.p, views[v]->degree.p, cv[v] * cv[v], v == 0 ? 1 : 0, n);
+            SB_LAUNCH_CHECK();
+        }
+    }
+    const int nb = 256;
+    DevBuf<double> psum;
+    DevBuf<int64_t> pbad;
+    psum.alloc(nb);
+    pbad.alloc(nb);
+    degree_stats_kernel<<<nb, 256, 0, st>>>(main->degree.p, n, psum.p, pbad.p);
+    SB_LAUNCH_CHECK();
+    std::vector<double> hsum(nb);
+    std::vector<int64_t> hbad(nb);
+    SB_CUDA(cudaMemcpyAsync(hsum.data(), psum.p, sizeof(double) * nb, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaMemcpyAsync(hbad.data(), pbad.p, sizeof(int64_t) * nb, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    double tot[2] = {0.0, 0.0};
+    for (int i = 0; i < nb; ++i) { tot[0] += hsum[i]; tot[1] += static_cast<double>(hbad[i]); }
+    if (main->nranks > 1) {
+        DevBuf<double> t2;
+        t2.alloc(2);
+        SB_CUDA(cudaMemcpyAsync(t2.p, tot, sizeof(double) * 2, cudaMemcpyHostToDevice, st));
+        allreduce_f64(main, t2.p, 2);
+        SB_CUDA(cudaMemcpyAsync(tot, t2.p, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+    }
+    SB_CHECK(!(tot[1] > 0.0), "combine_views: a cell has a non-positive combined degree");
+    if (n > 0) {
+        // D^-1 and the trivial eigenvector from the combined degrees (rho is not used for them)
+        derive_rows_kernel<<<grid1d(n), 256, 0, st>>>(main->degree.p, main->rho.p, 1.0 / sqrt(tot[0]), n, main->r.p, main->dinv.p,
+                                                     main->u1.p);
+        SB_LAUNCH_CHECK();
+        for (int v = 0; v < n_views; ++v) {
+            view_rowscale_kernel<<<grid1d(n), 256, 0, st>>>(main->degree.p, views[v]->rho.p, cv[v], n, views[v]->r.p);
+            SB_LAUNCH_CHECK();
+        }
+        main->neg_one.alloc(n);
+        fill_f32(main, main->neg_one.p, -1.f, n);
+    }
+    count_launch(main, n_views * 2 + 3);
+    if (degree_out && n > 0) SB_CUDA(cudaMemcpyAsync(degree_out, main->degree.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    main->views.assign(views + 1, views + n_views);
 }
 
 }  // namespace snapb

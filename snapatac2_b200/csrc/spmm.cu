@@ -110,7 +110,8 @@ gather_rows_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ 
 
 // Shared-memory tiled path (b = 4 or 8): both passes run over the sliced-ELL copies.
 template <int B>
-void apply_tiled(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, cudaEvent_t* evs, bool vr_ready) {
+void apply_tiled(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, cudaEvent_t* evs, bool vr_ready,
+                 const float* subscale, const float* sub, int64_t lds) {
     SB_CHECK(ldy == B, "tiled operator: Y must be packed (leading dimension b)");
     const int64_t n = c->n_local, m = c->m;
     cudaStream_t st = c->stream;
@@ -128,7 +129,7 @@ void apply_tiled(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t
     allreduce_f32(c, c->W.p, m * B);
     if (evs) SB_CUDA(cudaEventRecord(evs[2], st));
     // pass 2: Y = r .* (P W) - dinv .* V
-    sell_spmm(c, c->S2, c->W.p, Y, c->r.p, c->dinv.p, V, ldv);
+    sell_spmm(c, c->S2, c->W.p, Y, c->r.p, subscale, sub, lds);
     if (evs) SB_CUDA(cudaEventRecord(evs[3], st));
 }
 
@@ -137,7 +138,8 @@ inline int grid_rows(snapb200_ctx* c, int64_t nrows) {
 }
 
 template <int B>
-void apply_impl(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, cudaEvent_t* evs, bool vr_ready) {
+void apply_impl(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, cudaEvent_t* evs, bool vr_ready,
+                const float* subscale, const float* sub, int64_t lds) {
     const int64_t n = c->n_local, m = c->m;
     cudaStream_t st = c->stream;
     c->Vr.ensure(std::max<int64_t>(1, n * B));
@@ -165,10 +167,10 @@ void apply_impl(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t 
     if (n > 0) {
         if (c->X.has_values())
             gather_rows_kernel<B, true, true><<<grid_rows(c, n), 256, 0, st>>>(
-                c->X.ptr.p, c->X.idx.p, c->X.val.p, c->W.p, c->r.p, n, Y, ldy, c->dinv.p, V, ldv);
+                c->X.ptr.p, c->X.idx.p, c->X.val.p, c->W.p, c->r.p, n, Y, ldy, subscale, sub, lds);
         else
             gather_rows_kernel<B, false, true><<<grid_rows(c, n), 256, 0, st>>>(
-                c->X.ptr.p, c->X.idx.p, nullptr, c->W.p, c->r.p, n, Y, ldy, c->dinv.p, V, ldv);
+                c->X.ptr.p, c->X.idx.p, nullptr, c->W.p, c->r.p, n, Y, ldy, subscale, sub, lds);
         SB_LAUNCH_CHECK();
         count_launch(c);
     }
@@ -177,23 +179,46 @@ void apply_impl(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t 
 
 }  // namespace
 
-void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, int b, cudaEvent_t* evs,
-                        bool vr_ready) {
-    SB_CHECK(c->prepared, "operator: call prepare first");
-    SB_CHECK(ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "operator: Y must be 16-byte aligned");
+// one view's two passes:  Y = r .* (P (w^2 .* P^T (r .* V))) - subscale .* sub
+static void apply_view(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, int b, cudaEvent_t* evs,
+                       bool vr_ready, const float* subscale, const float* sub, int64_t lds) {
     if (use_tiled(c, b)) {
         ensure_tiled(c, b);   // no-op when prepare() already built the copies for this width
         c->stats.spmm_tiled = 1;
-        if (b == 8) apply_tiled<8>(c, V, ldv, Y, ldy, evs, vr_ready);
-        else apply_tiled<4>(c, V, ldv, Y, ldy, evs, vr_ready);
+        if (b == 8) apply_tiled<8>(c, V, ldv, Y, ldy, evs, vr_ready, subscale, sub, lds);
+        else apply_tiled<4>(c, V, ldv, Y, ldy, evs, vr_ready, subscale, sub, lds);
         return;
     }
     c->stats.spmm_tiled = 0;
     switch (b) {
-        case 4: apply_impl<4>(c, V, ldv, Y, ldy, evs, vr_ready); break;
-        case 8: apply_impl<8>(c, V, ldv, Y, ldy, evs, vr_ready); break;
-        case 16: apply_impl<16>(c, V, ldv, Y, ldy, evs, vr_ready); break;
+        case 4: apply_impl<4>(c, V, ldv, Y, ldy, evs, vr_ready, subscale, sub, lds); break;
+        case 8: apply_impl<8>(c, V, ldv, Y, ldy, evs, vr_ready, subscale, sub, lds); break;
+        case 16: apply_impl<16>(c, V, ldv, Y, ldy, evs, vr_ready, subscale, sub, lds); break;
         default: throw Error("operator: block width must be 4, 8 or 16");
+    }
+}
+
+void operator_apply_dev(snapb200_ctx* c, const float* V, int64_t ldv, float* Y, int64_t ldy, int b, cudaEvent_t* evs,
+                        bool vr_ready) {
+    SB_CHECK(c->prepared, "operator: call prepare first");
+    SB_CHECK(ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0, "operator: Y must be 16-byte aligned");
+    if (c->views.empty()) {
+        apply_view(c, V, ldv, Y, ldy, b, evs, vr_ready, c->dinv.p, V, ldv);
+        return;
+    }
+    // multi-view: Y = sum_v X~_v X~_v^T V - dinv .* V; the first view subtracts dinv .* V, the others
+    // accumulate onto Y (subscale = -1, sub = Y)
+    if (evs) {
+        SB_CUDA(cudaEventRecord(evs[0], c->stream));
+    }
+    apply_view(c, V, ldv, Y, ldy, b, nullptr, vr_ready, c->dinv.p, V, ldv);
+    for (snapb200_ctx* v : c->views) {
+        apply_view(v, V, ldv, Y, ldy, b, nullptr, false, c->neg_one.p, Y, ldy);
+    }
+    if (evs) {
+        SB_CUDA(cudaEventRecord(evs[1], c->stream));
+        SB_CUDA(cudaEventRecord(evs[2], c->stream));
+        SB_CUDA(cudaEventRecord(evs[3], c->stream));
     }
 }
 

@@ -29,6 +29,9 @@ class Engine:
 
     # ------------------------------------------------------------ lifetime
     def close(self):
+        for v in getattr(self, "_view_engines", []):
+            v.close()
+        self._view_engines = []
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
             self._lib.snapb200_destroy(self._ctx)
             self._ctx = C.c_void_p()
@@ -76,23 +79,35 @@ class Engine:
         self.n_local, self.n_global, self.row0, self.m = int(n_local), int(n_global), int(row0), int(m)
 
     def load_csr(self, X, n_global=None, row0=0, binarized: bool | None = None):
-        """Load a scipy CSR row shard.  ``binarized=True`` skips the values
-        (caller guarantees every stored entry is 1)."""
+        """Load a scipy CSR row shard as it is: int32 or int64 index arrays and any supported value
+        dtype go to the library untouched (pageable memory is fine -- the library stages them with
+        a thread team, narrows 64-bit indices on the way and recognises an all-ones value array
+        without shipping it).  ``binarized=True`` skips even the scan of the values (caller
+        guarantees every stored entry is 1).  Rows must be sorted and duplicate-free; the device
+        checks that, and a matrix that fails the check is canonicalised on the host and retried."""
         if not sp.issparse(X):
             X = sp.csr_matrix(np.asarray(X))
         if X.format != "csr":
             raise ValueError("X must be a CSR matrix (the reference rejects CSC input as well)")
-        if not X.has_canonical_format:      # sorted, duplicate-free rows are part of the C ABI contract
+
+        def attempt(M):
+            indptr = np.ascontiguousarray(M.indptr)
+            indices = np.ascontiguousarray(M.indices)
+            values = None
+            if not binarized:
+                values = np.ascontiguousarray(M.data)
+                if _lib.value_kind(values.dtype) is None:
+                    values = values.astype(np.float64)
+            self.load_arrays(indptr, indices, values, M.shape[0], M.shape[1], n_global, row0)
+
+        try:
+            attempt(X)
+        except RuntimeError as e:
+            if "strictly increasing" not in str(e):
+                raise
             X = X.copy()
-            X.sum_duplicates()
-        indptr = np.ascontiguousarray(X.indptr)
-        indices = np.ascontiguousarray(X.indices)
-        values = None
-        if not binarized:
-            values = np.ascontiguousarray(X.data)
-            if _lib.value_kind(values.dtype) is None:
-                values = values.astype(np.float64)
-        self.load_arrays(indptr, indices, values, X.shape[0], X.shape[1], n_global, row0)
+            X.sum_duplicates()      # sorts the rows and merges duplicates (scipy's canonical format)
+            attempt(X)
 
     def generate(self, spec, row0=0, n_local=None):
         """Synthetic planted-cluster rows generated on the device."""
@@ -154,6 +169,36 @@ class Engine:
         rho = np.empty(self.n_local, dtype=np.float64)
         _lib.check(self._lib.snapb200_view_norms(self._ctx, _lib.ptr(idf), _lib.ptr(rho)))
         return idf, rho
+
+    # ------------------------------------------------------------ multi-view (virtual hstack)
+    def attach_view(self, view: "Engine"):
+        """``view`` adopts this engine's stream and communicator (multi_spectral); this engine must
+        outlive it."""
+        _lib.check(self._lib.snapb200_attach_view(self._ctx, view._ctx))
+        view.rank, view.nranks = self.rank, self.nranks
+
+    def view_frobenius(self, sample_rows_local) -> float:
+        """Value of the reference's ``frobenius_norm`` snippet on the sampled unit rows (csr_matrix
+        reading: ``sum((X X^T) @ (X X^T))``); collective over the row shards."""
+        rows = np.ascontiguousarray(sample_rows_local, dtype=np.int64)
+        out = C.c_double()
+        _lib.check(self._lib.snapb200_view_frobenius(self._ctx, _lib.ptr(rows) if rows.size else None, int(rows.size), C.byref(out)))
+        return out.value
+
+    def combine_views(self, views: "list[Engine]", scales, want_degree=False):
+        """Chain the prepared ``views`` (``views[0]`` is this engine) with the view scales ``c_v``."""
+        assert views and views[0] is self
+        arr = (C.c_void_p * len(views))(*[v._ctx for v in views])
+        cv = np.ascontiguousarray(scales, dtype=np.float64)
+        deg = np.empty(self.n_local, dtype=np.float64) if want_degree else None
+        _lib.check(self._lib.snapb200_combine_views(self._ctx, arr, _lib.ptr(cv), len(views), _lib.ptr(deg)))
+        return deg
+
+    def get_vector(self, which: str) -> np.ndarray:
+        code = {"weights": 0, "rho": 1, "degree": 2, "colsum": 3}[which]
+        out = np.empty(self.m if code in (0, 3) else self.n_local, dtype=np.float64)
+        _lib.check(self._lib.snapb200_get_vector(self._ctx, code, _lib.ptr(out)))
+        return out
 
     def prepare_projection(self, want_outputs=True):
         """What :meth:`project` needs (weights, row norms, cell-major tiled copy), without the

@@ -322,30 +322,37 @@ def spectral(
     return evals, evecs
 
 
-def _frobenius_offdiag(xhat: sp.csr_matrix) -> float:
-    """``sqrt(sum((X X^T)^2) - n)`` on (at most 2000) unit-norm rows -- the view
-    normaliser of embedding.rs:454-471.  A 2000 x 2000 Gram: host side."""
-    s = xhat @ xhat.T
-    return float(np.sqrt(float(s.multiply(s).sum()) - xhat.shape[0]))
+def _view_engines(engine: Engine, n_views: int) -> list[Engine]:
+    """``engine`` plus ``n_views - 1`` further contexts on the same GPU that share its stream and
+    communicator (kept with the engine and reused across calls)."""
+    extra = getattr(engine, "_view_engines", None)
+    if extra is None:
+        extra = engine._view_engines = []
+    while len(extra) < n_views - 1:
+        v = Engine(engine.device)
+        engine.attach_view(v)
+        extra.append(v)
+    return [engine] + extra[:n_views - 1]
 
 
 def multi_spectral_embedding(engine: Engine, xs, selected_features, weights, n_components, random_state,
-                             *, sample_rows=None, tol=0.0, block=0, return_parts=False):
-    """Counterpart of ``internal.multi_spectral_embedding`` (embedding.rs:388-452).
+                             *, sample_rows=None, tol=0.0, block=0, return_parts=False, container="csr_matrix"):
+    """Counterpart of ``internal.multi_spectral_embedding`` (embedding.rs:388-452), entirely on the
+    device and without the column concatenation ever being formed.
 
-    Per view the device computes the IDF weights and the norms of the
-    IDF-weighted rows (``snapb200_view_norms``; embedding.rs:413-416).  The
-    Frobenius normaliser is taken over all rows when ``n <= 2000`` and over
-    2000 sampled rows otherwise (:417-421); the reference samples with Rust's
-    ``StdRng(2023)``, which cannot be reproduced outside Rust, so the sample is
-    ``sample_rows`` if given, else ``numpy.random.RandomState(2023)`` -- a
-    documented deviation.  The views are scaled by ``sqrt((w_i/norm_i)/sum)``
-    (:428-442), concatenated column-wise (:443) -- on the host -- and handed to
-    the ordinary load/prepare/eigsh path with the concatenated IDF weights as
-    feature weights and ``c_v / rho_v,i`` folded into the stored values, so the
-    stacked rows already have unit norm exactly as in ``spectral_mf`` (:447).
-    Under ``torchrun`` every rank passes its block of cells of every view; the
-    sampled rows for the normaliser are exchanged over ``torch.distributed``.
+    Every view gets its own context on the GPU: load, column selection, IDF weights, row norms,
+    both tiled copies and its single-view degrees -- the ordinary ``prepare`` (:404-416).  The view
+    normaliser ``frobenius_norm`` (:454-471) is evaluated on all rows when ``n <= 2000`` and on
+    2000 sampled rows otherwise (:417-421); the reference samples with Rust's ``StdRng(2023)``,
+    which cannot be reproduced outside Rust, so the sample is ``sample_rows`` if given, else
+    ``numpy.random.RandomState(2023)`` -- a documented deviation.  ``container`` names the scipy
+    container the embedded Python snippet receives: ``"csr_matrix"`` (what pyanndata builds, the
+    default; ``np.power`` is then a matrix power and the snippet equals ``||(X X^T) 1||^2``, two
+    SpMVs on the device) or ``"csr_array"`` (element-wise square, the Frobenius norm the name
+    promises; the <= 2000 x 2000 Gram of the sampled rows is formed on the host).  The scaled views
+    (:428-442) are then chained behind one operator, ``A = sum_v X~_v X~_v^T - D^-1`` (the hstack of
+    :443 and ``spectral_mf`` of :447 in factored form; ``snapb200_combine_views``).  Under
+    ``torchrun`` every rank passes its block of cells of every view.
     """
     rank, world = dist.world()
     n_local = xs[0].shape[0]
@@ -354,48 +361,53 @@ def multi_spectral_embedding(engine: Engine, xs, selected_features, weights, n_c
         n_global, row0 = sum(n_locals), dist.shard_offsets(n_locals)[rank]
     else:
         n_global, row0 = n_local, 0
-    views, idfs, norms = [], [], []
-    for X, sel in zip(xs, selected_features):
+    if n_global <= 2000:
+        rows = np.arange(n_global)
+    elif sample_rows is not None:
+        rows = np.sort(np.asarray(sample_rows))
+    else:
+        rows = np.sort(np.random.RandomState(2023).choice(n_global, 2000, replace=False))
+    mine = rows[(rows >= row0) & (rows < row0 + n_local)] - row0
+    views = _view_engines(engine, len(xs))
+    norms, idfs = [], []
+    for eng, X, sel in zip(views, xs, selected_features):
         if not sp.issparse(X) or X.format != "csr":
             X = sp.csr_matrix(X)
         if X.shape[0] != n_local:
             raise ValueError("all views must hold the same cells")
         mask, _ = _feature_mask(sel, X.shape[1], None)
-        engine.load_csr(X, n_global=n_global, row0=row0)
+        eng.load_csr(X, n_global=n_global, row0=row0)
         if mask is not None:
-            engine.select_features(mask)
-            X = X[:, mask]
-        idf, rho = engine.view_norms()          # document frequencies are all-reduced over the shards
-        Xs = sp.csr_matrix(X, dtype=np.float64)
-        if n_global <= 2000:
-            rows = np.arange(n_global)
-        elif sample_rows is not None:
-            rows = np.sort(np.asarray(sample_rows))
+            eng.select_features(mask)
+        eng.set_feature_weights(None)           # the views always use their own IDF (:413)
+        idf, _ = eng.prepare(want_outputs=return_parts)
+        if container == "csr_matrix":
+            total = eng.view_frobenius(mine)
+        elif container == "csr_array":
+            w, rho = eng.get_vector("weights"), eng.get_vector("rho")
+            Xm = X[mine] if mask is None else X[mine][:, np.flatnonzero(mask)]
+            xhat_s = sp.csr_matrix(sp.diags(1.0 / rho[mine]) @ (sp.csr_matrix(Xm, dtype=np.float64) @ sp.diags(w)))
+            if world > 1:   # the sampled unit rows of all shards on every rank
+                xhat_s = sp.csr_matrix(sp.vstack(dist.allgather_objects(xhat_s), format="csr"))
+            g = xhat_s @ xhat_s.T
+            total = float(g.multiply(g).sum())
         else:
-            rows = np.sort(np.random.RandomState(2023).choice(n_global, 2000, replace=False))
-        mine = rows[(rows >= row0) & (rows < row0 + n_local)] - row0
-        xhat_s = sp.csr_matrix(sp.diags(1.0 / rho[mine]) @ (Xs[mine] @ sp.diags(idf)))
-        if world > 1:   # the sampled unit rows of all shards, in global row order, on every rank
-            xhat_s = sp.csr_matrix(sp.vstack(dist.allgather_objects(xhat_s), format="csr"))
-        norms.append(_frobenius_offdiag(xhat_s))
-        views.append((Xs, rho))
+            raise ValueError("container must be 'csr_matrix' or 'csr_array'")
+        norms.append(float(np.sqrt(total - len(rows))))
         idfs.append(idf)
     ws = [w / nrm for w, nrm in zip(weights, norms)]
     w_sum = float(sum(ws))
-    scaled = [sp.diags(np.sqrt(w / w_sum) / rho) @ Xs for (Xs, rho), w in zip(views, ws)]
-    stacked = sp.csr_matrix(sp.hstack(scaled, format="csr"))
-    stacked.sort_indices()
-    fw = np.concatenate(idfs)
-    out = spectral_embedding(engine, stacked, None, n_components, random_state, fw, n_global=n_global, row0=row0,
-                             tol=tol, block=block, return_parts=return_parts)
+    scales = [float(np.sqrt(w / w_sum)) for w in ws]
+    degree = engine.combine_views(views, scales, want_degree=return_parts)
+    evals, evecs = engine.eigsh(n_components, seed=random_state, tol=tol, block=block)
     if return_parts:
-        return out + (norms,)
-    return out
+        return evals, evecs, np.concatenate(idfs), degree, norms
+    return evals, evecs
 
 
 def multi_spectral(adatas, n_comps: int = 30, features="selected", weights=None,
                    random_state: int = 0, weighted_by_sd: bool = True, *,
-                   engine: Engine | None = None, sample_rows=None):
+                   engine: Engine | None = None, sample_rows=None, container: str = "csr_matrix"):
     """Laplacian eigenmaps on several modalities at once -- same call as
     ``snap.tl.multi_spectral`` (tools/_embedding.py:483-540); returns
     ``(evals, evecs)`` and does not write into the AnnData objects."""
@@ -406,13 +418,10 @@ def multi_spectral(adatas, n_comps: int = 30, features="selected", weights=None,
         features = [_resolve_features(a, f) for a, f in zip(adatas, features)]
     if weights is None:                                                     # :530-531
         weights = [1.0 for _ in adatas]
-    n_obs = min(a.n_obs for a in adatas)
-    if dist.world()[1] > 1:
-        n_obs = sum(dist.allgather_ints(n_obs))
-    n_comps = min(n_obs - 1, n_comps)
+    # (no n_comps clamp here: the reference's multi_spectral has none, :523-533)
     eng = _check_engine(engine) if engine is not None else default_engine()
     evals, evecs = multi_spectral_embedding(eng, [_get_csr(a) for a in adatas], features, weights,
-                                            n_comps, random_state, sample_rows=sample_rows)   # :533
+                                            n_comps, random_state, sample_rows=sample_rows, container=container)   # :533
     if weighted_by_sd:                                                      # :535-538
         idx = [i for i in range(evals.shape[0]) if evals[i] > 0]
         evals = evals[idx]

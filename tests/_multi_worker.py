@@ -17,8 +17,15 @@ torch.cuda.set_device(local)
 td.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
 mode = sys.argv[1] if len(sys.argv) > 1 else "auto"
 
-spec = synth.make_spec(9000, 60000, 1200, n_clusters=40, seed=3)
-k = 20
+# SNAPB200_MULTI_CONFIG=c3: the same check on BASELINE.json configs[2] (1M x 500k, ~5k nnz/cell, k=30);
+# rank 0 then holds its shard and the whole matrix (fits one B200)
+BIG = os.environ.get("SNAPB200_MULTI_CONFIG", "") == "c3"
+if BIG:
+    spec = synth.make_spec(1_000_000, 500_000, 5_000, n_clusters=48, seed=0)
+    k = 30
+else:
+    spec = synth.make_spec(9000, 60000, 1200, n_clusters=40, seed=3)
+    k = 20
 bounds = dist.equal_row_splits(spec.n, world)
 r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
 
@@ -35,12 +42,13 @@ parts = [None] * world
 td.gather_object((deg, evecs), parts if rank == 0 else None, dst=0)
 
 # the public wrapper in distributed mode: every rank passes its own row block
-X_local = eng.export_csr()
-ad = MiniAnnData(X_local)
-tl._engine = eng
-ev_w, emb_w = tl.spectral(ad, n_comps=k, features=None, inplace=False, weighted_by_sd=False)
-assert np.allclose(ev_w, evals, rtol=1e-9), (ev_w, evals)
-assert emb_w.shape == (r1 - r0, k)
+if not BIG:
+    X_local = eng.export_csr()
+    ad = MiniAnnData(X_local)
+    tl._engine = eng
+    ev_w, emb_w = tl.spectral(ad, n_comps=k, features=None, inplace=False, weighted_by_sd=False)
+    assert np.allclose(ev_w, evals, rtol=1e-9), (ev_w, evals)
+    assert emb_w.shape == (r1 - r0, k)
 
 if rank == 0:
     deg_all = np.concatenate([p[0] for p in parts])
@@ -56,8 +64,14 @@ if rank == 0:
     cos = np.abs(np.sum(evec_all * evec1, axis=0)) / (np.linalg.norm(evec_all, axis=0) * np.linalg.norm(evec1, axis=0))
     assert cos.min() > 0.99999, cos
     assert abs(np.linalg.norm(evec_all[:, 3]) - 1.0) < 1e-5
-    print(f"MULTI_OK world={world} mode={mode} n_ops={stats['n_ops']} ms_comm={stats['ms_comm']:.3f} min_cos={cos.min():.8f}")
+    print(f"MULTI_OK world={world} mode={mode} n={spec.n} k={k} n_ops={stats['n_ops']} ms_comm={stats['ms_comm']:.3f} "
+          f"max_rel_eval_diff={np.max(np.abs(evals - ev1) / np.abs(ev1)):.3e} min_cos={cos.min():.8f}")
     solo.close()
+if BIG:
+    td.barrier()
+    eng.close()
+    td.destroy_process_group()
+    sys.exit(0)
 
 # ---- multi-view (tl.multi_spectral, embedding.rs:388-452) on row shards: every rank passes its
 #      block of both views; the result must match the CPU oracle on the full views

@@ -220,6 +220,16 @@ def test_multi_spectral_matches_oracle(engine):
     ev_o, evec_o = oracle.multi_spectral_embedding([atac, rna], [None, None], [1.0, 1.0], 8, 0)
     evals, evecs = tl.multi_spectral_embedding(engine, [atac, rna], [None, None], [1.0, 1.0], 8, 0)
     _check_against(ev_o, evec_o, evals, evecs)
+    # the intermediate quantities: view normalisers (both readings of the frobenius_norm snippet) and degrees
+    for container in ("csr_matrix", "csr_array"):
+        ev_o, evec_o, norms_o, deg_o = oracle.multi_spectral_embedding([atac, rna], [None, None], [1.0, 3.0], 8, 0,
+                                                                       return_parts=True, container=container)
+        evals, evecs, idf, deg, norms = tl.multi_spectral_embedding(engine, [atac, rna], [None, None], [1.0, 3.0], 8, 0,
+                                                                    return_parts=True, container=container)
+        np.testing.assert_allclose(norms, norms_o, rtol=TOL_VEC)
+        np.testing.assert_allclose(deg, deg_o, rtol=TOL_VEC)
+        np.testing.assert_allclose(idf, np.concatenate([oracle.idf(atac), oracle.idf(rna)]), rtol=TOL_VEC)
+        _check_against(ev_o, evec_o, evals, evecs)
     # wrapper: weights, weighted_by_sd, no write into the AnnData objects
     a1, a2 = MiniAnnData(atac), MiniAnnData(rna)
     ev_w, emb_w = tl.multi_spectral([a1, a2], n_comps=6, features=None, weights=[2.0, 1.0], engine=engine)
