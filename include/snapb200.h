@@ -183,10 +183,15 @@ int  snapb200_operator_time(snapb200_ctx* ctx, int b, int iters, int flush_l2,
  * scipy eigsh(which='LM') + argsort()[::-1] returns at embedding.rs:164-171.
  * Block Lanczos with full re-orthogonalisation and thick restart.
  * evals: k doubles.  evecs: n_local x k doubles, row-major (this rank's rows).
- * tol <= 0 selects the default (1e-5 relative residual); block 0 -> default. */
+ * tol <= 0 selects the default (1e-5 relative residual); block 0 -> default.
+ * scale_by_sqrt_eval != 0: eigenvector columns whose eigenvalue is positive are returned
+ * multiplied by sqrt(eigenvalue) -- the wrapper's weighted_by_sd step
+ * (tools/_embedding.py:286-289) folded into the final basis rotation on the device.
+ * The stats field `converged` tells whether the tolerance was met (scipy raises
+ * ArpackNoConvergence otherwise; the Python mirror does the same). */
 int  snapb200_eigsh(snapb200_ctx* ctx, int k, int64_t seed, double tol,
                     int block, int max_basis, int max_ops,
-                    double* evals, double* evecs);
+                    double* evals, double* evecs, int scale_by_sqrt_eval);
 
 int  snapb200_get_stats(snapb200_ctx* ctx, snapb200_stats* out);
 

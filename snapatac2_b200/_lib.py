@@ -84,7 +84,7 @@ def load() -> C.CDLL:
         "snapb200_project": [vp, i32, vp, i32, vp],
         "snapb200_operator_apply": [vp, vp, vp, i32],
         "snapb200_operator_time": [vp, i32, i32, i32, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(dbl)],
-        "snapb200_eigsh": [vp, i32, i64, dbl, i32, i32, i32, vp, vp],
+        "snapb200_eigsh": [vp, i32, i64, dbl, i32, i32, i32, vp, vp, i32],
         "snapb200_get_stats": [vp, C.POINTER(Stats)],
         "snapb200_get_stream": [vp, C.POINTER(vp)],
         "snapb200_set_spmm_mode": [vp, i32],

@@ -502,10 +502,10 @@ int snapb200_operator_time(snapb200_ctx* c, int b, int iters, int flush, double*
 }
 
 int snapb200_eigsh(snapb200_ctx* c, int k, int64_t seed, double tol, int block, int max_basis, int max_ops,
-                   double* evals, double* evecs) {
+                   double* evals, double* evecs, int scale_by_sqrt_eval) {
     return guarded([&] {
         bind(c);
-        eigsh(c, k, seed, tol, block > 0 ? block : c->block, max_basis, max_ops, evals, evecs);
+        eigsh(c, k, seed, tol, block > 0 ? block : c->block, max_basis, max_ops, evals, evecs, scale_by_sqrt_eval != 0);
     });
 }
 

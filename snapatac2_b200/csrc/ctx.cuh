@@ -282,7 +282,7 @@ void ensure_tiled(snapb200_ctx* c, int b);
 
 // ---- lanczos.cu
 void eigsh(snapb200_ctx* c, int k, int64_t seed, double tol, int block, int max_basis, int max_ops,
-           double* evals, double* evecs);
+           double* evals, double* evecs, bool scale_by_sqrt_eval);
 
 inline void count_launch(snapb200_ctx* c, int64_t n = 1) { c->stats.kernel_launches += n; }
 

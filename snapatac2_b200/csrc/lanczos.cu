@@ -188,7 +188,7 @@ struct Ritz {
 // switches to checking before it enqueues.
 template <int B>
 void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis, int max_ops, double* evals,
-                double* evecs) {
+                double* evecs, bool scale_by_sqrt_eval) {
     HostClock wall;
     const int64_t n = c->n_local, ng = c->n_global;
     cudaStream_t st = c->stream;
@@ -444,7 +444,10 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
     std::vector<double> Smat(static_cast<size_t>(nb) * k8, 0.0);
     for (int q = 0; q < k; ++q) {
         evals[q] = ritz.theta[sel[q]];
-        for (int a = 0; a < nv; ++a) Smat[static_cast<size_t>(ritz.idx[a]) * k8 + q] = ritz.S[static_cast<size_t>(a) * nv + sel[q]];
+        // weighted_by_sd of the wrapper (tools/_embedding.py:286-289) folded into the rotation: columns with a
+        // positive eigenvalue come out multiplied by sqrt(lambda) at no cost (the others are dropped by the caller)
+        const double sc = (scale_by_sqrt_eval && evals[q] > 0.0) ? std::sqrt(evals[q]) : 1.0;
+        for (int a = 0; a < nv; ++a) Smat[static_cast<size_t>(ritz.idx[a]) * k8 + q] = sc * ritz.S[static_cast<size_t>(a) * nv + sel[q]];
     }
     dS.ensure(static_cast<int64_t>(nb) * k8);
     SB_CUDA(cudaMemcpyAsync(dS.p, Smat.data(), sizeof(double) * Smat.size(), cudaMemcpyHostToDevice, st));
@@ -479,13 +482,13 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
 }  // namespace
 
 void eigsh(snapb200_ctx* c, int k, int64_t seed, double tol, int block, int max_basis, int max_ops, double* evals,
-           double* evecs) {
+           double* evecs, bool scale_by_sqrt_eval) {
     SB_CHECK(c->prepared, "eigsh: call prepare first");
     if (block <= 0) block = c->block;
     switch (block) {
-        case 4: eigsh_impl<4>(c, k, seed, tol, max_basis, max_ops, evals, evecs); break;
-        case 8: eigsh_impl<8>(c, k, seed, tol, max_basis, max_ops, evals, evecs); break;
-        case 16: eigsh_impl<16>(c, k, seed, tol, max_basis, max_ops, evals, evecs); break;
+        case 4: eigsh_impl<4>(c, k, seed, tol, max_basis, max_ops, evals, evecs, scale_by_sqrt_eval); break;
+        case 8: eigsh_impl<8>(c, k, seed, tol, max_basis, max_ops, evals, evecs, scale_by_sqrt_eval); break;
+        case 16: eigsh_impl<16>(c, k, seed, tol, max_basis, max_ops, evals, evecs, scale_by_sqrt_eval); break;
         default: throw Error("eigsh: block width must be 4, 8 or 16");
     }
 }

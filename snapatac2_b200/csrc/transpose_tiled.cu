@@ -26,6 +26,7 @@
 // to CTAs depends on timing, never the output).
 #include "ctx.cuh"
 
+#include <stdlib.h>
 #include <algorithm>
 #include <vector>
 
@@ -356,6 +357,336 @@ tile_vals_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
     }
 }
 
+// ==========================================================================
+// Bucketed transpose (default; m <= kTrF * kTrMaxBuckets features).
+//
+// The emit kernel above walks the CSR rows of a cell tile once per 1024-feature range and finds
+// ~10 entries per (row, range): one thread per row with a handful of entries each, then one thread
+// per feature over a 1024 x 1024 bitmap that is 1 % full -- a few active lanes per warp on both
+// sides (ncu: IPC 1.3).  Here every pass over the entries is entry-parallel and coalesced:
+//   A1  rowcnt[r][k]   entries of row r in feature bucket k (kTrF features): one warp streams a
+//                      row, 128 contiguous bytes per load; rows are sorted, so a bucket is a run;
+//   A2  rowoff[r][k]   exclusive prefix of rowcnt over the rows of r's cell tile, bucket totals;
+//   A3  scatter        the same streaming walk as A1 writes every entry, as (feature in bucket,
+//                      tile-local cell), to  tmp[tile][bucket][rowoff + position in the run] -- the
+//                      tile's entries grouped by bucket, each bucket still in row order; runs of
+//                      consecutive rows are adjacent in the output, so the stores merge in L2;
+//   B   per (tile, bucket): a stable counting sort of the bucket's ~125k entries by feature
+//       (per-warp counters in shared memory over consecutive slices, ranks inside a 32-entry
+//       batch by match.any): segment lengths, offsets and the 16-bit ids of the TileT layout.
+// All positions come from prefix sums: no atomics on data, the result does not depend on timing.
+// A tile's buckets get regions padded for the worst case (7 slots per feature), so no pass has
+// to know the exact padded segment lengths of earlier buckets.
+// ==========================================================================
+constexpr int kTrLog = 10;
+constexpr int kTrF = 1 << kTrLog;          // features per bucket
+constexpr int kTrMaxBuckets = 2048;        // per-warp run counters of A1 / A3 (4 KB each)
+constexpr int kTrWarps = 16;               // warps per CTA in A1 / A3
+
+// one row, streamed by one warp: run lengths per bucket, optionally the scatter
+template <bool SCATTER>
+__device__ __forceinline__ void tr_walk_row(const int32_t* __restrict__ idx, int64_t rs, int64_t re, uint16_t* pos,
+                                            const uint32_t* __restrict__ roff, const int64_t* __restrict__ tbase,
+                                            uint32_t* __restrict__ tmp, uint32_t r_local, int lane) {
+    for (int64_t p0 = rs; p0 < re; p0 += 128) {
+        int j[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t p = p0 + 32 * u + lane;
+            j[u] = (p < re) ? ld_stream_int(idx + p) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool valid = j[u] >= 0;
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            if (vmask == 0u) break;
+            const int k = valid ? (j[u] >> kTrLog) : -1;
+            const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
+            const bool head = valid && (lane == 0 || k != kprev);
+            const unsigned hmask = __ballot_sync(0xffffffffu, head);
+            const int nvalid = __popc(vmask);
+            // the run this lane heads ends at the next head (or at the end of the batch)
+            const unsigned above = hmask & ~((2u << lane) - 1u);
+            const int end = above ? (__ffs(above) - 1) : nvalid;
+            uint32_t off = 0;
+            if (head) {
+                const uint32_t done = pos[k];           // entries of this bucket already seen in this row
+                pos[k] = static_cast<uint16_t>(done + (end - lane));
+                if (SCATTER) off = roff[k] + done;
+            }
+            if (SCATTER) {
+                const int h = 31 - __clz(hmask & ((2u << lane) - 1u));   // my run's head lane
+                const uint32_t base = __shfl_sync(0xffffffffu, off, h);
+                if (valid)
+                    tmp[tbase[k] + base + (lane - h)] = (static_cast<uint32_t>(j[u] & (kTrF - 1)) << 14) | r_local;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// A1: grid-stride over rows in order (one warp per row)
+__global__ void __launch_bounds__(kTrWarps * 32)
+tr_rowcnt_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int NBp,
+                 uint16_t* __restrict__ rowcnt) {
+    extern __shared__ __align__(16) uint16_t tr_pos[];   // kTrWarps x NBp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t* pos = tr_pos + static_cast<size_t>(warp) * NBp;
+    for (int i = lane; i < NBp; i += 32) pos[i] = 0;
+    __syncwarp();
+    const int64_t nw = static_cast<int64_t>(gridDim.x) * kTrWarps;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * kTrWarps + warp; r < n; r += nw) {
+        tr_walk_row<false>(idx, ptr[r], ptr[r + 1], pos, nullptr, nullptr, nullptr, 0u, lane);
+        __syncwarp();
+        uint16_t* out = rowcnt + r * NBp;
+        for (int i = lane; i < NBp; i += 32) {
+            out[i] = pos[i];
+            pos[i] = 0;
+        }
+        __syncwarp();
+    }
+}
+
+// A2: one CTA per (cell tile, group of 32 buckets): exclusive prefix over the tile's rows
+__global__ void __launch_bounds__(1024)
+tr_rowscan_kernel(const uint16_t* __restrict__ rowcnt, int64_t n, int H, int NBp, uint32_t* __restrict__ rowoff,
+                  int64_t* __restrict__ btot) {
+    __shared__ uint32_t wsum[32][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int groups = NBp / 32;
+    const int64_t t = blockIdx.x / groups;
+    const int g = blockIdx.x % groups;
+    const int64_t r_lo = t * H;
+    const int nr = static_cast<int>(min(static_cast<int64_t>(H), n - r_lo));
+    const int per = (nr + 31) / 32;
+    const int a = min(nr, warp * per), b = min(nr, a + per);
+    const uint16_t* src = rowcnt + r_lo * NBp + g * 32 + lane;
+    uint32_t s = 0;
+    for (int r = a; r < b; ++r) s += src[static_cast<int64_t>(r) * NBp];
+    wsum[warp][lane] = s;
+    __syncthreads();
+    uint32_t run = 0;
+    for (int w = 0; w < warp; ++w) run += wsum[w][lane];
+    if (warp == 31) btot[t * NBp + g * 32 + lane] = static_cast<int64_t>(run + s);
+    uint32_t* dst = rowoff + r_lo * NBp + g * 32 + lane;
+    for (int r = a; r < b; ++r) {
+        dst[static_cast<int64_t>(r) * NBp] = run;
+        run += src[static_cast<int64_t>(r) * NBp];
+    }
+}
+
+// A3
+__global__ void __launch_bounds__(kTrWarps * 32)
+tr_scatter_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int H, int NBp,
+                  const uint32_t* __restrict__ rowoff, const int64_t* __restrict__ tmp_base, uint32_t* __restrict__ tmp) {
+    extern __shared__ __align__(16) uint16_t tr_pos[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t* pos = tr_pos + static_cast<size_t>(warp) * NBp;
+    for (int i = lane; i < NBp; i += 32) pos[i] = 0;
+    __syncwarp();
+    const int64_t nw = static_cast<int64_t>(gridDim.x) * kTrWarps;
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * kTrWarps + warp; r < n; r += nw) {
+        const int64_t t = r / H;
+        tr_walk_row<true>(idx, ptr[r], ptr[r + 1], pos, rowoff + r * NBp, tmp_base + t * NBp, tmp,
+                          static_cast<uint32_t>(r - t * H), lane);
+        __syncwarp();
+        for (int i = lane; i < NBp; i += 32) pos[i] = 0;
+        __syncwarp();
+    }
+}
+
+// B: one unit = (cell tile, bucket); persistent CTAs pull units from a counter
+__global__ void __launch_bounds__(1024, 1)
+tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restrict__ tmp_base, const int64_t* __restrict__ btot,
+                      const uint32_t* __restrict__ ureg, const int64_t* __restrict__ tile_base, int64_t m, int NB, int NBp,
+                      int64_t n_units, uint16_t* __restrict__ cnt, uint32_t* __restrict__ segoff,
+                      uint16_t* __restrict__ ids, unsigned long long* __restrict__ counter) {
+    extern __shared__ __align__(16) uint16_t cw[];      // 32 warps x kTrF counters, then running offsets
+    __shared__ uint32_t segstart[kTrF];
+    __shared__ uint32_t wsum[32];
+    __shared__ long long s_unit;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint16_t* mine = cw + static_cast<size_t>(warp) * kTrF;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_unit = static_cast<long long>(atomicAdd(counter, 1ull));
+        __syncthreads();
+        const int64_t u = s_unit;
+        if (u >= n_units) break;
+        const int64_t t = u / NB;
+        const int k = static_cast<int>(u - t * NB);
+        const int64_t E = btot[t * NBp + k];
+        const uint32_t* in = tmp + tmp_base[t * NBp + k];
+        const int64_t f0 = static_cast<int64_t>(k) << kTrLog;
+        const int nf = static_cast<int>(min(static_cast<int64_t>(kTrF), m - f0));
+        for (int i = tid; i < 32 * kTrF / 2; i += 1024) reinterpret_cast<uint32_t*>(cw)[i] = 0u;
+        __syncthreads();
+        // ---- counts per (warp slice, feature); slices are consecutive, so slice order = row order
+        const int64_t per = ((E + 31) / 32 + 31) / 32 * 32;
+        const int64_t a = min(E, warp * per), b = min(E, a + per);
+        for (int64_t p0 = a; p0 < b; p0 += 32) {
+            const int64_t p = p0 + lane;
+            const bool valid = p < b;
+            const uint32_t e = valid ? in[p] : 0xFFFFFFFFu;
+            const uint32_t f = e >> 14;                      // an invalid lane gets a key no feature has
+            const unsigned same = __match_any_sync(0xffffffffu, f);
+            if (valid && lane == __ffs(same) - 1) mine[f] = static_cast<uint16_t>(mine[f] + __popc(same));
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- per feature: exclusive prefix over the warps, segment length, padded exclusive scan
+        {
+            uint32_t total = 0;
+            if (tid < nf) {
+                for (int w = 0; w < 32; ++w) {
+                    const uint16_t c0 = cw[static_cast<size_t>(w) * kTrF + tid];
+                    cw[static_cast<size_t>(w) * kTrF + tid] = static_cast<uint16_t>(total);
+                    total += c0;
+                }
+                cnt[t * m + f0 + tid] = static_cast<uint16_t>(total);
+            }
+            const uint32_t v = (total + 7u) & ~7u;
+            uint32_t x = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            if (lane == 31) wsum[warp] = x;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t w = wsum[lane];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+                    if (lane >= d) w += y;
+                }
+                wsum[lane] = w;
+            }
+            __syncthreads();
+            const uint32_t excl = ureg[t * NBp + k] + (warp > 0 ? wsum[warp - 1] : 0u) + (x - v);
+            segstart[tid] = excl;
+            if (tid < nf) segoff[t * m + f0 + tid] = excl;
+        }
+        __syncthreads();
+        // ---- stable scatter
+        uint16_t* out = ids + tile_base[t];
+        for (int64_t p0 = a; p0 < b; p0 += 32) {
+            const int64_t p = p0 + lane;
+            const bool valid = p < b;
+            const uint32_t e = valid ? in[p] : 0xFFFFFFFFu;
+            const uint32_t f = e >> 14;
+            const unsigned same = __match_any_sync(0xffffffffu, f);
+            const int leader = __ffs(same) - 1;
+            uint32_t base = 0;
+            if (valid && lane == leader) {
+                base = mine[f];
+                mine[f] = static_cast<uint16_t>(base + __popc(same));
+            }
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (valid) out[segstart[f] + base + __popc(same & ((1u << lane) - 1u))] = static_cast<uint16_t>(e & 0x3FFFu);
+            __syncwarp();
+        }
+    }
+}
+
+static void transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
+    const Csr& X = c->X;
+    TileT& T = c->XtT;
+    cudaStream_t st = c->stream;
+    const int64_t n = X.nrows, m = c->m;
+    const int nt = T.n_tiles;
+    const int NB = static_cast<int>(ceil_div(m, kTrF));
+    const int NBp = (NB + 31) / 32 * 32;
+    DevBuf<uint16_t> rowcnt;
+    DevBuf<uint32_t> rowoff, ureg, tmp;
+    DevBuf<int64_t> btot, tmp_base;
+    DevBuf<unsigned long long> counter;
+    rowcnt.alloc(std::max<int64_t>(1, n * NBp));
+    rowoff.alloc(std::max<int64_t>(1, n * NBp));
+    btot.alloc(static_cast<int64_t>(nt) * NBp);
+    tmp_base.alloc(static_cast<int64_t>(nt) * NBp);
+    ureg.alloc(static_cast<int64_t>(nt) * NBp);
+    counter.alloc(1);
+    SB_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+    SB_CUDA(cudaMemsetAsync(btot.p, 0, sizeof(int64_t) * nt * NBp, st));
+    const size_t smem_walk = static_cast<size_t>(kTrWarps) * NBp * sizeof(uint16_t);
+    static_assert(kTrF == 1024, "tr_bucket_sort_kernel scans one feature per thread of a 1024-thread CTA");
+    // A1 only reads: as many resident warps as fit.  A3 also scatters: the rows in flight bound the
+    // output windows that must stay in L2 until their sectors are complete (rows x ~40 B x buckets),
+    // so it runs with half the warps.
+    int cta_per_sm_a1 = 4, cta_per_sm_a3 = 2;
+    if (const char* e = getenv("SNAPB200_TR_CTAS")) cta_per_sm_a3 = std::max(1, atoi(e));
+    const int walk_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kTrWarps), c->num_sms * cta_per_sm_a1)));
+    const int scat_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kTrWarps), c->num_sms * cta_per_sm_a3)));
+    if (n > 0) {
+        SB_CUDA(cudaFuncSetAttribute(tr_rowcnt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_walk)));
+        tr_rowcnt_kernel<<<walk_grid, kTrWarps * 32, smem_walk, st>>>(X.ptr.p, X.idx.p, n, NBp, rowcnt.p);
+        SB_LAUNCH_CHECK();
+        tr_rowscan_kernel<<<static_cast<unsigned>(static_cast<int64_t>(nt) * (NBp / 32)), 1024, 0, st>>>(rowcnt.p, n, tile_rows, NBp,
+                                                                                                      rowoff.p, btot.p);
+        SB_LAUNCH_CHECK();
+    }
+    // ---- bucket bases (host: nt x NB numbers): exact offsets into tmp, worst-case padded regions of the output
+    std::vector<int64_t> hb(static_cast<size_t>(nt) * NBp), htb(static_cast<size_t>(nt) * NBp), tb(nt + 1);
+    std::vector<uint32_t> hureg(static_cast<size_t>(nt) * NBp);
+    SB_CUDA(cudaMemcpyAsync(hb.data(), btot.p, sizeof(int64_t) * hb.size(), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    int64_t run_tmp = 0, counted = 0;
+    tb[0] = 0;
+    for (int t = 0; t < nt; ++t) {
+        int64_t reg = 0;
+        for (int k = 0; k < NBp; ++k) {
+            const int64_t e = hb[static_cast<size_t>(t) * NBp + k];
+            htb[static_cast<size_t>(t) * NBp + k] = run_tmp;
+            hureg[static_cast<size_t>(t) * NBp + k] = static_cast<uint32_t>(reg);
+            run_tmp += e;
+            counted += e;
+            if (k < NB) {
+                const int64_t nf = std::min<int64_t>(kTrF, m - static_cast<int64_t>(k) * kTrF);
+                reg += (e + 7 * std::min<int64_t>(nf, e) + 7) / 8 * 8;   // every non-empty segment pads by at most 7
+            }
+        }
+        SB_CHECK(reg < (1ll << 32), "transpose_tiled: more than 2^32 slots in one cell tile");
+        tb[t + 1] = tb[t] + reg;
+    }
+    SB_CHECK(counted == X.nnz, "transpose_tiled: count mismatch (column index out of range or unsorted rows?)");
+    SB_CUDA(cudaMemcpyAsync(tmp_base.p, htb.data(), sizeof(int64_t) * htb.size(), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(ureg.p, hureg.data(), sizeof(uint32_t) * hureg.size(), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(T.tile_base.p, tb.data(), sizeof(int64_t) * (nt + 1), cudaMemcpyHostToDevice, st));
+    T.ids.alloc(tb[nt] + 8);
+    tmp.alloc(std::max<int64_t>(1, X.nnz));
+    if (n > 0 && X.nnz > 0) {
+        SB_CUDA(cudaFuncSetAttribute(tr_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_walk)));
+        tr_scatter_kernel<<<scat_grid, kTrWarps * 32, smem_walk, st>>>(X.ptr.p, X.idx.p, n, tile_rows, NBp, rowoff.p, tmp_base.p, tmp.p);
+        SB_LAUNCH_CHECK();
+    }
+    {
+        const int64_t n_units = static_cast<int64_t>(nt) * NB;
+        const size_t smem = static_cast<size_t>(32) * kTrF * sizeof(uint16_t);
+        SB_CUDA(cudaFuncSetAttribute(tr_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const int grid = static_cast<int>(std::min<int64_t>(n_units, c->num_sms));
+        tr_bucket_sort_kernel<<<grid, 1024, smem, st>>>(tmp.p, tmp_base.p, btot.p, ureg.p, T.tile_base.p, m, NB, NBp, n_units,
+                                                        T.cnt.p, T.segoff.p, T.ids.p, counter.p);
+        SB_LAUNCH_CHECK();
+    }
+    if (df_local) {
+        tile_df_kernel<<<static_cast<unsigned>(ceil_div(m, 256)), 256, 0, st>>>(T.cnt.p, m, nt, df_local);
+        SB_LAUNCH_CHECK();
+    }
+    if (X.has_values() && X.nnz > 0) {
+        T.vals.alloc(tb[nt] + 8);
+        const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(static_cast<int64_t>(nt) * m, 8),
+                                                              static_cast<int64_t>(c->num_sms) * 16));
+        tile_vals_kernel<<<blocks, 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, m, tile_rows, nt, T.cnt.p, T.segoff.p,
+                                                 T.tile_base.p, T.ids.p, T.vals.p);
+        SB_LAUNCH_CHECK();
+    }
+    count_launch(c, 6);
+    SB_CUDA(cudaStreamSynchronize(st));   // host tables and temporaries stay alive until everything ran
+    T.built = true;
+}
+
 }  // namespace
 
 void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
@@ -373,6 +704,12 @@ void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
     T.cnt.alloc(static_cast<int64_t>(nt) * m);
     T.segoff.alloc(static_cast<int64_t>(nt) * m);
     T.tile_base.alloc(nt + 1);
+    const char* lg = getenv("SNAPB200_TRANSPOSE_LEGACY");
+    const bool legacy = lg != nullptr && lg[0] == '1';
+    if (!legacy && ceil_div(m, kTrF) <= kTrMaxBuckets && tile_rows <= (1 << 14)) {
+        transpose_bucketed(c, tile_rows, df_local);
+        return;
+    }
     DevBuf<unsigned long long> counter;
     DevBuf<int64_t> totals;
     counter.alloc(2);

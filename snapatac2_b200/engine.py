@@ -237,11 +237,12 @@ class Engine:
                                                     C.byref(p1), C.byref(cm), C.byref(p2)))
         return p1.value, cm.value, p2.value
 
-    def eigsh(self, k, seed=0, tol=0.0, block=0, max_basis=0, max_ops=0, out_evecs=None):
+    def eigsh(self, k, seed=0, tol=0.0, block=0, max_basis=0, max_ops=0, out_evecs=None, scale_by_sqrt_eval=False):
         evals = np.empty(k, dtype=np.float64)
         evecs = np.empty((self.n_local, k), dtype=np.float64) if out_evecs is None else out_evecs
         _lib.check(self._lib.snapb200_eigsh(self._ctx, int(k), int(seed), float(tol), int(block),
-                                            int(max_basis), int(max_ops), _lib.ptr(evals), _lib.ptr(evecs)))
+                                            int(max_basis), int(max_ops), _lib.ptr(evals), _lib.ptr(evecs),
+                                            1 if scale_by_sqrt_eval else 0))
         st = self.stats()
         if not st["converged"]:
             # scipy's eigsh, which the reference calls (embedding.rs:166-167), raises here as well

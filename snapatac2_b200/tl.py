@@ -103,9 +103,10 @@ def _get_csr(adata):
 
 def spectral_embedding(engine: Engine, X, selected_features, n_components, random_state,
                        feature_weights=None, *, n_global=None, row0=0, binarized=None,
-                       tol=0.0, block=0, max_basis=0, max_ops=0, return_parts=False):
+                       tol=0.0, block=0, max_basis=0, max_ops=0, return_parts=False, scale_by_sqrt_eval=False):
     """Counterpart of the PyO3 entry ``internal.spectral_embedding``
-    (embedding.rs:24-59): load -> [select] -> [weights] -> prepare -> eigsh."""
+    (embedding.rs:24-59): load -> [select] -> [weights] -> prepare -> eigsh.
+    ``scale_by_sqrt_eval``: see :func:`_weight_by_sd`."""
     mask, fw = _feature_mask(selected_features, X.shape[1], feature_weights)
     engine.load_csr(X, n_global=n_global, row0=row0, binarized=binarized)
     if mask is not None:
@@ -113,10 +114,22 @@ def spectral_embedding(engine: Engine, X, selected_features, n_components, rando
     engine.set_feature_weights(fw)
     idf, degree = engine.prepare(want_outputs=return_parts)
     evals, evecs = engine.eigsh(n_components, seed=random_state, tol=tol, block=block,
-                                max_basis=max_basis, max_ops=max_ops)
+                                max_basis=max_basis, max_ops=max_ops, scale_by_sqrt_eval=scale_by_sqrt_eval)
     if return_parts:
         return evals, evecs, idf, degree
     return evals, evecs
+
+
+def _weight_by_sd(evals, evecs, already_scaled):
+    """``weighted_by_sd`` (tools/_embedding.py:286-289): keep the components with a positive eigenvalue,
+    scaled by ``sqrt(eigenvalue)``.  On the full-matrix path the scaling is folded into the final basis
+    rotation on the device (``already_scaled``), so a 1M x 30 result is not copied twice more on the host."""
+    keep = evals > 0
+    if not already_scaled:
+        evecs = evecs[:, keep] * np.sqrt(evals[keep])
+    elif not keep.all():
+        evecs = np.ascontiguousarray(evecs[:, keep])
+    return evals[keep], evecs
 
 
 def orthogonalize(evals, evecs):
@@ -305,15 +318,16 @@ def spectral(
         v, u = spectral_embedding_nystrom(eng, X, features, n_comps, sample_size, sample_method != "random",
                                           chunk_size, tol=tol, block=block)
         evals, evecs = orthogonalize(v, u)
+        scaled = False
     else:
         evals, evecs = spectral_embedding(eng, X, features, n_comps, random_state, feature_weights,
-                                          n_global=n_global, row0=row0, tol=tol, block=block)   # :249
+                                          n_global=n_global, row0=row0, tol=tol, block=block,
+                                          scale_by_sqrt_eval=weighted_by_sd)                     # :249
+        scaled = weighted_by_sd
     logging.getLogger(__name__).info("spectral: %s", eng.stats())
 
     if weighted_by_sd:                                              # :286-289
-        idx = [i for i in range(evals.shape[0]) if evals[i] > 0]
-        evals = evals[idx]
-        evecs = evecs[:, idx] * np.sqrt(evals)
+        evals, evecs = _weight_by_sd(evals, evecs, scaled)
 
     if inplace:                                                     # :291-293
         adata.uns["spectral_eigenvalue"] = evals
@@ -336,7 +350,8 @@ def _view_engines(engine: Engine, n_views: int) -> list[Engine]:
 
 
 def multi_spectral_embedding(engine: Engine, xs, selected_features, weights, n_components, random_state,
-                             *, sample_rows=None, tol=0.0, block=0, return_parts=False, container="csr_matrix"):
+                             *, sample_rows=None, tol=0.0, block=0, return_parts=False, container="csr_matrix",
+                             scale_by_sqrt_eval=False):
     """Counterpart of ``internal.multi_spectral_embedding`` (embedding.rs:388-452), entirely on the
     device and without the column concatenation ever being formed.
 
@@ -399,7 +414,7 @@ def multi_spectral_embedding(engine: Engine, xs, selected_features, weights, n_c
     w_sum = float(sum(ws))
     scales = [float(np.sqrt(w / w_sum)) for w in ws]
     degree = engine.combine_views(views, scales, want_degree=return_parts)
-    evals, evecs = engine.eigsh(n_components, seed=random_state, tol=tol, block=block)
+    evals, evecs = engine.eigsh(n_components, seed=random_state, tol=tol, block=block, scale_by_sqrt_eval=scale_by_sqrt_eval)
     if return_parts:
         return evals, evecs, np.concatenate(idfs), degree, norms
     return evals, evecs
@@ -421,9 +436,8 @@ def multi_spectral(adatas, n_comps: int = 30, features="selected", weights=None,
     # (no n_comps clamp here: the reference's multi_spectral has none, :523-533)
     eng = _check_engine(engine) if engine is not None else default_engine()
     evals, evecs = multi_spectral_embedding(eng, [_get_csr(a) for a in adatas], features, weights,
-                                            n_comps, random_state, sample_rows=sample_rows, container=container)   # :533
+                                            n_comps, random_state, sample_rows=sample_rows, container=container,
+                                            scale_by_sqrt_eval=weighted_by_sd)                # :533
     if weighted_by_sd:                                                      # :535-538
-        idx = [i for i in range(evals.shape[0]) if evals[i] > 0]
-        evals = evals[idx]
-        evecs = evecs[:, idx] * np.sqrt(evals)
+        evals, evecs = _weight_by_sd(evals, evecs, True)
     return evals, evecs

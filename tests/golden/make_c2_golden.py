@@ -25,12 +25,19 @@ from snapatac2_b200 import synth  # noqa: E402
 OUT = Path(__file__).resolve().parent
 
 
+def _gen(a):
+    n, m, nnz_row, K, r0, r1 = a
+    return synth.generate_csr(synth.make_spec(n, m, nnz_row, K, seed=0), r0, r1, dtype=np.float64)
+
+
 def main():
     n, m, nnz_row, K, k = 100_000, 500_000, 5_000, 48, 30
     spec = synth.make_spec(n, m, nnz_row, K, seed=0)
     t0 = time.time()
-    parts = [synth.generate_csr(spec, r0, min(5000, n - r0), dtype=np.float64) for r0 in range(0, n, 5000)]
+    from concurrent.futures import ProcessPoolExecutor
     import scipy.sparse as sp
+    with ProcessPoolExecutor(max_workers=6) as ex:
+        parts = list(ex.map(_gen, [(n, m, nnz_row, K, r0, min(n, r0 + 2500)) for r0 in range(0, n, 2500)]))
     X = sp.vstack(parts, format="csr")
     del parts
     print(f"generated {X.shape} nnz={X.nnz} in {time.time() - t0:.0f} s", flush=True)

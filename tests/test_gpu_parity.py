@@ -146,6 +146,27 @@ def test_config1_parity_against_oracle(engine):
         assert st["n_ops"] < 60 and st["max_residual"] < 1e-6
 
 
+def test_config2_parity_against_oracle(engine):
+    """BASELINE.json configs[1]: 100k cells x 500k bins, ~5k nnz/cell, n_comps=30 (4.9e8 stored entries; the
+    production kernels: bucketed transpose, tiled SpMM).  The oracle side ran on a CPU box for six minutes
+    (tests/golden/make_c2_golden.py, 78 ARPACK mat-vecs); the fixture keeps the eigenvalues, every 5th degree,
+    every 25th IDF weight and the eigenvector rows of 4000 sampled cells."""
+    from conftest import GOLDEN
+    z = np.load(GOLDEN / "c2_100kx500k.npz")
+    spec = synth.make_spec(100_000, 500_000, 5_000, n_clusters=48, seed=0)
+    engine.generate(spec)
+    assert engine.shape()[2] == int(z["nnz"])
+    engine.set_feature_weights(None)
+    idf, deg = engine.prepare()
+    np.testing.assert_allclose(idf[::25], z["idf_25"], rtol=TOL_VEC)
+    np.testing.assert_allclose(deg[::5], z["degree_5"], rtol=TOL_VEC)
+    evals, evecs = engine.eigsh(30, seed=0)
+    assert engine.stats()["spmm_tiled"] == 1
+    np.testing.assert_allclose(evals, z["evals"], rtol=TOL_EVAL)
+    cos = eigvec_agreement(z["evals"], z["evecs_rows"], evecs[z["rows"]])
+    assert cos.min() >= MIN_COS, cos
+
+
 def test_thick_restart_small_basis(engine):
     X, z = load_golden("tile_600x4000")
     engine.load_csr(X)

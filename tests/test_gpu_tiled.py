@@ -165,3 +165,29 @@ def test_projection_products_tiled_and_csr(engine, valued, block):
     finally:
         engine.set_spmm_mode("auto")
         engine.set_block(4)
+
+
+def test_bucketed_transpose_equals_legacy_bitmap_transpose(engine, monkeypatch):
+    """The bucketed transpose (row-run tables + per-bucket counting sort) and the first version
+    (shared-memory bitmap per 1024 x 1024 block) must produce the same feature-major copy: segments
+    in ascending cell order, hence bitwise identical operator results -- binarised and valued,
+    ragged rows, a shard that is not a multiple of the tile height."""
+    rng = np.random.default_rng(5)
+    for n, m, nnz_row, valued in ((13000, 70000, 400, False), (2500, 3000, 200, True), (300, 1500, 40, False)):
+        spec = synth.make_spec(n, m, nnz_row, n_clusters=12, seed=n)
+        X = synth.generate_csr(spec, dtype=np.float32)
+        if valued:
+            X.data = rng.integers(1, 6, size=X.nnz).astype(np.float32)
+        V = rng.standard_normal((n, 4)).astype(np.float32)
+        outs = []
+        for legacy in ("1", "0"):
+            monkeypatch.setenv("SNAPB200_TRANSPOSE_LEGACY", legacy)
+            engine.set_spmm_mode("tiled")
+            engine.load_csr(X)
+            engine.set_feature_weights(None)
+            idf, deg = engine.prepare()
+            outs.append((idf, deg, engine.operator_apply(V)))
+        engine.set_spmm_mode("auto")
+        np.testing.assert_array_equal(outs[0][0], outs[1][0])
+        np.testing.assert_array_equal(outs[0][1], outs[1][1])
+        np.testing.assert_array_equal(outs[0][2], outs[1][2])
