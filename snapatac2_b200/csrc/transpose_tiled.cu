@@ -358,7 +358,7 @@ tile_vals_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
 }
 
 // ==========================================================================
-// Bucketed transpose (default; m <= kTrF * kTrMaxBuckets features).
+// Bucketed transpose (opt-in: SNAPB200_TRANSPOSE=bucketed; m <= kTrF * kTrMaxBuckets features).
 //
 // The emit kernel above walks the CSR rows of a cell tile once per 1024-feature range and finds
 // ~10 entries per (row, range): one thread per row with a handful of entries each, then one thread
@@ -383,52 +383,20 @@ constexpr int kTrF = 1 << kTrLog;          // features per bucket
 constexpr int kTrMaxBuckets = 2048;        // per-warp run counters of A1 / A3 (4 KB each)
 constexpr int kTrWarps = 16;               // warps per CTA in A1 / A3
 
-// one row, streamed by one warp: run lengths per bucket, optionally the scatter
-template <bool SCATTER>
-__device__ __forceinline__ void tr_walk_row(const int32_t* __restrict__ idx, int64_t rs, int64_t re, uint16_t* pos,
-                                            const uint32_t* __restrict__ roff, const int64_t* __restrict__ tbase,
-                                            uint32_t* __restrict__ tmp, uint32_t r_local, int lane) {
-    for (int64_t p0 = rs; p0 < re; p0 += 128) {
-        int j[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t p = p0 + 32 * u + lane;
-            j[u] = (p < re) ? ld_stream_int(idx + p) : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const bool valid = j[u] >= 0;
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-            if (vmask == 0u) break;
-            const int k = valid ? (j[u] >> kTrLog) : -1;
-            const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
-            const bool head = valid && (lane == 0 || k != kprev);
-            const unsigned hmask = __ballot_sync(0xffffffffu, head);
-            const int nvalid = __popc(vmask);
-            // the run this lane heads ends at the next head (or at the end of the batch)
-            const unsigned above = hmask & ~((2u << lane) - 1u);
-            const int end = above ? (__ffs(above) - 1) : nvalid;
-            uint32_t off = 0;
-            if (head) {
-                const uint32_t done = pos[k];           // entries of this bucket already seen in this row
-                pos[k] = static_cast<uint16_t>(done + (end - lane));
-                if (SCATTER) off = roff[k] + done;
-            }
-            if (SCATTER) {
-                const int h = 31 - __clz(hmask & ((2u << lane) - 1u));   // my run's head lane
-                const uint32_t base = __shfl_sync(0xffffffffu, off, h);
-                if (valid)
-                    tmp[tbase[k] + base + (lane - h)] = (static_cast<uint32_t>(j[u] & (kTrF - 1)) << 14) | r_local;
-            }
-            __syncwarp();
-        }
-    }
+// A row is cut into kTrGroup shares of a multiple of 32 entries (the scatter pass hands every share
+// to its own warp).  share_len is that multiple for a row of `len` entries.
+constexpr int kTrGroup = 8;
+__device__ __forceinline__ int64_t tr_share_len(int64_t len) {
+    return ((len + kTrGroup - 1) / kTrGroup + 31) / 32 * 32;
 }
 
-// A1: grid-stride over rows in order (one warp per row)
+// A1: one warp streams a row (128 contiguous bytes per load, four loads in flight): run lengths per
+// bucket in a per-warp table.  For every share boundary it also records what the scatter pass
+// needs to start there: the bucket of the first entry and how many entries of that bucket's run
+// lie before the boundary (carry = bucket << 16 | count).
 __global__ void __launch_bounds__(kTrWarps * 32)
 tr_rowcnt_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int NBp,
-                 uint16_t* __restrict__ rowcnt) {
+                 uint16_t* __restrict__ rowcnt, uint32_t* __restrict__ carrytab) {
     extern __shared__ __align__(16) uint16_t tr_pos[];   // kTrWarps x NBp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t* pos = tr_pos + static_cast<size_t>(warp) * NBp;
@@ -436,7 +404,39 @@ tr_rowcnt_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
     __syncwarp();
     const int64_t nw = static_cast<int64_t>(gridDim.x) * kTrWarps;
     for (int64_t r = static_cast<int64_t>(blockIdx.x) * kTrWarps + warp; r < n; r += nw) {
-        tr_walk_row<false>(idx, ptr[r], ptr[r + 1], pos, nullptr, nullptr, nullptr, 0u, lane);
+        const int64_t rs = ptr[r], re = ptr[r + 1];
+        const int64_t share = tr_share_len(re - rs);
+        int64_t next_cut = rs + share;
+        int cut = 1;
+        for (int64_t p0 = rs; p0 < re; p0 += 128) {
+            int j[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t p = p0 + 32 * u + lane;
+                j[u] = (p < re) ? ld_stream_int(idx + p) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool valid = j[u] >= 0;
+                const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                if (vmask == 0u) break;
+                const int k = valid ? (j[u] >> kTrLog) : -1;
+                if (p0 + 32 * u == next_cut) {          // a share of the scatter pass starts with this batch
+                    if (lane == 0) carrytab[r * kTrGroup + cut] = (static_cast<uint32_t>(k) << 16) | pos[k];
+                    next_cut += share;
+                    ++cut;
+                }
+                const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
+                const bool head = valid && (lane == 0 || k != kprev);
+                const unsigned hmask = __ballot_sync(0xffffffffu, head);
+                const int nvalid = __popc(vmask);
+                // the run this lane heads ends at the next head (or at the end of the batch)
+                const unsigned above = hmask & ~((2u << lane) - 1u);
+                const int end = above ? (__ffs(above) - 1) : nvalid;
+                if (head) pos[k] = static_cast<uint16_t>(pos[k] + (end - lane));
+                __syncwarp();
+            }
+        }
         __syncwarp();
         uint16_t* out = rowcnt + r * NBp;
         for (int i = lane; i < NBp; i += 32) {
@@ -475,38 +475,106 @@ tr_rowscan_kernel(const uint16_t* __restrict__ rowcnt, int64_t n, int H, int NBp
     }
 }
 
-// A3
+// A3: one warp per (row, share) -- the shares of a row go to consecutive warps, so the rows in
+// flight (and with them the output windows that must stay in L2 until their 32-byte sectors are
+// complete) are kTrGroup times fewer than with a warp per row, and no warp waits for another.
+// The warp stages the destinations of the buckets its share touches (a contiguous range, rows are
+// sorted): bucket start inside the tile's tmp region + entries of earlier rows; the part of the
+// first bucket's run that lies before the share comes from A1's carry table.  A run that
+// continues from the previous batch is always the first of the batch, so its length so far travels
+// in two registers.
 __global__ void __launch_bounds__(kTrWarps * 32)
 tr_scatter_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int H, int NBp,
-                  const uint32_t* __restrict__ rowoff, const int64_t* __restrict__ tmp_base, uint32_t* __restrict__ tmp) {
-    extern __shared__ __align__(16) uint16_t tr_pos[];
+                  const uint32_t* __restrict__ rowoff, const uint32_t* __restrict__ trel, const int64_t* __restrict__ tile_tmp0,
+                  const uint32_t* __restrict__ carrytab, uint32_t* __restrict__ tmp_all) {
+    extern __shared__ __align__(16) uint32_t tr_dst[];   // kTrWarps x NBp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint16_t* pos = tr_pos + static_cast<size_t>(warp) * NBp;
-    for (int i = lane; i < NBp; i += 32) pos[i] = 0;
-    __syncwarp();
-    const int64_t nw = static_cast<int64_t>(gridDim.x) * kTrWarps;
-    for (int64_t r = static_cast<int64_t>(blockIdx.x) * kTrWarps + warp; r < n; r += nw) {
+    uint32_t* dst0 = tr_dst + static_cast<size_t>(warp) * NBp;
+    const int64_t n_items = n * kTrGroup;
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * kTrWarps;
+    for (int64_t item = static_cast<int64_t>(blockIdx.x) * kTrWarps + warp; item < n_items; item += stride) {
+        const int64_t r = item / kTrGroup;
+        const int wg = static_cast<int>(item - r * kTrGroup);
+        const int64_t rs = ptr[r], re = ptr[r + 1];
+        const int64_t share = tr_share_len(re - rs);
+        const int64_t cs = rs + wg * share;
+        if (cs >= re) continue;
+        const int64_t ce = min(re, cs + share);
         const int64_t t = r / H;
-        tr_walk_row<true>(idx, ptr[r], ptr[r + 1], pos, rowoff + r * NBp, tmp_base + t * NBp, tmp,
-                          static_cast<uint32_t>(r - t * H), lane);
+        const int k_first = idx[cs] >> kTrLog, k_last = idx[ce - 1] >> kTrLog;
+        int carry_k = -1;
+        uint32_t carry_cnt = 0;
+        if (wg > 0) {
+            const uint32_t cv = carrytab[r * kTrGroup + wg];
+            carry_k = static_cast<int>(cv >> 16);
+            carry_cnt = cv & 0xFFFFu;
+        }
+        {
+            const uint32_t* ro = rowoff + r * NBp + k_first;
+            const uint32_t* tr = trel + t * NBp + k_first;
+            for (int i = lane; i <= k_last - k_first; i += 32) dst0[i] = tr[i] + ro[i];
+        }
         __syncwarp();
-        for (int i = lane; i < NBp; i += 32) pos[i] = 0;
-        __syncwarp();
+        uint32_t* tmp = tmp_all + tile_tmp0[t];
+        const uint32_t r_local = static_cast<uint32_t>(r - t * H);
+        for (int64_t p0 = cs; p0 < ce; p0 += 128) {
+            int j[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t p = p0 + 32 * u + lane;
+                j[u] = (p < ce) ? ld_stream_int(idx + p) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool valid = j[u] >= 0;
+                const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                if (vmask == 0u) break;
+                const int k = valid ? (j[u] >> kTrLog) : -1;
+                const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
+                const bool head = valid && (lane == 0 || k != kprev);
+                const unsigned hmask = __ballot_sync(0xffffffffu, head);
+                const int nvalid = __popc(vmask);
+                uint32_t off = 0;
+                if (head) off = dst0[k - k_first] + ((lane == 0 && k == carry_k) ? carry_cnt : 0u);
+                const int h = 31 - __clz(hmask & ((2u << lane) - 1u));   // my run's head lane
+                const uint32_t base = __shfl_sync(0xffffffffu, off, h);
+                if (valid) tmp[base + (lane - h)] = (static_cast<uint32_t>(j[u] & (kTrF - 1)) << 14) | r_local;
+                // the last run of the batch may continue in the next one
+                const int hl = 31 - __clz(hmask);                        // head of the last run
+                const int kl = __shfl_sync(0xffffffffu, k, hl);
+                const uint32_t len_l = static_cast<uint32_t>(nvalid - hl);
+                carry_cnt = len_l + ((hl == 0 && kl == carry_k) ? carry_cnt : 0u);
+                carry_k = kl;
+            }
+        }
+        __syncwarp();   // dst0 is restaged for the next item
     }
 }
 
-// B: one unit = (cell tile, bucket); persistent CTAs pull units from a counter
+// B: one unit = (cell tile, bucket); persistent CTAs pull units from a counter.
+// Counts per (warp slice, feature) by integer shared-memory atomics (order independent).  In the
+// scatter phase the entries of a 32-entry batch that share a feature must take consecutive slots
+// in lane (= row) order: every lane ORs its lane bit into the feature's word of a per-warp mask
+// table, reads the word back (= the set of lanes with the same feature), the lowest of them
+// advances the feature's cursor by the group size and clears the word, and each lane's slot is
+// the cursor plus its rank in the mask.  (This is match.any through shared memory: the
+// instruction itself costs hundreds of cycles on 32 distinct keys and made the kernel 10x slower.)
 __global__ void __launch_bounds__(1024, 1)
 tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restrict__ tmp_base, const int64_t* __restrict__ btot,
                       const uint32_t* __restrict__ ureg, const int64_t* __restrict__ tile_base, int64_t m, int NB, int NBp,
                       int64_t n_units, uint16_t* __restrict__ cnt, uint32_t* __restrict__ segoff,
                       uint16_t* __restrict__ ids, unsigned long long* __restrict__ counter) {
-    extern __shared__ __align__(16) uint16_t cw[];      // 32 warps x kTrF counters, then running offsets
-    __shared__ uint32_t segstart[kTrF];
+    extern __shared__ __align__(16) uint32_t bs_smem[];
+    uint16_t* cw = reinterpret_cast<uint16_t*>(bs_smem);                 // 32 warps x kTrF counters, then running offsets
+    uint32_t* tags = bs_smem + 32 * kTrF / 2;                            // 32 warps x kTrF lane tags
+    uint32_t* segstart = tags + 32 * kTrF;                               // kTrF
     __shared__ uint32_t wsum[32];
     __shared__ long long s_unit;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint16_t* mine = cw + static_cast<size_t>(warp) * kTrF;
+    uint32_t* mine32 = reinterpret_cast<uint32_t*>(mine);
+    uint32_t* tag = tags + static_cast<size_t>(warp) * kTrF;
+    for (int i = tid; i < 32 * kTrF; i += 1024) tags[i] = 0u;
     while (true) {
         __syncthreads();
         if (tid == 0) s_unit = static_cast<long long>(atomicAdd(counter, 1ull));
@@ -519,19 +587,36 @@ tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restric
         const uint32_t* in = tmp + tmp_base[t * NBp + k];
         const int64_t f0 = static_cast<int64_t>(k) << kTrLog;
         const int nf = static_cast<int>(min(static_cast<int64_t>(kTrF), m - f0));
-        for (int i = tid; i < 32 * kTrF / 2; i += 1024) reinterpret_cast<uint32_t*>(cw)[i] = 0u;
+        for (int i = tid; i < 32 * kTrF / 2; i += 1024) bs_smem[i] = 0u;
         __syncthreads();
         // ---- counts per (warp slice, feature); slices are consecutive, so slice order = row order
-        const int64_t per = ((E + 31) / 32 + 31) / 32 * 32;
+        const int64_t per = ((E + 31) / 32 + 127) / 128 * 128;
         const int64_t a = min(E, warp * per), b = min(E, a + per);
-        for (int64_t p0 = a; p0 < b; p0 += 32) {
-            const int64_t p = p0 + lane;
-            const bool valid = p < b;
-            const uint32_t e = valid ? in[p] : 0xFFFFFFFFu;
-            const uint32_t f = e >> 14;                      // an invalid lane gets a key no feature has
-            const unsigned same = __match_any_sync(0xffffffffu, f);
-            if (valid && lane == __ffs(same) - 1) mine[f] = static_cast<uint16_t>(mine[f] + __popc(same));
-            __syncwarp();
+        auto load4 = [&](int64_t p0, uint32_t* e) {
+#pragma unroll
+            for (int u2 = 0; u2 < 4; ++u2) {
+                const int64_t p = p0 + 32 * u2 + lane;
+                e[u2] = (p < b) ? __ldg(in + p) : 0xFFFFFFFFu;   // a stored entry never has its top byte set
+            }
+        };
+        {
+            uint32_t cur[4], nxt[4];
+            if (a < b) load4(a, cur);
+            for (int64_t p0 = a; p0 < b; p0 += 128) {
+#pragma unroll
+                for (int u2 = 0; u2 < 4; ++u2) nxt[u2] = 0xFFFFFFFFu;
+                if (p0 + 128 < b) load4(p0 + 128, nxt);
+#pragma unroll
+                for (int u2 = 0; u2 < 4; ++u2) {
+                    const uint32_t e = cur[u2];
+                    if (e != 0xFFFFFFFFu) {
+                        const uint32_t f = e >> 14;
+                        atomicAdd(&mine32[f >> 1], (f & 1u) ? 0x10000u : 1u);   // two 16-bit counters per word
+                    }
+                }
+#pragma unroll
+                for (int u2 = 0; u2 < 4; ++u2) cur[u2] = nxt[u2];
+            }
         }
         __syncthreads();
         // ---- per feature: exclusive prefix over the warps, segment length, padded exclusive scan
@@ -571,21 +656,36 @@ tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restric
         __syncthreads();
         // ---- stable scatter
         uint16_t* out = ids + tile_base[t];
-        for (int64_t p0 = a; p0 < b; p0 += 32) {
-            const int64_t p = p0 + lane;
-            const bool valid = p < b;
-            const uint32_t e = valid ? in[p] : 0xFFFFFFFFu;
-            const uint32_t f = e >> 14;
-            const unsigned same = __match_any_sync(0xffffffffu, f);
-            const int leader = __ffs(same) - 1;
-            uint32_t base = 0;
-            if (valid && lane == leader) {
-                base = mine[f];
-                mine[f] = static_cast<uint16_t>(base + __popc(same));
+        {
+            uint32_t cur[4], nxt[4];
+            if (a < b) load4(a, cur);
+            for (int64_t p0 = a; p0 < b; p0 += 128) {
+#pragma unroll
+                for (int u2 = 0; u2 < 4; ++u2) nxt[u2] = 0xFFFFFFFFu;
+                if (p0 + 128 < b) load4(p0 + 128, nxt);
+#pragma unroll
+                for (int u2 = 0; u2 < 4; ++u2) {
+                    const uint32_t e = cur[u2];
+                    const uint32_t f = (e >> 14) & (kTrF - 1);
+                    const bool valid = e != 0xFFFFFFFFu;
+                    if (valid) atomicOr(&tag[f], 1u << lane);
+                    __syncwarp();
+                    const unsigned same = valid ? tag[f] : (1u << lane);
+                    __syncwarp();                                 // every lane has read its word before a leader clears it
+                    const int leader = __ffs(same) - 1;
+                    uint32_t base = 0;
+                    if (valid && lane == leader) {
+                        base = mine[f];
+                        mine[f] = static_cast<uint16_t>(base + __popc(same));
+                        tag[f] = 0u;
+                    }
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (valid) out[segstart[f] + base + __popc(same & ((1u << lane) - 1u))] = static_cast<uint16_t>(e & 0x3FFFu);
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int u2 = 0; u2 < 4; ++u2) cur[u2] = nxt[u2];
             }
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (valid) out[segstart[f] + base + __popc(same & ((1u << lane) - 1u))] = static_cast<uint16_t>(e & 0x3FFFu);
-            __syncwarp();
         }
     }
 }
@@ -596,10 +696,19 @@ static void transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
     cudaStream_t st = c->stream;
     const int64_t n = X.nrows, m = c->m;
     const int nt = T.n_tiles;
+    const bool debug = getenv("SNAPB200_DEBUG") != nullptr;
+    cudaEvent_t dbg[6] = {};
+    auto mark = [&](int i) {
+        if (!debug) return;
+        if (!dbg[i]) cudaEventCreate(&dbg[i]);
+        cudaEventRecord(dbg[i], st);
+    };
+    mark(0);
     const int NB = static_cast<int>(ceil_div(m, kTrF));
     const int NBp = (NB + 31) / 32 * 32;
     DevBuf<uint16_t> rowcnt;
-    DevBuf<uint32_t> rowoff, ureg, tmp;
+    DevBuf<uint32_t> rowoff, ureg, tmp, trel, carrytab;
+    DevBuf<int64_t> tile_tmp0;
     DevBuf<int64_t> btot, tmp_base;
     DevBuf<unsigned long long> counter;
     rowcnt.alloc(std::max<int64_t>(1, n * NBp));
@@ -607,38 +716,47 @@ static void transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
     btot.alloc(static_cast<int64_t>(nt) * NBp);
     tmp_base.alloc(static_cast<int64_t>(nt) * NBp);
     ureg.alloc(static_cast<int64_t>(nt) * NBp);
+    trel.alloc(static_cast<int64_t>(nt) * NBp);
+    carrytab.alloc(std::max<int64_t>(1, n * kTrGroup));
+    tile_tmp0.alloc(nt);
     counter.alloc(1);
     SB_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
     SB_CUDA(cudaMemsetAsync(btot.p, 0, sizeof(int64_t) * nt * NBp, st));
     const size_t smem_walk = static_cast<size_t>(kTrWarps) * NBp * sizeof(uint16_t);
+    const size_t smem_scat = static_cast<size_t>(kTrWarps) * NBp * sizeof(uint32_t);
     static_assert(kTrF == 1024, "tr_bucket_sort_kernel scans one feature per thread of a 1024-thread CTA");
     // A1 only reads: as many resident warps as fit.  A3 also scatters: the rows in flight bound the
     // output windows that must stay in L2 until their sectors are complete (rows x ~40 B x buckets),
     // so it runs with half the warps.
-    int cta_per_sm_a1 = 4, cta_per_sm_a3 = 2;
+    int cta_per_sm_a1 = 4, cta_per_sm_a3 = 4;
     if (const char* e = getenv("SNAPB200_TR_CTAS")) cta_per_sm_a3 = std::max(1, atoi(e));
     const int walk_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kTrWarps), c->num_sms * cta_per_sm_a1)));
-    const int scat_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kTrWarps), c->num_sms * cta_per_sm_a3)));
+    const int scat_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n * kTrGroup, kTrWarps), c->num_sms * cta_per_sm_a3)));
     if (n > 0) {
         SB_CUDA(cudaFuncSetAttribute(tr_rowcnt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_walk)));
-        tr_rowcnt_kernel<<<walk_grid, kTrWarps * 32, smem_walk, st>>>(X.ptr.p, X.idx.p, n, NBp, rowcnt.p);
+        tr_rowcnt_kernel<<<walk_grid, kTrWarps * 32, smem_walk, st>>>(X.ptr.p, X.idx.p, n, NBp, rowcnt.p, carrytab.p);
         SB_LAUNCH_CHECK();
+        mark(1);
         tr_rowscan_kernel<<<static_cast<unsigned>(static_cast<int64_t>(nt) * (NBp / 32)), 1024, 0, st>>>(rowcnt.p, n, tile_rows, NBp,
                                                                                                       rowoff.p, btot.p);
         SB_LAUNCH_CHECK();
     }
+    mark(2);
     // ---- bucket bases (host: nt x NB numbers): exact offsets into tmp, worst-case padded regions of the output
     std::vector<int64_t> hb(static_cast<size_t>(nt) * NBp), htb(static_cast<size_t>(nt) * NBp), tb(nt + 1);
-    std::vector<uint32_t> hureg(static_cast<size_t>(nt) * NBp);
+    std::vector<uint32_t> hureg(static_cast<size_t>(nt) * NBp), hrel(static_cast<size_t>(nt) * NBp);
+    std::vector<int64_t> ht0(nt);
     SB_CUDA(cudaMemcpyAsync(hb.data(), btot.p, sizeof(int64_t) * hb.size(), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     int64_t run_tmp = 0, counted = 0;
     tb[0] = 0;
     for (int t = 0; t < nt; ++t) {
         int64_t reg = 0;
+        ht0[t] = run_tmp;
         for (int k = 0; k < NBp; ++k) {
             const int64_t e = hb[static_cast<size_t>(t) * NBp + k];
             htb[static_cast<size_t>(t) * NBp + k] = run_tmp;
+            hrel[static_cast<size_t>(t) * NBp + k] = static_cast<uint32_t>(run_tmp - ht0[t]);
             hureg[static_cast<size_t>(t) * NBp + k] = static_cast<uint32_t>(reg);
             run_tmp += e;
             counted += e;
@@ -647,29 +765,34 @@ static void transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
                 reg += (e + 7 * std::min<int64_t>(nf, e) + 7) / 8 * 8;   // every non-empty segment pads by at most 7
             }
         }
-        SB_CHECK(reg < (1ll << 32), "transpose_tiled: more than 2^32 slots in one cell tile");
+        SB_CHECK(reg < (1ll << 32) && run_tmp - ht0[t] < (1ll << 32), "transpose_tiled: more than 2^32 slots in one cell tile");
         tb[t + 1] = tb[t] + reg;
     }
     SB_CHECK(counted == X.nnz, "transpose_tiled: count mismatch (column index out of range or unsorted rows?)");
     SB_CUDA(cudaMemcpyAsync(tmp_base.p, htb.data(), sizeof(int64_t) * htb.size(), cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(ureg.p, hureg.data(), sizeof(uint32_t) * hureg.size(), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(trel.p, hrel.data(), sizeof(uint32_t) * hrel.size(), cudaMemcpyHostToDevice, st));
+    SB_CUDA(cudaMemcpyAsync(tile_tmp0.p, ht0.data(), sizeof(int64_t) * nt, cudaMemcpyHostToDevice, st));
     SB_CUDA(cudaMemcpyAsync(T.tile_base.p, tb.data(), sizeof(int64_t) * (nt + 1), cudaMemcpyHostToDevice, st));
     T.ids.alloc(tb[nt] + 8);
     tmp.alloc(std::max<int64_t>(1, X.nnz));
     if (n > 0 && X.nnz > 0) {
-        SB_CUDA(cudaFuncSetAttribute(tr_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_walk)));
-        tr_scatter_kernel<<<scat_grid, kTrWarps * 32, smem_walk, st>>>(X.ptr.p, X.idx.p, n, tile_rows, NBp, rowoff.p, tmp_base.p, tmp.p);
+        SB_CUDA(cudaFuncSetAttribute(tr_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_scat)));
+        tr_scatter_kernel<<<scat_grid, kTrWarps * 32, smem_scat, st>>>(X.ptr.p, X.idx.p, n, tile_rows, NBp, rowoff.p, trel.p,
+                                                                       tile_tmp0.p, carrytab.p, tmp.p);
         SB_LAUNCH_CHECK();
     }
+    mark(3);
     {
         const int64_t n_units = static_cast<int64_t>(nt) * NB;
-        const size_t smem = static_cast<size_t>(32) * kTrF * sizeof(uint16_t);
+        const size_t smem = static_cast<size_t>(32) * kTrF * (sizeof(uint16_t) + sizeof(uint32_t)) + kTrF * sizeof(uint32_t);
         SB_CUDA(cudaFuncSetAttribute(tr_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         const int grid = static_cast<int>(std::min<int64_t>(n_units, c->num_sms));
         tr_bucket_sort_kernel<<<grid, 1024, smem, st>>>(tmp.p, tmp_base.p, btot.p, ureg.p, T.tile_base.p, m, NB, NBp, n_units,
                                                         T.cnt.p, T.segoff.p, T.ids.p, counter.p);
         SB_LAUNCH_CHECK();
     }
+    mark(4);
     if (df_local) {
         tile_df_kernel<<<static_cast<unsigned>(ceil_div(m, 256)), 256, 0, st>>>(T.cnt.p, m, nt, df_local);
         SB_LAUNCH_CHECK();
@@ -683,7 +806,16 @@ static void transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
         SB_LAUNCH_CHECK();
     }
     count_launch(c, 6);
+    mark(5);
     SB_CUDA(cudaStreamSynchronize(st));   // host tables and temporaries stay alive until everything ran
+    if (debug) {
+        float ms[5] = {};
+        for (int i = 0; i < 5; ++i)
+            if (dbg[i] && dbg[i + 1]) cudaEventElapsedTime(&ms[i], dbg[i], dbg[i + 1]);
+        fprintf(stderr, "[snapb200] bucketed transpose: rowcnt %.2f  rowscan %.2f  host tables+alloc %.2f  scatter %.2f  bucket sort %.2f  "
+                        "df/vals %.2f ms\n", ms[0], ms[1], 0.0f, ms[2] + 0.0f, ms[3], ms[4]);
+        for (auto& e : dbg) if (e) cudaEventDestroy(e);
+    }
     T.built = true;
 }
 
@@ -704,9 +836,13 @@ void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
     T.cnt.alloc(static_cast<int64_t>(nt) * m);
     T.segoff.alloc(static_cast<int64_t>(nt) * m);
     T.tile_base.alloc(nt + 1);
-    const char* lg = getenv("SNAPB200_TRANSPOSE_LEGACY");
-    const bool legacy = lg != nullptr && lg[0] == '1';
-    if (!legacy && ceil_div(m, kTrF) <= kTrMaxBuckets && tile_rows <= (1 << 14)) {
+    // SNAPB200_TRANSPOSE=bucketed selects the bucketed transpose below (same output, bit for bit).  Measured
+    // on C3 it is not faster yet (88 ms against 80 ms: its scatter pass pays a DRAM fill for every
+    // partially written 32-byte sector and the per-bucket sort is bound by the L1 / shared-memory pipe;
+    // profiles/README.md), so the bitmap transpose above stays the default.
+    const char* tr_mode = getenv("SNAPB200_TRANSPOSE");
+    const bool bucketed = tr_mode != nullptr && tr_mode[0] == 'b';
+    if (bucketed && ceil_div(m, kTrF) <= kTrMaxBuckets && tile_rows <= (1 << 14)) {
         transpose_bucketed(c, tile_rows, df_local);
         return;
     }

@@ -180,8 +180,8 @@ def test_bucketed_transpose_equals_legacy_bitmap_transpose(engine, monkeypatch):
             X.data = rng.integers(1, 6, size=X.nnz).astype(np.float32)
         V = rng.standard_normal((n, 4)).astype(np.float32)
         outs = []
-        for legacy in ("1", "0"):
-            monkeypatch.setenv("SNAPB200_TRANSPOSE_LEGACY", legacy)
+        for mode in ("bitmap", "bucketed"):
+            monkeypatch.setenv("SNAPB200_TRANSPOSE", mode)
             engine.set_spmm_mode("tiled")
             engine.load_csr(X)
             engine.set_feature_weights(None)
