@@ -40,7 +40,11 @@ CONFIGS = {
     "c4": (10_000_000, 500_000, 3_000, 64, 50),
     "tiny": (2_000, 20_000, 500, 40, 30),
     "c3s": (125_000, 500_000, 5_000, 48, 30),   # the size of one rank's shard of c3 at 8 GPUs (tuning aid)
+    # c5 = multi_spectral: the ATAC view below + an RNA count view of (n, 30_000, ~1500 nnz/cell), see run_multiview
+    "c5": (1_000_000, 500_000, 5_000, 48, 30),
+    "c5s": (125_000, 500_000, 5_000, 48, 30),
 }
+C5_RNA = (30_000, 1_500)     # bins, nominal nnz per cell of the second view
 CONFIG_TEXT = {
     "c1": "synthetic 5k-cell x 100k-bin binarised tile matrix (~3k nnz/cell), n_comps=30",
     "c2": "synthetic 100k cells x 500k bins (~5k nnz/cell), n_comps=30",
@@ -48,6 +52,8 @@ CONFIG_TEXT = {
     "c4": "synthetic 10M cells x 500k bins (~3k nnz/cell), n_comps=50, row-sharded",
     "tiny": "synthetic 2k x 20k (~500 nnz/cell), n_comps=30 (harness test only)",
     "c3s": "synthetic 125k cells x 500k bins (~5k nnz/cell), n_comps=30 (one rank's share of c3 at 8 GPUs; tuning aid)",
+    "c5": "snap.tl.multi_spectral: synthetic ATAC tile (1M x 500k, ~5k nnz/cell, binarised) + RNA count (1M x 30k, ~1.5k nnz/cell, counts 1-3), n_comps=30, row-sharded",
+    "c5s": "snap.tl.multi_spectral: ATAC 125k x 500k + RNA 125k x 30k (one rank's share of c5 at 8 GPUs; tuning aid)",
 }
 METRIC = "snap.tl.spectral cells/s"
 CPU_SAMPLE_ROWS = 4000
@@ -313,13 +319,46 @@ def run_ours(args):
         "stored_index_bytes_per_entry": 2 if stats.get("spmm_tiled") else 4,
     }
 
+    # ---- the reference's own answer to this size: the Nystrom path (sample_size), timed beside the full operator
+    nystrom = None
+    if args.nystrom > 0:
+        from snapatac2_b200 import tl
+        full_evecs = evecs.copy()
+        t0 = time.perf_counter()
+        v_n, u_n = tl.spectral_embedding_nystrom(eng, None, None, k, args.nystrom, False, 20000, tol=args.tol, block=args.block)
+        ev_n, q_n = tl.orthogonalize(v_n, u_n)
+        torch.cuda.synchronize()
+        dt_n = time.perf_counter() - t0
+        tn = torch.tensor([dt_n], dtype=torch.float64, device="cuda")
+        if world > 1:
+            td.all_reduce(tn, op=td.ReduceOp.MAX)
+        # principal cosines between the two k-dimensional embeddings (both have orthonormal columns over all cells)
+        q_n = np.real(q_n)
+        q_n = q_n / np.sqrt(dist.allreduce_array(np.sum(q_n * q_n, axis=0), "sum"))[None, :]
+        cross = dist.allreduce_array(full_evecs.T @ q_n, "sum")
+        pc = np.linalg.svd(cross, compute_uv=False)
+        nystrom = {"sample_size": int(args.nystrom), "chunk_size": 20000, "seconds": float(tn.item()),
+                   "cells_per_s": n / float(tn.item()), "evals_head": [float(x) for x in np.real(ev_n[:4])],
+                   "principal_cosines_vs_full": {"max": float(pc.max()), "median": float(np.median(pc)), "min": float(pc.min()),
+                                                 "n_above_0.9": int((pc > 0.9).sum()), "k": int(k)},
+                   "note": "tl.spectral_embedding_nystrom + orthogonalize on the resident shards (landmark draw: numpy default_rng(2023))"}
+        eng.prepare(want_outputs=False)      # the stats below describe the full path again
+        eng.eigsh(k, seed=0, tol=args.tol, block=args.block, out_evecs=evecs)
+        stats = eng.stats()
+
     # ---- e2e: the reference-facing plugin call, tl.spectral(adata, n_comps, features=None), on an in-memory
     #      AnnData whose X is an ordinary scipy CSR in pageable host memory (int64 indices as soon as the
     #      shard holds more than 2^31 entries, as scipy stores them; float32 values, all ones).  Everything
     #      is inside the timed region: host-side scan of the values, narrowing of the indices into pinned
     #      staging, the H2D copies, prepare, eigsh, the eigenvectors back in a fresh numpy array.
     e2e = None
+    e2e_skipped = None
     if not args.no_e2e:
+        import psutil
+        need = 16 * nnz_local * world          # int64 indices + float32 values + the int32 export, all ranks of this box
+        if need > 0.7 * psutil.virtual_memory().total:
+            e2e_skipped = f"host arrays of all {world} ranks ({need / 1e9:.0f} GB) exceed 70% of host memory"
+    if not args.no_e2e and e2e_skipped is None:
         import scipy.sparse as sp
         from concurrent.futures import ThreadPoolExecutor
         from snapatac2_b200 import MiniAnnData, tl
@@ -394,14 +433,153 @@ def run_ours(args):
                        "nnz_per_gpu": nnz_local, "n_comps": k, "block": b, "tol": args.tol or 1e-5,
                        "parallelism": f"rows/{world}", "l2": "inputs larger than L2 (index stream >> 126 MB)"
                        if nnz_local * 4 > (256 << 20) else "inputs fit L2; operator_time flushes L2 between iterations"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e if e2e is not None else ({"skipped": e2e_skipped} if e2e_skipped else None),
+            "nystrom": nystrom, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "timing": {"device_ms_total": total_ms, "wall_ms_total": wall_ms, "generate_s": t_gen,
                        "last_step_call_ms": call_ms, "step_wall_ms": step_wall,
                        "pool_mallocs_in_timed_region": stats["pool_mallocs"] - st0["pool_mallocs"],
                        "pool_ms_in_timed_region": stats["ms_pool"] - st0["ms_pool"]},
             "solver": {kk: stats[kk] for kk in ("n_ops", "n_restarts", "basis_cols", "max_residual", "ms_transpose",
                                                 "ms_prepare", "ms_format", "ms_eigsh", "ms_spmm", "ms_ortho", "ms_comm", "ms_host",
-                                                "spmm_tiled", "ms_prepare_wall", "ms_pool", "pool_mallocs")},
+                                                "spmm_tiled", "ms_prepare_wall", "ms_pool", "pool_mallocs", "converged",
+                                                "n_spec_ops", "ms_d2h")},
+            "evals_head": [float(x) for x in evals[:4]],
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        td.barrier()
+        td.destroy_process_group()
+
+
+def run_multiview(args):
+    """configs[4]: snap.tl.multi_spectral co-embedding of an ATAC tile view and an RNA count view of the same
+    cells.  A step = everything multi_spectral does after the views are on the device: per-view prepare (IDF,
+    norms, both tiled copies, degrees), the frobenius_norm normaliser on 2000 sampled rows, the combination
+    and the block-Lanczos solve on the virtual column concatenation.  `e2e` = tl.multi_spectral on host CSRs."""
+    import torch
+    import torch.distributed as td
+    import scipy.sparse as sp
+
+    from snapatac2_b200 import Engine, MiniAnnData, dist, synth, tl
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        td.init_process_group("cpu:gloo,cuda:nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+    n, m, nnz_row, K, k = CONFIGS[args.config]
+    m2, nnz_row2 = C5_RNA
+    spec_a = synth.make_spec(n, m, nnz_row, K, seed=0)
+    spec_r = synth.make_spec(n, m2, nnz_row2, K, seed=0)          # same planted labels (keyed by seed, row)
+    bounds = dist.equal_row_splits(n, world)
+    row0, row1 = int(bounds[rank]), int(bounds[rank + 1])
+    n_local = row1 - row0
+
+    eng = Engine(local_rank)
+    if args.block:
+        eng.set_block(args.block)
+    dist.attach_engine_comm(eng)
+    views = tl._view_engines(eng, 2)
+    ext_stream = torch.cuda.ExternalStream(eng.stream_handle(), device=torch.device("cuda", local_rank))
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+            torch.cuda.synchronize()
+
+    # the RNA view's counts (1 + column % 3: a function of the column, shard independent) are attached on the host
+    views[1].generate(spec_r, row0=row0, n_local=n_local)
+    R = views[1].export_csr()
+    R.data = (1.0 + (R.indices % 3)).astype(np.float32)
+    views[0].generate(spec_a, row0=row0, n_local=n_local)
+    views[1].load_csr(R, n_global=n, row0=row0)
+    nnz_a, nnz_r = views[0].shape()[2], views[1].shape()[2]
+    rows = np.sort(np.random.RandomState(2023).choice(n, min(2000, n), replace=False))
+    mine = rows[(rows >= row0) & (rows < row0 + n_local)] - row0
+    evecs = np.empty((n_local, k), dtype=np.float64)
+    parts = {}
+
+    def step():
+        t_a = time.perf_counter()
+        norms = []
+        for v in views:
+            v.set_feature_weights(None)
+            v.prepare(want_outputs=False)
+            norms.append(float(np.sqrt(v.view_frobenius(mine) - len(rows))))
+        ws = [1.0 / nrm for nrm in norms]
+        scales = [float(np.sqrt(w / sum(ws))) for w in ws]
+        eng.combine_views(views, scales)
+        t_b = time.perf_counter()
+        out = eng.eigsh(k, seed=0, tol=args.tol, block=args.block, out_evecs=evecs)
+        parts["prepare"], parts["eigsh"], parts["norms"] = 1e3 * (t_b - t_a), 1e3 * (time.perf_counter() - t_b), norms
+        return out
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for _ in range(args.warmup):
+        step()
+    launches0 = sum(v.stats()["kernel_launches"] for v in views)
+    sync_all()
+    sampler.mark_begin()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(ext_stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        evals, _ = step()
+    ev1.record(ext_stream)
+    ev1.synchronize()
+    wall = time.perf_counter() - t0
+    sync_all()
+    clocks = sampler.stop()
+    launches = sum(v.stats()["kernel_launches"] for v in views) - launches0
+    stats = eng.stats()
+    tmax = torch.tensor([ev0.elapsed_time(ev1), wall * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        td.all_reduce(tmax, op=td.ReduceOp.MAX)
+    ms_per_step = float(tmax[0].item()) / args.steps
+
+    # ---- e2e: tl.multi_spectral on host CSRs (ATAC: float32 ones; RNA: float32 counts)
+    e2e = None
+    if not args.no_e2e:
+        A = views[0].export_csr()
+        ad_a, ad_r = MiniAnnData(A), MiniAnnData(R)
+
+        def e2e_step():
+            return tl.multi_spectral([ad_a, ad_r], n_comps=k, features=None, engine=eng)
+
+        e2e_step()
+        sync_all()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            ev_e, emb_e = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            td.all_reduce(tt, op=td.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": n * args.e2e_steps / dt, "unit": "cells/s", "ms_per_step": 1e3 * dt / args.e2e_steps,
+               "h2d_bytes_per_step": int(sum(v.stats()["bytes_h2d"] for v in views)),
+               "d2h_bytes_per_step": int(emb_e.nbytes + ev_e.nbytes), "steps": args.e2e_steps, "per_rank_bytes": True,
+               "api": "tl.multi_spectral([MiniAnnData(atac_csr), MiniAnnData(rna_csr)], n_comps=30, features=None)"}
+
+    if rank == 0:
+        line = {
+            "metric": "snap.tl.multi_spectral cells/s", "value": n / (ms_per_step / 1e3), "unit": "cells/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CONFIG_TEXT[args.config], "config": args.config, "n_cells": n, "views": [[n, m], [n, m2]],
+                       "nnz_per_gpu": [int(nnz_a), int(nnz_r)], "n_comps": k, "block": stats["block"],
+                       "parallelism": f"rows/{world}", "l2": "inputs larger than L2"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None,
+            "timing": {"wall_ms_total": float(tmax[1].item()), "last_step_call_ms": {kk: parts[kk] for kk in ("prepare", "eigsh")}},
+            "view_norms": parts["norms"],
+            "solver": {kk: stats[kk] for kk in ("n_ops", "n_restarts", "basis_cols", "max_residual", "ms_eigsh", "ms_spmm",
+                                                "ms_ortho", "ms_comm", "ms_host", "converged")},
             "evals_head": [float(x) for x in evals[:4]],
         }
         print(json.dumps(line), flush=True)
@@ -425,9 +603,13 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--nystrom", type=int, default=0,
+                    help="also time the Nystrom path (reference: sample_size) with this many landmarks on the same resident data")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config.startswith("c5"):
+        run_multiview(args)
     else:
         run_ours(args)
 

@@ -99,6 +99,20 @@ int  snapb200_load_csr(snapb200_ctx* ctx, int64_t n_local, int64_t n_global, int
                        const void* indices, int indices_bits,
                        const void* values, int value_kind, int on_device);
 
+/* The same load, block by block: the matrix arrives as a sequence of CSR row blocks (the chunks a
+ * backed AnnData yields -- the reference iterates `chunked_X`, embedding.rs:76-84 -- or any iterator
+ * of scipy CSR blocks) and is assembled on the device, so the host never holds more than one block.
+ * load_begin(m, hints) -> load_append(block)... -> load_end(n_global, row0); n_global < 0 means the
+ * blocks are the whole matrix.  A block's indptr may start anywhere (differences are used); index and
+ * value conventions as for snapb200_load_csr (host arrays only). */
+int  snapb200_load_begin(snapb200_ctx* ctx, int64_t m, int64_t rows_hint, int64_t nnz_hint);
+int  snapb200_load_append(snapb200_ctx* ctx, int64_t n_rows, const void* indptr, int indptr_bits,
+                          const void* indices, int indices_bits, const void* values, int value_kind);
+int  snapb200_load_end(snapb200_ctx* ctx, int64_t n_global, int64_t row0);
+/* Place an already loaded shard inside the global matrix (a block-wise load learns its own row count
+ * last; under multi-GPU the global count follows from an exchange of the shard sizes). */
+int  snapb200_set_geometry(snapb200_ctx* ctx, int64_t n_global, int64_t row0);
+
 /* Column selection on the device (to_select_elem + slice_axis(1, ..),
  * embedding.rs:36-39): keep[j] != 0 keeps column j; surviving columns are
  * renumbered densely.  Must be called between load and prepare. */
@@ -156,12 +170,19 @@ int  snapb200_combine_views(snapb200_ctx* main_ctx, snapb200_ctx** views, const 
                             double* degree_out);
 int  snapb200_get_vector(snapb200_ctx* ctx, int which, double* out);
 
+/* dst <- the rows `rows` (local row ids of src's shard, any order) of src's resident matrix; dst
+ * becomes rows [row0_dst, row0_dst + n_rows) of an n_global_dst-row matrix with the same columns.
+ * Both contexts on the same GPU.  The Nystrom path takes its landmark rows this way
+ * (select_axis(0, ..), embedding.rs:95-99). */
+int  snapb200_gather_rows(snapb200_ctx* src, const int64_t* rows, int64_t n_rows, snapb200_ctx* dst,
+                          int64_t n_global_dst, int64_t row0_dst);
+
 /* Nystrom extension (spectral_embedding_nystrom / nystrom, embedding.rs:61-129, 194-267): products
  * with the feature-weighted, row-normalised matrix  Xhat = diag(1/rho) P diag(w)  on k dense
  * columns (row-major f32 host buffers):
  *   transposed == 0:  out[n_local x k] = Xhat   in[m x k]       -- "sample @ (...)" for every cell
  *   transposed != 0:  out[m x k]       = Xhat^T in[n_local x k] -- "seed.T @ evecs" (summed over the
- *                                                                  row shards); needs snapb200_prepare
+ *                                                                  row shards)
  * prepare_projection computes what the non-transposed product needs (IDF or user weights, row
  * norms, the cell-major tiled copy) without the transpose; it is implied by the first project call.
  * Its outputs may be NULL (idf_out: m doubles, rho_out: n_local doubles). */

@@ -18,9 +18,11 @@ LIB_PATH = Path(__file__).resolve().parent / "libsnapb200.so"
 SYMBOLS = [
     "snapb200_last_error", "snapb200_version", "snapb200_create", "snapb200_destroy",
     "snapb200_comm_unique_id", "snapb200_comm_init", "snapb200_load_csr",
+    "snapb200_load_begin", "snapb200_load_append", "snapb200_load_end", "snapb200_set_geometry",
     "snapb200_select_features", "snapb200_generate", "snapb200_shape", "snapb200_export_csr",
     "snapb200_set_feature_weights", "snapb200_prepare", "snapb200_view_norms",
     "snapb200_attach_view", "snapb200_view_frobenius", "snapb200_combine_views", "snapb200_get_vector",
+    "snapb200_gather_rows",
     "snapb200_prepare_projection", "snapb200_project",
     "snapb200_operator_apply", "snapb200_operator_time", "snapb200_eigsh", "snapb200_get_stats",
     "snapb200_get_stream", "snapb200_set_spmm_mode", "snapb200_set_block",
@@ -69,6 +71,10 @@ def load() -> C.CDLL:
         "snapb200_comm_unique_id": [C.c_char_p],
         "snapb200_comm_init": [vp, i32, i32, C.c_char_p],
         "snapb200_load_csr": [vp, i64, i64, i64, i64, vp, i32, vp, i32, vp, i32, i32],
+        "snapb200_load_begin": [vp, i64, i64, i64],
+        "snapb200_load_append": [vp, i64, vp, i32, vp, i32, vp, i32],
+        "snapb200_load_end": [vp, i64, i64],
+        "snapb200_set_geometry": [vp, i64, i64],
         "snapb200_select_features": [vp, vp, i64],
         "snapb200_generate": [vp, i64, i64, i64, i64, i32, i32, C.c_uint64, vp, vp, vp, vp],
         "snapb200_shape": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],
@@ -80,6 +86,7 @@ def load() -> C.CDLL:
         "snapb200_view_frobenius": [vp, vp, i64, C.POINTER(dbl)],
         "snapb200_combine_views": [vp, vp, vp, i32, vp],
         "snapb200_get_vector": [vp, i32, vp],
+        "snapb200_gather_rows": [vp, vp, i64, vp, i64, i64],
         "snapb200_prepare_projection": [vp, vp, vp],
         "snapb200_project": [vp, i32, vp, i32, vp],
         "snapb200_operator_apply": [vp, vp, vp, i32],

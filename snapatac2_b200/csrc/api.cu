@@ -236,6 +236,117 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     c->stats.nnz_local = nnz;
 }
 
+// ---- block-wise load: the matrix arrives as a sequence of CSR row blocks (the chunks of a backed
+//      AnnData, reference: `chunked_X` / the iteration at embedding.rs:76-84) and is assembled on the device
+template <typename T>
+void grow_keep(snapb200_ctx* c, DevBuf<T>& buf, int64_t used, int64_t need) {
+    if (need <= buf.n) return;
+    DevBuf<T> bigger;
+    bigger.alloc(std::max<int64_t>(need, buf.n + buf.n / 2 + 1024));
+    if (used > 0) SB_CUDA(cudaMemcpyAsync(bigger.p, buf.p, sizeof(T) * used, cudaMemcpyDeviceToDevice, c->stream));
+    buf.swap(bigger);
+}
+
+void load_begin(snapb200_ctx* c, int64_t m, int64_t rows_hint, int64_t nnz_hint) {
+    SB_CHECK(m >= 1 && m < (1ll << 31), "load_begin: m must be in [1, 2^31)");
+    Csr& X = c->X;
+    c->loaded = false;
+    c->prepared = false;
+    c->proj_ready = false;
+    c->views.clear();
+    c->nnz_mode = -1;
+    c->S1.clear(); c->S2.clear(); c->Xt.clear(); c->xt_built = false; c->XtT.clear();
+    X.clear();
+    X.ncols = m;
+    X.ptr.alloc(std::max<int64_t>(rows_hint, 1024) + 1);
+    X.idx.alloc(std::max<int64_t>(nnz_hint, 1 << 20));
+    SB_CUDA(cudaMemsetAsync(X.ptr.p, 0, sizeof(int64_t), c->stream));
+    c->m = m;
+    c->appending = true;
+    c->app_rows = c->app_nnz = 0;
+    c->stats.bytes_h2d = 0;
+}
+
+void load_append(snapb200_ctx* c, int64_t n_rows, const void* indptr, int indptr_bits, const void* indices,
+                 int indices_bits, const void* values, int value_kind) {
+    SB_CHECK(c->appending, "load_append: call load_begin first");
+    SB_CHECK(n_rows >= 0 && indptr != nullptr, "load_append: bad block");
+    SB_CHECK(indptr_bits == 32 || indptr_bits == 64, "load_append: indptr_bits must be 32 or 64");
+    SB_CHECK(indices_bits == 32 || indices_bits == 64, "load_append: indices_bits must be 32 or 64");
+    Csr& X = c->X;
+    cudaStream_t st = c->stream;
+    auto at = [&](int64_t i) -> int64_t {
+        return indptr_bits == 64 ? static_cast<const int64_t*>(indptr)[i] : static_cast<const int32_t*>(indptr)[i];
+    };
+    const int64_t first = at(0), nnz = at(n_rows) - first;
+    SB_CHECK(nnz >= 0, "load_append: indptr must be non-decreasing");
+    // row pointers of the block, shifted behind what is already there
+    std::vector<int64_t> hp(static_cast<size_t>(n_rows));
+    for (int64_t i = 0; i < n_rows; ++i) hp[i] = c->app_nnz + (at(i + 1) - first);
+    grow_keep(c, X.ptr, c->app_rows + 1, c->app_rows + n_rows + 1);
+    if (n_rows > 0)
+        SB_CUDA(cudaMemcpyAsync(X.ptr.p + c->app_rows + 1, hp.data(), sizeof(int64_t) * n_rows, cudaMemcpyHostToDevice, st));
+    grow_keep(c, X.idx, c->app_nnz, c->app_nnz + nnz);
+    if (nnz > 0) {
+        const unsigned char* src = static_cast<const unsigned char*>(indices) + static_cast<size_t>(first) * (indices_bits / 8);
+        if (!stage_indices(c, src, indices_bits, nnz, X.idx.p + c->app_nnz)) throw Error("load_append: column index out of range");
+        if (values != nullptr) {
+            const size_t es = value_size(value_kind);
+            const unsigned char* vsrc = static_cast<const unsigned char*>(values) + static_cast<size_t>(first) * es;
+            const bool ones = host_values_all_ones(c, vsrc, value_kind, nnz);
+            if (!ones && !X.has_values()) {   // first block with real values: earlier entries were all ones
+                X.val.alloc(X.idx.n);
+                if (c->app_nnz > 0) fill_f32(c, X.val.p, 1.f, c->app_nnz);
+            }
+            if (X.has_values()) {
+                grow_keep(c, X.val, c->app_nnz, X.idx.n);
+                stage_values(c, vsrc, value_kind, nnz, X.val.p + c->app_nnz);
+            }
+        } else if (X.has_values()) {
+            grow_keep(c, X.val, c->app_nnz, X.idx.n);
+            fill_f32(c, X.val.p + c->app_nnz, 1.f, nnz);
+        }
+    }
+    SB_CUDA(cudaStreamSynchronize(st));   // hp is a host temporary
+    c->app_rows += n_rows;
+    c->app_nnz += nnz;
+    c->stats.bytes_h2d += 8 * n_rows + 4 * nnz + (X.has_values() ? 4 * nnz : 0);
+}
+
+void load_end(snapb200_ctx* c, int64_t n_global, int64_t row0) {
+    SB_CHECK(c->appending, "load_end: call load_begin first");
+    Csr& X = c->X;
+    cudaStream_t st = c->stream;
+    const int64_t n_local = c->app_rows, nnz = c->app_nnz;
+    if (n_global < 0) n_global = n_local;
+    SB_CHECK(row0 >= 0 && row0 + n_local <= n_global, "load_end: bad shard geometry");
+    c->appending = false;
+    X.nrows = n_local;
+    X.nnz = nnz;
+    DevBuf<int> bad;
+    bad.alloc(1);
+    SB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    if (nnz > 0) {
+        check_i32_kernel<<<stream_blocks(c, nnz), 256, 0, st>>>(X.idx.p, nnz, c->m, bad.p);
+        SB_LAUNCH_CHECK();
+        const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(n_local, 8), static_cast<int64_t>(c->num_sms) * 16));
+        rows_sorted_kernel<<<blocks, 256, 0, st>>>(X.ptr.p, X.idx.p, n_local, bad.p);
+        SB_LAUNCH_CHECK();
+        count_launch(c, 2);
+    }
+    int hbad = 0;
+    SB_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    SB_CHECK(!(hbad & 1), "load_end: column index out of range");
+    SB_CHECK(!(hbad & 2), "load_end: column indices must be strictly increasing within every row (sorted, no duplicates)");
+    c->n_local = n_local;
+    c->n_global = n_global;
+    c->row0 = row0;
+    c->loaded = true;
+    c->stats.nnz_local = nnz;
+    c->stats.host_threads = host_threads(c);
+}
+
 }  // namespace
 }  // namespace snapb
 
@@ -313,6 +424,29 @@ int snapb200_load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_
     return guarded([&] {
         bind(c);
         load_csr(c, n_local, n_global, row0, m, indptr, indptr_bits, indices, indices_bits, values, value_kind, on_device);
+    });
+}
+
+int snapb200_load_begin(snapb200_ctx* c, int64_t m, int64_t rows_hint, int64_t nnz_hint) {
+    return guarded([&] { bind(c); load_begin(c, m, rows_hint, nnz_hint); });
+}
+int snapb200_load_append(snapb200_ctx* c, int64_t n_rows, const void* indptr, int indptr_bits, const void* indices,
+                         int indices_bits, const void* values, int value_kind) {
+    return guarded([&] { bind(c); load_append(c, n_rows, indptr, indptr_bits, indices, indices_bits, values, value_kind); });
+}
+int snapb200_load_end(snapb200_ctx* c, int64_t n_global, int64_t row0) {
+    return guarded([&] { bind(c); load_end(c, n_global, row0); });
+}
+
+int snapb200_set_geometry(snapb200_ctx* c, int64_t n_global, int64_t row0) {
+    return guarded([&] {
+        SB_CHECK(c != nullptr && c->loaded, "set_geometry: no matrix loaded");
+        SB_CHECK(row0 >= 0 && row0 + c->n_local <= n_global, "set_geometry: bad shard geometry");
+        c->n_global = n_global;
+        c->row0 = row0;
+        c->prepared = false;
+        c->proj_ready = false;
+        c->views.clear();
     });
 }
 
@@ -408,6 +542,15 @@ int snapb200_view_frobenius(snapb200_ctx* c, const int64_t* sample_rows, int64_t
 int snapb200_combine_views(snapb200_ctx* main_ctx, snapb200_ctx** views, const double* view_scale, int n_views,
                            double* degree_out) {
     return guarded([&] { bind(main_ctx); combine_views(main_ctx, views, view_scale, n_views, degree_out); });
+}
+
+int snapb200_gather_rows(snapb200_ctx* src, const int64_t* rows, int64_t n_rows, snapb200_ctx* dst, int64_t n_global_dst,
+                         int64_t row0_dst) {
+    return guarded([&] {
+        SB_CHECK(src != nullptr && dst != nullptr, "gather_rows: null context");
+        bind(dst);
+        gather_rows(src, rows, n_rows, dst, n_global_dst, row0_dst);
+    });
 }
 
 int snapb200_get_vector(snapb200_ctx* c, int which, double* out) {

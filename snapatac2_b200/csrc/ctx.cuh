@@ -168,6 +168,10 @@ struct snapb200_ctx {
     // operator applications but each costs less than half.
     int block = 4;
 
+    // block-wise load in progress (load_begin / load_append / load_end): rows and entries appended so far
+    bool appending = false;
+    int64_t app_rows = 0, app_nnz = 0;
+
     // user feature weights (host copy, optional)
     std::vector<double> user_weights;
 
@@ -246,6 +250,8 @@ void prepare(snapb200_ctx* c, double* idf_out, double* degree_out);
 void view_norms(snapb200_ctx* c, double* idf_out, double* rho_out);
 double view_frobenius(snapb200_ctx* c, const int64_t* sample_rows, int64_t ns_local);
 void combine_views(snapb200_ctx* main, snapb200_ctx** views, const double* cv, int n_views, double* degree_out);
+void gather_rows(snapb200_ctx* src, const int64_t* rows_host, int64_t nr, snapb200_ctx* dst, int64_t n_global_dst,
+                 int64_t row0_dst);
 // IDF (or user) weights and weighted row norms of the loaded matrix into device buffers (no transpose)
 void weights_and_norms(snapb200_ctx* c, double* w_dev, double* rho_dev);
 

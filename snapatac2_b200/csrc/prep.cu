@@ -840,4 +840,80 @@ void combine_views(snapb200_ctx* main, snapb200_ctx** views, const double* cv, i
     main->views.assign(views + 1, views + n_views);
 }
 
+// --------------------------------------------------------------------------
+// Row gather between two contexts on the same device: dst <- the rows `rows` (local ids, any order)
+// of src's resident CSR.  The Nystrom path takes its landmark rows this way (select_axis(0, ..),
+// embedding.rs:95-99) without a round trip through the host.
+// --------------------------------------------------------------------------
+namespace {
+__global__ void gather_len_kernel(const int64_t* __restrict__ ptr, const int64_t* __restrict__ rows, int64_t nr,
+                                  int32_t* __restrict__ len) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < nr) len[i] = static_cast<int32_t>(ptr[rows[i] + 1] - ptr[rows[i]]);
+}
+__global__ void gather_copy_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, const float* __restrict__ val,
+                                   const int64_t* __restrict__ rows, int64_t nr, const int64_t* __restrict__ optr,
+                                   int32_t* __restrict__ oidx, float* __restrict__ oval) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+    for (int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5; i < nr; i += nwarps) {
+        const int64_t s = ptr[rows[i]], e = ptr[rows[i] + 1], o = optr[i];
+        for (int64_t p = s + lane; p < e; p += 32) {
+            oidx[o + (p - s)] = idx[p];
+            if (val) oval[o + (p - s)] = val[p];
+        }
+    }
+}
+}  // namespace
+
+void gather_rows(snapb200_ctx* src, const int64_t* rows_host, int64_t nr, snapb200_ctx* dst, int64_t n_global_dst,
+                 int64_t row0_dst) {
+    SB_CHECK(src->loaded, "gather_rows: no matrix loaded in the source context");
+    SB_CHECK(src != dst && src->device == dst->device, "gather_rows: need two contexts on the same device");
+    SB_CHECK(nr >= 0 && row0_dst >= 0 && row0_dst + nr <= n_global_dst, "gather_rows: bad shard geometry");
+    for (int64_t i = 0; i < nr; ++i) SB_CHECK(rows_host[i] >= 0 && rows_host[i] < src->n_local, "gather_rows: row out of range");
+    if (src->stream != dst->stream) SB_CUDA(cudaStreamSynchronize(src->stream));
+    cudaStream_t st = dst->stream;
+    const Csr& X = src->X;
+    Csr& Y = dst->X;
+    dst->loaded = false;
+    dst->prepared = false;
+    dst->proj_ready = false;
+    dst->views.clear();
+    dst->nnz_mode = -1;
+    dst->S1.clear(); dst->S2.clear(); dst->Xt.clear(); dst->xt_built = false; dst->XtT.clear();
+    DevBuf<int64_t> rows;
+    DevBuf<int32_t> len;
+    rows.alloc(std::max<int64_t>(1, nr));
+    len.alloc(std::max<int64_t>(1, nr));
+    Y.nrows = nr;
+    Y.ncols = X.ncols;
+    Y.ptr.alloc(nr + 1);
+    if (nr > 0) {
+        SB_CUDA(cudaMemcpyAsync(rows.p, rows_host, sizeof(int64_t) * nr, cudaMemcpyHostToDevice, st));
+        gather_len_kernel<<<grid1d(nr), 256, 0, st>>>(X.ptr.p, rows.p, nr, len.p);
+        SB_LAUNCH_CHECK();
+    }
+    exclusive_scan_i32_to_i64(dst, len.p, Y.ptr.p, nr);
+    int64_t nnz = 0;
+    SB_CUDA(cudaMemcpyAsync(&nnz, Y.ptr.p + nr, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    Y.nnz = nnz;
+    Y.idx.alloc(std::max<int64_t>(1, nnz));
+    if (X.has_values()) Y.val.alloc(std::max<int64_t>(1, nnz)); else Y.val.release();
+    if (nr > 0 && nnz > 0) {
+        gather_copy_kernel<<<grid_for_rows(dst, nr), 256, 0, st>>>(X.ptr.p, X.idx.p, X.val.p, rows.p, nr, Y.ptr.p, Y.idx.p,
+                                                                  Y.val.p);
+        SB_LAUNCH_CHECK();
+    }
+    count_launch(dst, 2);
+    SB_CUDA(cudaStreamSynchronize(st));
+    dst->n_local = nr;
+    dst->n_global = n_global_dst;
+    dst->row0 = row0_dst;
+    dst->m = src->m;
+    dst->loaded = true;
+    dst->stats.nnz_local = nnz;
+}
+
 }  // namespace snapb

@@ -337,7 +337,8 @@ void prepare_projection(snapb200_ctx* c) {
 
 void project(snapb200_ctx* c, bool transposed, const float* in_host, int k, float* out_host) {
     SB_CHECK(k >= 1, "project: k must be positive");
-    SB_CHECK(!transposed || c->prepared, "project_t: call prepare first");
+    // (the transposed product runs over the feature-major tiled copy when prepare() built it, otherwise over
+    //  a CSR transpose built on first use)
     if (!c->proj_ready) prepare_projection(c);
     // column blocks of the width the tiled copies were built for (8 on the CSR path)
     const int b = (c->S2.built && (c->S2.b == 4 || c->S2.b == 8)) ? c->S2.b : 8;

@@ -50,6 +50,38 @@ def allgather_objects(obj) -> list:
     return out
 
 
+def allreduce_array(arr: np.ndarray, op: str = "sum") -> np.ndarray:
+    """Element-wise all-reduce of a small host array over the torch.distributed world (identity
+    without one).  Used for host-side bookkeeping only (chunk sums of the Nystrom normalisation,
+    document frequencies in streamed mode) -- the data path reduces inside the library over NCCL."""
+    if not is_distributed():
+        return arr
+    import torch
+    import torch.distributed as td
+    rop = {"sum": td.ReduceOp.SUM, "min": td.ReduceOp.MIN, "max": td.ReduceOp.MAX}[op]
+    t = torch.from_numpy(np.ascontiguousarray(arr).copy())
+    try:
+        td.all_reduce(t, op=rop)
+    except RuntimeError:            # NCCL-only process group: reduce on the device
+        t = t.cuda()
+        td.all_reduce(t, op=rop)
+        t = t.cpu()
+    return t.numpy()
+
+
+def chunk_overlaps(row0: int, n_local: int, chunk_size: int):
+    """Global ``chunk_size`` row blocks that overlap the shard ``[row0, row0 + n_local)``:
+    yields ``(chunk index, local start, local stop)``."""
+    if n_local <= 0:
+        return
+    c = row0 // chunk_size
+    while c * chunk_size < row0 + n_local:
+        lo = max(c * chunk_size, row0) - row0
+        hi = min((c + 1) * chunk_size, row0 + n_local) - row0
+        yield c, lo, hi
+        c += 1
+
+
 def shard_offsets(n_locals: list[int]) -> list[int]:
     """Global row offset of every rank's shard from the list of shard sizes."""
     offs, run = [], 0

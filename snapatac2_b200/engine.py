@@ -109,6 +109,39 @@ class Engine:
             X.sum_duplicates()      # sorts the rows and merges duplicates (scipy's canonical format)
             attempt(X)
 
+    def load_blocks(self, blocks, m, n_global=None, row0=0, rows_hint=0, nnz_hint=0):
+        """Assemble this rank's shard on the device from an iterable of scipy CSR row blocks (the
+        chunks of a backed AnnData): the host never holds more than one block.  ``n_global=None``:
+        the blocks are the whole matrix."""
+        _lib.check(self._lib.snapb200_load_begin(self._ctx, int(m), int(rows_hint), int(nnz_hint)))
+        for blk in blocks:
+            if not sp.issparse(blk):
+                blk = sp.csr_matrix(np.asarray(blk))
+            blk = blk.tocsr()
+            if blk.shape[1] != m:
+                raise ValueError("every row block must have the matrix's number of columns")
+            if not blk.has_sorted_indices:      # per block: cheap next to reading it from disk
+                blk = blk.copy()
+                blk.sum_duplicates()
+            indptr = np.ascontiguousarray(blk.indptr)
+            indices = np.ascontiguousarray(blk.indices)
+            values = np.ascontiguousarray(blk.data)
+            if _lib.value_kind(values.dtype) is None:
+                values = values.astype(np.float64)
+            bits = lambda a: 8 * a.itemsize
+            _lib.check(self._lib.snapb200_load_append(
+                self._ctx, int(blk.shape[0]), _lib.ptr(indptr), bits(indptr), _lib.ptr(indices), bits(indices),
+                _lib.ptr(values), int(_lib.value_kind(values.dtype))))
+        _lib.check(self._lib.snapb200_load_end(self._ctx, -1 if n_global is None else int(n_global), int(row0)))
+        n, m2, _ = self.shape()
+        self.n_local, self.m, self.row0 = int(n), int(m2), int(row0)
+        self.n_global = self.n_local if n_global is None else int(n_global)
+
+    def set_geometry(self, n_global, row0):
+        """Place an already loaded shard inside the global matrix (block-wise loads learn their own size last)."""
+        _lib.check(self._lib.snapb200_set_geometry(self._ctx, int(n_global), int(row0)))
+        self.n_global, self.row0 = int(n_global), int(row0)
+
     def generate(self, spec, row0=0, n_local=None):
         """Synthetic planted-cluster rows generated on the device."""
         n_local = spec.n - row0 if n_local is None else n_local
@@ -200,6 +233,14 @@ class Engine:
         _lib.check(self._lib.snapb200_get_vector(self._ctx, code, _lib.ptr(out)))
         return out
 
+    def gather_rows_into(self, rows_local, dst: "Engine", n_global=None, row0=0):
+        """``dst`` <- the rows ``rows_local`` of this engine's resident matrix (device to device)."""
+        rows = np.ascontiguousarray(rows_local, dtype=np.int64)
+        n_global = rows.size if n_global is None else n_global
+        _lib.check(self._lib.snapb200_gather_rows(self._ctx, _lib.ptr(rows) if rows.size else None, int(rows.size), dst._ctx,
+                                                  int(n_global), int(row0)))
+        dst.n_local, dst.n_global, dst.row0, dst.m = int(rows.size), int(n_global), int(row0), self.m
+
     def prepare_projection(self, want_outputs=True):
         """What :meth:`project` needs (weights, row norms, cell-major tiled copy), without the
         transpose.  Returns ``(w[m], rho[n_local])`` (or None, None)."""
@@ -217,12 +258,20 @@ class Engine:
         return out
 
     def project_t(self, U):
-        """``Xhat.T @ U`` (U: n_local x k) -> m x k, summed over the row shards; needs prepare()."""
+        """``Xhat.T @ U`` (U: n_local x k) -> m x k, summed over the row shards."""
         U = np.ascontiguousarray(U, dtype=np.float32)
         assert U.ndim == 2 and U.shape[0] == self.n_local
         out = np.empty((self.m, U.shape[1]), dtype=np.float32)
         _lib.check(self._lib.snapb200_project(self._ctx, 1, _lib.ptr(U), int(U.shape[1]), _lib.ptr(out)))
         return out
+
+    def project_t_ones(self):
+        """``Xhat.T @ 1`` of the loaded block (streamed Nystrom degree pass, on a context outside the
+        communicator): the column sums of the normalised rows, fp32 through the SpMM path."""
+        ones = np.ones((self.n_local, 1), dtype=np.float32)
+        out = np.empty((self.m, 1), dtype=np.float32)
+        _lib.check(self._lib.snapb200_project(self._ctx, 1, _lib.ptr(ones), 1, _lib.ptr(out)))
+        return out[:, 0].astype(np.float64)
 
     def operator_apply(self, V):
         V = np.ascontiguousarray(V, dtype=np.float32)

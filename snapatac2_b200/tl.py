@@ -91,24 +91,79 @@ def _feature_mask(features, n_vars, feature_weights):
 
 
 def _get_csr(adata):
+    """``adata.X`` as a scipy CSR matrix -- or, when it is not one (a backed AnnData element, a lazy
+    array, a generator of row blocks), a :class:`RowBlocks` source the engine assembles on the device
+    block by block (``with_anndata!`` dispatch, utils/anndata.rs:174-236: in-memory and backed data
+    take the same path)."""
     X = adata.X
-    if hasattr(X, "__getitem__") and not sp.issparse(X) and not isinstance(X, np.ndarray):
-        X = X[...]   # backed / lazy element
     if isinstance(X, np.ndarray):
         X = sp.csr_matrix(X)
-    if not sp.issparse(X) or X.format != "csr":
-        raise ValueError("adata.X must be a CSR matrix")
-    return X
+    if sp.issparse(X):
+        if X.format != "csr":
+            raise ValueError("adata.X must be a CSR matrix")
+        return X
+    return RowBlocks(X, adata.n_vars)
+
+
+class RowBlocks:
+    """Row-block view of an ``adata.X`` that is not an in-memory scipy matrix.
+
+    Accepted sources, in this order: an object with ``chunked(chunk_size)`` (SnapATAC2's backed
+    elements; yields ``(block, start, end)`` or blocks), an object with ``shape`` and row slicing
+    (``anndata``'s backed sparse dataset, h5py-style lazy arrays), or any iterable of CSR blocks
+    (a one-shot generator works: the data is only walked once)."""
+
+    def __init__(self, source, n_vars):
+        self.source = source
+        self.n_vars = int(n_vars)
+
+    def blocks(self, chunk_size):
+        src = self.source
+        if hasattr(src, "chunked"):
+            for item in src.chunked(chunk_size):
+                yield item[0] if isinstance(item, tuple) else item
+        elif hasattr(src, "shape") and hasattr(src, "__getitem__"):
+            for i in range(0, int(src.shape[0]), chunk_size):
+                yield src[i:i + chunk_size]
+        else:
+            yield from src
+
+
+def _load(engine: Engine, X, chunk_size=20000):
+    """Load ``X`` (scipy CSR or :class:`RowBlocks`) as this rank's shard; returns ``(n_global, row0)``."""
+    rank, ws = dist.world()
+    if isinstance(X, RowBlocks):
+        engine.load_blocks(X.blocks(chunk_size), X.n_vars)
+        n_local = engine.n_local
+        if ws > 1:
+            n_locals = dist.allgather_ints(n_local)
+            engine.set_geometry(sum(n_locals), dist.shard_offsets(n_locals)[rank])
+        return engine.n_global, engine.row0
+    n_local = X.shape[0]
+    if ws > 1:
+        n_locals = dist.allgather_ints(n_local)
+        n_global, row0 = sum(n_locals), dist.shard_offsets(n_locals)[rank]
+    else:
+        n_global, row0 = n_local, 0
+    engine.load_csr(X, n_global=n_global, row0=row0)
+    return n_global, row0
 
 
 def spectral_embedding(engine: Engine, X, selected_features, n_components, random_state,
                        feature_weights=None, *, n_global=None, row0=0, binarized=None,
-                       tol=0.0, block=0, max_basis=0, max_ops=0, return_parts=False, scale_by_sqrt_eval=False):
+                       tol=0.0, block=0, max_basis=0, max_ops=0, return_parts=False, scale_by_sqrt_eval=False,
+                       chunk_size=20000):
     """Counterpart of the PyO3 entry ``internal.spectral_embedding``
     (embedding.rs:24-59): load -> [select] -> [weights] -> prepare -> eigsh.
     ``scale_by_sqrt_eval``: see :func:`_weight_by_sd`."""
-    mask, fw = _feature_mask(selected_features, X.shape[1], feature_weights)
-    engine.load_csr(X, n_global=n_global, row0=row0, binarized=binarized)
+    blocks = isinstance(X, RowBlocks)
+    mask, fw = _feature_mask(selected_features, X.n_vars if blocks else X.shape[1], feature_weights)
+    if blocks:                      # backed / lazy X: assembled on the device block by block
+        engine.load_blocks(X.blocks(chunk_size), X.n_vars)
+        if n_global is not None:
+            engine.set_geometry(n_global, row0)
+    else:
+        engine.load_csr(X, n_global=n_global, row0=row0, binarized=binarized)
     if mask is not None:
         engine.select_features(mask)
     engine.set_feature_weights(fw)
@@ -134,9 +189,19 @@ def _weight_by_sd(evals, evecs, already_scaled):
 
 def orthogonalize(evals, evecs):
     """``orthogonalize`` of the reference wrapper (tools/_embedding.py:397-413): turns the Nystrom
-    extension into an orthogonal eigenbasis (k x k algebra after one thin SVD; host side)."""
-    _, sigma, vt = np.linalg.svd(evecs, full_matrices=False)
-    v = vt.T
+    extension into an orthogonal eigenbasis (k x k algebra after one thin SVD; host side).
+
+    Row-sharded (``torchrun``): ``evecs`` is this rank's block of rows.  The singular values and right
+    singular vectors of the whole matrix come from its k x k Gram matrix, summed over the shards
+    (``sigma^2, V = eigh(U^T U)``); everything after that is k x k or row-local."""
+    if dist.world()[1] > 1:
+        gram = dist.allreduce_array(evecs.T @ evecs, "sum")
+        s2, v = np.linalg.eigh(gram)
+        order = np.argsort(s2)[::-1]
+        sigma, v = np.sqrt(np.maximum(s2[order], 0.0)), v[:, order]
+    else:
+        _, sigma, vt = np.linalg.svd(evecs, full_matrices=False)
+        v = vt.T
     b = np.multiply(v.T, evals.reshape((1, -1))) @ v
     b = b * sigma.reshape((-1, 1)) * sigma.reshape((1, -1))
     evals_new, evecs_new = np.linalg.eig(b)
@@ -146,6 +211,68 @@ def orthogonalize(evals, evecs):
     return evals_new, evecs @ v @ evecs_new
 
 
+def _nystrom_normalise(q, v, chunk_size, n_global, row0):
+    """The per-chunk degree normalisation of ``nystrom`` (embedding.rs:224-227), over ``chunk_size`` row
+    blocks of the GLOBAL row order exactly as the reference streams them; a block that spans two
+    shards gets its column sums and its smallest positive degree from both (two tiny all-reduces)."""
+    n_chunks = -(-n_global // chunk_size)
+    k = q.shape[1]
+    sums = np.zeros((n_chunks, k), dtype=np.float64)
+    spans = list(dist.chunk_overlaps(row0, q.shape[0], chunk_size))
+    for c, lo, hi in spans:
+        sums[c] = q[lo:hi].sum(axis=0)
+    sums = dist.allreduce_array(sums, "sum")
+    mins = np.full(n_chunks, np.inf, dtype=np.float64)
+    dds = {}
+    for c, lo, hi in spans:
+        t = sums[c] * v                                      # :224
+        dd = q[lo:hi] @ t                                    # :225
+        dds[c] = dd
+        pos = dd[dd > 0]
+        if pos.size:
+            mins[c] = pos.min()
+    mins = dist.allreduce_array(mins, "min")
+    for c, lo, hi in spans:
+        dd = dds[c]
+        dd[dd <= 0] = mins[c]                                # :226
+        q[lo:hi] /= np.sqrt(dd)[:, None]                     # :227
+    return q
+
+
+def _streamed_degrees(device, chunk_csr, n_local, chunk_size, w):
+    """``compute_degrees`` (embedding.rs:328-360) with one ``chunk_size`` block of cells on the device at a
+    time: pass 1 accumulates the column sums of the normalised rows (all-reduced over the shards), pass 2
+    forms ``d = Xhat colsum - 1`` block by block.  The blocks go through a context of their own that is
+    not part of the communicator (shards have different numbers of blocks)."""
+    csum = np.zeros(w.shape[0], dtype=np.float64)
+    solo = Engine(device)
+    try:
+        for i in range(0, n_local, chunk_size):
+            solo.load_csr(chunk_csr(i))
+            solo.set_feature_weights(w)
+            solo.prepare_projection(want_outputs=False)
+            csum += solo.project_t_ones()
+        csum = dist.allreduce_array(csum, "sum")
+        deg_local = np.empty(n_local, dtype=np.float64)
+        for i in range(0, n_local, chunk_size):
+            solo.load_csr(chunk_csr(i))
+            solo.set_feature_weights(w)
+            deg_local[i:i + chunk_size] = solo.project(csum[:, None].astype(np.float32))[:, 0].astype(np.float64) - 1.0
+    finally:
+        solo.close()
+    return deg_local
+
+
+def _draw_landmarks(n, sample_size, degree_all):
+    """``rand::seq::index::sample`` / ``sample_weighted`` with ``StdRng::seed_from_u64(2023)`` (embedding.rs:87-94)
+    cannot be reproduced outside Rust: numpy's ``default_rng(2023)`` stands in (identical on every rank)."""
+    rng = np.random.default_rng(2023)
+    if degree_all is not None:                               # compute_probs (:362-365)
+        p = 1.0 / degree_all
+        return rng.choice(n, size=sample_size, replace=False, p=p / p.sum())
+    return rng.choice(n, size=sample_size, replace=False)
+
+
 def spectral_embedding_nystrom(engine: Engine, X, selected_features, n_components, sample_size,
                                weighted_by_degree, chunk_size, feature_weights=None, *, landmarks=None,
                                seed_engine: Engine | None = None, tol=0.0, block=0, return_parts=False,
@@ -153,42 +280,59 @@ def spectral_embedding_nystrom(engine: Engine, X, selected_features, n_component
     """Counterpart of ``internal.spectral_embedding_nystrom`` (embedding.rs:61-129): spectral
     embedding of ``sample_size`` landmark cells, extended to every cell (``nystrom``, :194-267).
 
-    Device work: IDF weights and row norms of all cells, the embedding of the landmark
-    matrix (a second context on the same GPU: load / prepare / eigsh with the global
-    weights), ``seed.T @ evecs`` (``snapb200_project`` transposed) and ``sample @ (...)`` for
-    every cell (``snapb200_project``).  The per-chunk degree normalisation (:224-227, over
-    ``chunk_size`` row blocks exactly as the reference streams them) is n x k algebra on
-    the host.  Landmarks: the reference draws them with Rust's ``StdRng::seed_from_u64(2023)``
-    (:87-94); that stream is not reproduced -- numpy's ``default_rng(2023)`` is used instead
-    (pass ``landmarks`` to fix them).  Single GPU.
+    Device work: IDF weights and row norms of all cells, the embedding of the landmark rows (a
+    second context that shares the stream and communicator: device-side row gather, prepare and
+    eigsh with the global weights), ``seed.T @ evecs`` (``snapb200_project`` transposed, summed
+    over the row shards) and ``sample @ (...)`` for every cell (``snapb200_project``).  The per-chunk
+    degree normalisation (:224-227) is n x k algebra on the host over the same global ``chunk_size``
+    row blocks the reference streams.  Landmarks: see :func:`_draw_landmarks`; pass ``landmarks``
+    (global row ids) to fix them.
 
-    ``stream=True`` keeps only one ``chunk_size`` block of cells on the device at a time, the
-    way the reference iterates a backed AnnData (:76-84, :109-118): document frequencies are
-    accumulated chunk by chunk, then every chunk is loaded, normalised and projected on its
-    own.  Default: stream when the matrix would not fit next to its tiled copy (> 6e9 stored
-    entries).  Degree-weighted landmark sampling needs the degrees of all cells and is only
-    available without streaming."""
-    if dist.world()[1] > 1:
-        raise NotImplementedError("the Nystrom path runs on a single GPU")
-    mask, fw = _feature_mask(selected_features, X.shape[1], feature_weights)
-    n = X.shape[0]
-    cols = None if mask is None else np.flatnonzero(mask)
-    if stream is None:
-        stream = X.nnz > 6_000_000_000
-    degree = None
+    Row-sharded under ``torchrun``: every rank passes its block of cells (or ``X=None`` if the engine
+    already holds it, e.g. generated on the device); the landmark matrix is itself row-sharded --
+    every rank contributes the landmarks that fall into its block -- and embedded by the ordinary
+    distributed solve, so no rows ever travel between GPUs.
+
+    ``stream=True`` keeps only one ``chunk_size`` block of cells on the device at a time, the way
+    the reference iterates a backed AnnData (:76-84, :109-118): document frequencies are
+    accumulated chunk by chunk, degree-weighted sampling takes two more streaming passes
+    (``compute_degrees``, :328-360), then every chunk is loaded, normalised and projected on its
+    own.  Default: stream when the shard would not fit next to its tiled copy (> 6e9 stored entries).
+    """
+    rank, world = dist.world()
+    resident = X is None
+    if resident:
+        n_local, m_all, _ = engine.shape()
+        mask, fw, cols = None, feature_weights, None
+        stream = False
+    else:
+        mask, fw = _feature_mask(selected_features, X.shape[1], feature_weights)
+        n_local = X.shape[0]
+        cols = None if mask is None else np.flatnonzero(mask)
+        if stream is None:
+            stream = X.nnz > 6_000_000_000
+    if world > 1:
+        n_locals = dist.allgather_ints(n_local)
+        n, row0 = sum(n_locals), dist.shard_offsets(n_locals)[rank]
+    else:
+        n, row0 = n_local, 0
+
+    def chunk_csr(i):
+        Xc = X[i:i + chunk_size]
+        if cols is not None:
+            Xc = Xc[:, cols]
+        return sp.csr_matrix(Xc)
+
+    degree_all = None
     if stream:
-        if landmarks is None and weighted_by_degree:
-            raise NotImplementedError("degree-weighted landmarks need the whole matrix on the device (stream=False)")
         if fw is not None:
             w = np.asarray(fw, dtype=np.float64)
         else:                                               # idf_from_chunks (:288-312)
             m_sel = X.shape[1] if cols is None else cols.size
             df = np.zeros(m_sel, dtype=np.int64)
-            for i in range(0, n, chunk_size):
-                Xc = X[i:i + chunk_size]
-                if cols is not None:
-                    Xc = Xc[:, cols]
-                df += np.bincount(Xc.indices, minlength=m_sel)
+            for i in range(0, n_local, chunk_size):
+                df += np.bincount(chunk_csr(i).indices, minlength=m_sel)
+            df = dist.allreduce_array(df, "sum")
             if np.all(df == df[0]):
                 w = np.ones(m_sel, dtype=np.float64)
             else:
@@ -196,59 +340,73 @@ def spectral_embedding_nystrom(engine: Engine, X, selected_features, n_component
                 d[d == 0] = 1.0
                 d[d == n] = n - 1.0
                 w = np.log(n / d)
+        if landmarks is None and weighted_by_degree:        # compute_degrees (:328-360): two streaming passes
+            deg_local = _streamed_degrees(engine.device, chunk_csr, n_local, chunk_size, w)
+            degree_all = np.concatenate(dist.allgather_objects(deg_local)) if world > 1 else deg_local
     else:
-        engine.load_csr(X)
-        if mask is not None:
-            engine.select_features(mask)
+        if not resident:
+            engine.load_csr(X, n_global=n, row0=row0)
+            if mask is not None:
+                engine.select_features(mask)
         engine.set_feature_weights(fw)
         if landmarks is None and weighted_by_degree:
-            _, degree = engine.prepare()                    # compute_degrees (:328-360)
+            _, deg_local = engine.prepare()                 # compute_degrees (:328-360)
+            degree_all = np.concatenate(dist.allgather_objects(deg_local)) if world > 1 else deg_local
         w, _rho = engine.prepare_projection()               # idf over all cells (:76-84) + row norms
     if landmarks is None:
-        rng = np.random.default_rng(2023)
-        if weighted_by_degree:                              # compute_probs (:362-365)
-            p = 1.0 / degree
-            landmarks = rng.choice(n, size=sample_size, replace=False, p=p / p.sum())
-        else:
-            landmarks = rng.choice(n, size=sample_size, replace=False)
-    landmarks = np.asarray(landmarks, dtype=np.int64)
+        landmarks = _draw_landmarks(n, sample_size, degree_all)
+    lm_given = np.asarray(landmarks, dtype=np.int64)
+    lm_order = np.argsort(lm_given, kind="stable")
+    landmarks = lm_given[lm_order]                           # row order of the seed matrix is immaterial: ascending
+    mine = landmarks[(landmarks >= row0) & (landmarks < row0 + n_local)] - row0
+    if world > 1:
+        counts = dist.allgather_ints(mine.size)
+        s_total, s_row0 = sum(counts), dist.shard_offsets(counts)[rank]
+    else:
+        s_total, s_row0 = int(mine.size), 0
 
-    # landmark rows (host slice, :95-99), embedded on a second context with the global weights
-    Xs = X[landmarks]
-    if mask is not None:
-        Xs = Xs[:, np.flatnonzero(mask)]
+    # landmark rows (:95-99), embedded on a second context with the global weights
     own_seed = seed_engine is None
-    seed = Engine(engine.device) if own_seed else seed_engine
+    if own_seed:
+        seed = Engine(engine.device)
+        engine.attach_view(seed)                             # same stream, same communicator
+    else:
+        seed = seed_engine
     try:
-        seed.load_csr(sp.csr_matrix(Xs))
+        if stream:
+            Xs = X[mine]
+            if cols is not None:
+                Xs = Xs[:, cols]
+            seed.load_csr(sp.csr_matrix(Xs), n_global=s_total, row0=s_row0)
+        else:
+            engine.gather_rows_into(mine, seed, n_global=s_total, row0=s_row0)
         seed.set_feature_weights(w)
         _, d = seed.prepare()
         v, u = seed.eigsh(n_components, seed=0, tol=tol, block=block)   # spectral_mf(seed, k, 0) (:104)
         u = u / np.sqrt(d)[:, None]                          # :206-210
         u = u / v[None, :]                                   # :211-215
-        proj = seed.project_t(u)                             # seed.T @ evecs
+        proj = seed.project_t(u)                             # seed.T @ evecs, summed over the shards
     finally:
         if own_seed:
             seed.close()
     if stream:                                               # sample @ (seed.T @ evecs), chunk by chunk
-        q = np.empty((n, proj.shape[1]), dtype=np.float64)
-        for i in range(0, n, chunk_size):
-            Xc = X[i:i + chunk_size]
-            if cols is not None:
-                Xc = Xc[:, cols]
-            engine.load_csr(sp.csr_matrix(Xc))
-            engine.set_feature_weights(w)
-            q[i:i + chunk_size] = engine.project(proj)
+        q = np.empty((n_local, proj.shape[1]), dtype=np.float64)
+        solo = Engine(engine.device)
+        try:
+            for i in range(0, n_local, chunk_size):
+                solo.load_csr(chunk_csr(i))
+                solo.set_feature_weights(w)
+                q[i:i + chunk_size] = solo.project(proj)
+        finally:
+            solo.close()
     else:
         q = engine.project(proj).astype(np.float64)          # ... or for every cell at once
-    for i in range(0, n, chunk_size):                        # :224-227, per streamed chunk
-        qc = q[i:i + chunk_size]
-        t = qc.sum(axis=0) * v
-        dd = qc @ t
-        dd[dd <= 0] = np.min(dd[dd > 0])
-        qc /= np.sqrt(dd)[:, None]
+    q = _nystrom_normalise(q, v, chunk_size, n, row0)
     if return_parts:
-        return v, q, w, d, landmarks
+        if world == 1:                                       # landmark degrees back in the order the caller gave
+            d_sorted, d = d, np.empty_like(d)
+            d[lm_order] = d_sorted
+        return v, q, w, d, lm_given
     return v, q
 
 
@@ -315,6 +473,13 @@ def spectral(
     if sample_size < n_sample:                                      # :257-265
         logging.getLogger(__name__).info("Perform spectral embedding using the Nystrom algorithm...")
         # like the reference (:263), the Nystrom call does not receive feature_weights: IDF from all cells
+        if isinstance(X, RowBlocks):     # backed / lazy X: assemble the shard on the device first, then as resident data
+            mask, _ = _feature_mask(features, X.n_vars, None)
+            eng.load_blocks(X.blocks(chunk_size), X.n_vars)
+            eng.set_geometry(n_global, row0)
+            if mask is not None:
+                eng.select_features(mask)
+            X, features = None, None
         v, u = spectral_embedding_nystrom(eng, X, features, n_comps, sample_size, sample_method != "random",
                                           chunk_size, tol=tol, block=block)
         evals, evecs = orthogonalize(v, u)
@@ -322,7 +487,7 @@ def spectral(
     else:
         evals, evecs = spectral_embedding(eng, X, features, n_comps, random_state, feature_weights,
                                           n_global=n_global, row0=row0, tol=tol, block=block,
-                                          scale_by_sqrt_eval=weighted_by_sd)                     # :249
+                                          scale_by_sqrt_eval=weighted_by_sd, chunk_size=chunk_size)   # :249
         scaled = weighted_by_sd
     logging.getLogger(__name__).info("spectral: %s", eng.stats())
 
@@ -351,7 +516,7 @@ def _view_engines(engine: Engine, n_views: int) -> list[Engine]:
 
 def multi_spectral_embedding(engine: Engine, xs, selected_features, weights, n_components, random_state,
                              *, sample_rows=None, tol=0.0, block=0, return_parts=False, container="csr_matrix",
-                             scale_by_sqrt_eval=False):
+                             scale_by_sqrt_eval=False, n_local=None, chunk_size=20000):
     """Counterpart of ``internal.multi_spectral_embedding`` (embedding.rs:388-452), entirely on the
     device and without the column concatenation ever being formed.
 
@@ -370,7 +535,8 @@ def multi_spectral_embedding(engine: Engine, xs, selected_features, weights, n_c
     ``torchrun`` every rank passes its block of cells of every view.
     """
     rank, world = dist.world()
-    n_local = xs[0].shape[0]
+    if n_local is None:
+        n_local = next(X.shape[0] for X in xs if not isinstance(X, RowBlocks))
     if world > 1:      # every rank passes its own contiguous block of cells, the same block of every view
         n_locals = dist.allgather_ints(n_local)
         n_global, row0 = sum(n_locals), dist.shard_offsets(n_locals)[rank]
@@ -386,12 +552,21 @@ def multi_spectral_embedding(engine: Engine, xs, selected_features, weights, n_c
     views = _view_engines(engine, len(xs))
     norms, idfs = [], []
     for eng, X, sel in zip(views, xs, selected_features):
-        if not sp.issparse(X) or X.format != "csr":
-            X = sp.csr_matrix(X)
-        if X.shape[0] != n_local:
-            raise ValueError("all views must hold the same cells")
-        mask, _ = _feature_mask(sel, X.shape[1], None)
-        eng.load_csr(X, n_global=n_global, row0=row0)
+        if isinstance(X, RowBlocks):                # backed / lazy view: assembled on the device block by block
+            if container != "csr_matrix":
+                raise NotImplementedError("the csr_array reading needs the sampled rows on the host (in-memory views only)")
+            mask, _ = _feature_mask(sel, X.n_vars, None)
+            eng.load_blocks(X.blocks(chunk_size), X.n_vars)
+            if eng.n_local != n_local:
+                raise ValueError("all views must hold the same cells")
+            eng.set_geometry(n_global, row0)
+        else:
+            if not sp.issparse(X) or X.format != "csr":
+                X = sp.csr_matrix(X)
+            if X.shape[0] != n_local:
+                raise ValueError("all views must hold the same cells")
+            mask, _ = _feature_mask(sel, X.shape[1], None)
+            eng.load_csr(X, n_global=n_global, row0=row0)
         if mask is not None:
             eng.select_features(mask)
         eng.set_feature_weights(None)           # the views always use their own IDF (:413)
@@ -437,7 +612,7 @@ def multi_spectral(adatas, n_comps: int = 30, features="selected", weights=None,
     eng = _check_engine(engine) if engine is not None else default_engine()
     evals, evecs = multi_spectral_embedding(eng, [_get_csr(a) for a in adatas], features, weights,
                                             n_comps, random_state, sample_rows=sample_rows, container=container,
-                                            scale_by_sqrt_eval=weighted_by_sd)                # :533
+                                            scale_by_sqrt_eval=weighted_by_sd, n_local=adatas[0].n_obs)   # :533
     if weighted_by_sd:                                                      # :535-538
         evals, evecs = _weight_by_sd(evals, evecs, True)
     return evals, evecs

@@ -97,6 +97,23 @@ if rank == 0:
     np.testing.assert_allclose(ev_m, ev_o, rtol=1e-4)
     assert eigvec_agreement(ev_o, evec_o, emb_all).min() >= 0.999
     print(f"MULTIVIEW_OK world={world}")
+# ---- Nystrom path on row shards (embedding.rs:61-129): every rank passes its block, the landmark matrix
+#      is itself sharded (each rank contributes the landmarks inside its block); against the CPU oracle
+lm = np.sort(np.random.RandomState(11).choice(spec.n, 2500, replace=False))
+kn, chunk = 10, 2000
+v_n, q_n = tl.spectral_embedding_nystrom(eng, X_local, None, kn, lm.size, False, chunk, landmarks=lm)
+parts_n = [None] * world
+td.gather_object(q_n, parts_n if rank == 0 else None, dst=0)
+if rank == 0:
+    import oracle
+    from conftest import eigvec_agreement
+    XA = synth.generate_csr(spec, dtype=np.float64)
+    ev_o, q_o = oracle.spectral_embedding_nystrom(XA, None, kn, lm, chunk)
+    q_all = np.concatenate(parts_n, axis=0)
+    np.testing.assert_allclose(v_n, ev_o, rtol=1e-4)
+    assert eigvec_agreement(ev_o, q_o, q_all).min() >= 0.999
+    np.testing.assert_allclose(np.linalg.norm(q_all, axis=0), np.linalg.norm(q_o, axis=0), rtol=1e-3)
+    print(f"NYSTROM_OK world={world}")
 td.barrier()
 eng.close()
 td.destroy_process_group()

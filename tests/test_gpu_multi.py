@@ -28,3 +28,4 @@ def test_shard_invariance(mode):
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "MULTI_OK" in res.stdout
     assert "MULTIVIEW_OK" in res.stdout
+    assert "NYSTROM_OK" in res.stdout

@@ -155,6 +155,27 @@ r0 = int(bounds[rank])
 local = rows[(rows >= r0) & (rows < r0 + mine.shape[0])] - r0
 stacked = sp.vstack(dist.allgather_objects(sp.csr_matrix(mine[local])), format="csr")
 assert (stacked != full[rows]).nnz == 0
+# Nystrom per-chunk normalisation on shards (tl._nystrom_normalise): global chunk_size blocks that span
+# the two shards take their column sums and smallest positive degree from both
+from snapatac2_b200 import tl
+rng = np.random.RandomState(5)
+q_full = rng.standard_normal((spec.n, 4))
+q_full[7] *= -30.0                                     # some non-positive degrees, to exercise the clamp
+v = np.array([1.0, 0.5, 0.3, 0.2])
+chunk = 50                                             # shards are 60 rows: chunk 1 spans both
+want = []
+for i in range(0, spec.n, chunk):
+    qc = q_full[i:i + chunk].copy()
+    t = qc.sum(axis=0) * v
+    dd = qc @ t
+    dd[dd <= 0] = np.min(dd[dd > 0])
+    want.append(qc / np.sqrt(dd)[:, None])
+want = np.vstack(want)
+got = tl._nystrom_normalise(q_full[r0:r0 + mine.shape[0]].copy(), v, chunk, spec.n, r0)
+assert np.allclose(got, want[r0:r0 + mine.shape[0]], rtol=1e-12, atol=0), np.abs(got - want[r0:r0 + mine.shape[0]]).max()
+assert [c for c, _, _ in dist.chunk_overlaps(r0, mine.shape[0], chunk)] == ([0, 1] if rank == 0 else [1, 2])
+assert np.array_equal(dist.allreduce_array(np.array([rank + 1.0, 5.0]), "sum"), [3.0, 10.0])
+assert np.array_equal(dist.allreduce_array(np.array([rank + 1.0]), "min"), [1.0])
 td.barrier()
 td.destroy_process_group()
 print("ok", rank)
