@@ -426,6 +426,7 @@ def spectral(
     engine: Engine | None = None,
     tol: float = 0.0,
     block: int = 0,
+    on_degenerate: Literal["raise", "nan"] = "raise",
 ) -> tuple[np.ndarray, np.ndarray] | None:
     """Laplacian-eigenmaps embedding, matrix-free, on the GPU.
 
@@ -436,7 +437,13 @@ def spectral(
 
     Extra keyword-only knobs: ``engine`` (reuse a context), ``tol`` (relative
     residual, default 1e-5; the reference asks ARPACK for machine precision),
-    ``block`` (Lanczos block width 4/8/16, default 4).
+    ``block`` (Lanczos block width 4/8/16, default 4), ``on_degenerate``: a cell
+    whose row is empty after feature selection, or whose degree is not positive,
+    makes the reference divide by zero -- its row norm / ``1/d`` become inf or NaN
+    (embedding.rs:146,152,323), the NaN spreads through the operator and ARPACK
+    returns NaN everywhere.  ``"raise"`` (default) reports the cells instead;
+    ``"nan"`` reproduces the reference's outcome (all-NaN eigenvalues and embedding)
+    for callers that rely on it.
     """
     np.random.seed(random_state)                                    # :223
 
@@ -485,10 +492,18 @@ def spectral(
         evals, evecs = orthogonalize(v, u)
         scaled = False
     else:
-        evals, evecs = spectral_embedding(eng, X, features, n_comps, random_state, feature_weights,
-                                          n_global=n_global, row0=row0, tol=tol, block=block,
-                                          scale_by_sqrt_eval=weighted_by_sd, chunk_size=chunk_size)   # :249
-        scaled = weighted_by_sd
+        try:
+            evals, evecs = spectral_embedding(eng, X, features, n_comps, random_state, feature_weights,
+                                              n_global=n_global, row0=row0, tol=tol, block=block,
+                                              scale_by_sqrt_eval=weighted_by_sd, chunk_size=chunk_size)   # :249
+        except RuntimeError as e:
+            if on_degenerate != "nan" or "non-positive degree" not in str(e):
+                raise
+            evals = np.full(n_comps, np.nan)
+            evecs = np.full((n_local, n_comps), np.nan)
+            scaled = False                  # (weighted_by_sd then keeps nothing: `evals[i] > 0` is false for NaN, as in the reference)
+        else:
+            scaled = weighted_by_sd
     logging.getLogger(__name__).info("spectral: %s", eng.stats())
 
     if weighted_by_sd:                                              # :286-289

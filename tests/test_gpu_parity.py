@@ -214,6 +214,12 @@ def test_degenerate_rows_are_reported(engine):
     X = sp.csr_matrix(np.array([[1, 1, 0, 0], [0, 0, 0, 0], [0, 1, 1, 0], [1, 0, 1, 1.0]]))
     with pytest.raises(RuntimeError, match="empty row or a non-positive degree"):
         tl.spectral_embedding(engine, X, None, 2, 0)
+    # on_degenerate="nan": the reference's outcome (NaN spectrum; weighted_by_sd keeps no component of it)
+    ad = MiniAnnData(X)
+    ev, emb = tl.spectral(ad, n_comps=2, features=None, weighted_by_sd=False, inplace=False, engine=engine, on_degenerate="nan")
+    assert ev.shape == (2,) and emb.shape == (4, 2) and np.isnan(ev).all() and np.isnan(emb).all()
+    ev, emb = tl.spectral(ad, n_comps=2, features=None, inplace=False, engine=engine, on_degenerate="nan")
+    assert ev.shape == (0,) and emb.shape == (4, 0)
 
 
 def test_int64_indices_and_count_dtypes(engine):
