@@ -358,7 +358,7 @@ tile_vals_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
 }
 
 // ==========================================================================
-// Bucketed transpose (opt-in: SNAPB200_TRANSPOSE=bucketed; m <= kTrF * kTrMaxBuckets features).
+// Bucketed transpose (default for shards below 1e9 stored entries; m <= kTrF * kTrMaxBuckets features).
 //
 // The emit kernel above walks the CSR rows of a cell tile once per 1024-feature range and finds
 // ~10 entries per (row, range): one thread per row with a handful of entries each, then one thread
@@ -836,12 +836,15 @@ void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
     T.cnt.alloc(static_cast<int64_t>(nt) * m);
     T.segoff.alloc(static_cast<int64_t>(nt) * m);
     T.tile_base.alloc(nt + 1);
-    // SNAPB200_TRANSPOSE=bucketed selects the bucketed transpose below (same output, bit for bit).  Measured
-    // on C3 it is not faster yet (88 ms against 80 ms: its scatter pass pays a DRAM fill for every
-    // partially written 32-byte sector and the per-bucket sort is bound by the L1 / shared-memory pipe;
-    // profiles/README.md), so the bitmap transpose above stays the default.
+    // Two transposes with the same output, bit for bit: the bitmap transpose above and the bucketed one
+    // below.  Measured on a B200 (profiles/README.md): 80 vs 88 ms on C3 (4.9e9 stored entries: the bucketed
+    // scatter pays a DRAM fill for every partially written 32-byte sector and its per-bucket sort is bound by
+    // the L1 / shared-memory pipe), 11.7 vs 10.4 ms on a 1/8 shard of it (6.1e8 entries: the bitmap kernel's
+    // per-unit costs weigh more).  Default: bucketed below 1e9 stored entries, bitmap above;
+    // SNAPB200_TRANSPOSE=bitmap|bucketed forces one.
     const char* tr_mode = getenv("SNAPB200_TRANSPOSE");
-    const bool bucketed = tr_mode != nullptr && tr_mode[0] == 'b';
+    bool bucketed = X.nnz < 1000000000ll;
+    if (tr_mode != nullptr && tr_mode[0] == 'b') bucketed = tr_mode[1] == 'u';
     if (bucketed && ceil_div(m, kTrF) <= kTrMaxBuckets && tile_rows <= (1 << 14)) {
         transpose_bucketed(c, tile_rows, df_local);
         return;
