@@ -554,11 +554,11 @@ tr_scatter_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ i
 // B: one unit = (cell tile, bucket); persistent CTAs pull units from a counter.
 // Counts per (warp slice, feature) by integer shared-memory atomics (order independent).  In the
 // scatter phase the entries of a 32-entry batch that share a feature must take consecutive slots
-// in lane (= row) order: every lane ORs its lane bit into the feature's word of a per-warp mask
-// table, reads the word back (= the set of lanes with the same feature), the lowest of them
-// advances the feature's cursor by the group size and clears the word, and each lane's slot is
-// the cursor plus its rank in the mask.  (This is match.any through shared memory: the
-// instruction itself costs hundreds of cycles on 32 distinct keys and made the kernel 10x slower.)
+// in lane (= row) order: the set of lanes with the same feature comes from one ballot per feature
+// bit, the lowest of them advances the feature's cursor by the group size, and each lane's slot
+// is the cursor plus its rank in the set.  (This is match.any spelled out: the instruction itself
+// costs hundreds of cycles on 32 distinct keys and made the kernel 10x slower; a shared-memory
+// mask table worked but added to the pipe that bounds the kernel.)
 __global__ void __launch_bounds__(1024, 1)
 tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restrict__ tmp_base, const int64_t* __restrict__ btot,
                       const uint32_t* __restrict__ ureg, const int64_t* __restrict__ tile_base, int64_t m, int NB, int NBp,
@@ -566,15 +566,12 @@ tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restric
                       uint16_t* __restrict__ ids, unsigned long long* __restrict__ counter) {
     extern __shared__ __align__(16) uint32_t bs_smem[];
     uint16_t* cw = reinterpret_cast<uint16_t*>(bs_smem);                 // 32 warps x kTrF counters, then running offsets
-    uint32_t* tags = bs_smem + 32 * kTrF / 2;                            // 32 warps x kTrF lane tags
-    uint32_t* segstart = tags + 32 * kTrF;                               // kTrF
+    uint32_t* segstart = bs_smem + 32 * kTrF / 2;                        // kTrF
     __shared__ uint32_t wsum[32];
     __shared__ long long s_unit;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     uint16_t* mine = cw + static_cast<size_t>(warp) * kTrF;
     uint32_t* mine32 = reinterpret_cast<uint32_t*>(mine);
-    uint32_t* tag = tags + static_cast<size_t>(warp) * kTrF;
-    for (int i = tid; i < 32 * kTrF; i += 1024) tags[i] = 0u;
     while (true) {
         __syncthreads();
         if (tid == 0) s_unit = static_cast<long long>(atomicAdd(counter, 1ull));
@@ -668,16 +665,21 @@ tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restric
                     const uint32_t e = cur[u2];
                     const uint32_t f = (e >> 14) & (kTrF - 1);
                     const bool valid = e != 0xFFFFFFFFu;
-                    if (valid) atomicOr(&tag[f], 1u << lane);
-                    __syncwarp();
-                    const unsigned same = valid ? tag[f] : (1u << lane);
-                    __syncwarp();                                 // every lane has read its word before a leader clears it
+                    // lanes with the same feature: one ballot per feature bit (no shared-memory traffic: the kernel is
+                    // bound by the L1 / shared-memory pipe, the ALU has room)
+                    unsigned same = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+                    for (int bit = 0; bit < kTrLog; ++bit) {
+                        const bool one = (f >> bit) & 1u;
+                        const unsigned mb = __ballot_sync(0xffffffffu, one);
+                        same &= one ? mb : ~mb;
+                    }
+                    if (!valid) same = 1u << lane;
                     const int leader = __ffs(same) - 1;
                     uint32_t base = 0;
                     if (valid && lane == leader) {
                         base = mine[f];
                         mine[f] = static_cast<uint16_t>(base + __popc(same));
-                        tag[f] = 0u;
                     }
                     base = __shfl_sync(0xffffffffu, base, leader);
                     if (valid) out[segstart[f] + base + __popc(same & ((1u << lane) - 1u))] = static_cast<uint16_t>(e & 0x3FFFu);
@@ -785,7 +787,7 @@ static void transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
     mark(3);
     {
         const int64_t n_units = static_cast<int64_t>(nt) * NB;
-        const size_t smem = static_cast<size_t>(32) * kTrF * (sizeof(uint16_t) + sizeof(uint32_t)) + kTrF * sizeof(uint32_t);
+        const size_t smem = static_cast<size_t>(32) * kTrF * sizeof(uint16_t) + kTrF * sizeof(uint32_t);
         SB_CUDA(cudaFuncSetAttribute(tr_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         const int grid = static_cast<int>(std::min<int64_t>(n_units, c->num_sms));
         tr_bucket_sort_kernel<<<grid, 1024, smem, st>>>(tmp.p, tmp_base.p, btot.p, ureg.p, T.tile_base.p, m, NB, NBp, n_units,
