@@ -363,91 +363,103 @@ tile_vals_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
 // The emit kernel above walks the CSR rows of a cell tile once per 1024-feature range and finds
 // ~10 entries per (row, range): one thread per row with a handful of entries each, then one thread
 // per feature over a 1024 x 1024 bitmap that is 1 % full -- a few active lanes per warp on both
-// sides (ncu: IPC 1.3).  Here every pass over the entries is entry-parallel and coalesced:
-//   A1  rowcnt[r][k]   entries of row r in feature bucket k (kTrF features): one warp streams a
-//                      row, 128 contiguous bytes per load; rows are sorted, so a bucket is a run;
-//   A2  rowoff[r][k]   exclusive prefix of rowcnt over the rows of r's cell tile, bucket totals;
-//   A3  scatter        the same streaming walk as A1 writes every entry, as (feature in bucket,
-//                      tile-local cell), to  tmp[tile][bucket][rowoff + position in the run] -- the
-//                      tile's entries grouped by bucket, each bucket still in row order; runs of
-//                      consecutive rows are adjacent in the output, so the stores merge in L2;
-//   B   per (tile, bucket): a stable counting sort of the bucket's ~125k entries by feature
+// sides (ncu: IPC 1.3, 95 GB of DRAM reads for a 19.6 GB index stream).  Here every pass over the
+// entries is entry-parallel and coalesced, and every global write is a long contiguous piece:
+//   A1  slabcnt[s][k]  entries of the 16-row slab s in feature bucket k (kTrF = 512 features): one
+//                      warp streams the slab's rows, 128 contiguous bytes per load; rows are sorted,
+//                      so a bucket is a run of consecutive entries;
+//   A2  slaboff[s][k]  exclusive prefix of slabcnt over the slabs of s's cell tile, bucket totals;
+//   A3  scatter        one CTA per slab: its entries are partitioned by bucket IN SHARED MEMORY
+//                      (run lengths per (row, bucket), prefix over rows and buckets, 16-bit staging
+//                      of up to ~93k entries) and every bucket's piece -- the slab's ~80 entries of
+//                      that bucket, rows in order -- is written as one contiguous run to
+//                      tmp[tile][bucket][slaboff ...] as (feature in bucket, tile-local cell).  (A warp
+//                      writing each row's ~20-byte run by itself paid a DRAM fill for every partially
+//                      written 32-byte sector: 30 ms for this pass alone on C3.)
+//   B   per (tile, bucket): a stable counting sort of the bucket's ~62k entries by feature
 //       (per-warp counters in shared memory over consecutive slices, ranks inside a 32-entry
-//       batch by match.any): segment lengths, offsets and the 16-bit ids of the TileT layout.
+//       batch from one ballot per feature bit) INTO SHARED MEMORY, then the bucket's whole
+//       output -- the segments of its 512 features are adjacent in the TileT layout -- leaves as one
+//       coalesced copy.  (Two-byte scattered global stores kept the first version on the L1 pipe.)
 // All positions come from prefix sums: no atomics on data, the result does not depend on timing.
 // A tile's buckets get regions padded for the worst case (7 slots per feature), so no pass has
 // to know the exact padded segment lengths of earlier buckets.
 // ==========================================================================
-constexpr int kTrLog = 10;
+constexpr int kTrLog = 9;
 constexpr int kTrF = 1 << kTrLog;          // features per bucket
-constexpr int kTrMaxBuckets = 2048;        // per-warp run counters of A1 / A3 (4 KB each)
+constexpr int kTrMaxBuckets = 1024;        // run-length tables of A3: 16 rows x buckets x 2 B of shared memory
 constexpr int kTrWarps = 16;               // warps per CTA in A1 / A3
+constexpr int kTrSlab = 16;                // rows per slab (= warps of an A3 CTA)
+constexpr int kTrSmemMax = 232448;         // 227 KB of dynamic shared memory per CTA
 
-// A row is cut into kTrGroup shares of a multiple of 32 entries (the scatter pass hands every share
-// to its own warp).  share_len is that multiple for a row of `len` entries.
-constexpr int kTrGroup = 8;
-__device__ __forceinline__ int64_t tr_share_len(int64_t len) {
-    return ((len + kTrGroup - 1) / kTrGroup + 31) / 32 * 32;
+// Run lengths of one row per bucket, streamed by one warp: tab[k] += entries of the row in bucket k.
+__device__ __forceinline__ void tr_count_row(const int32_t* __restrict__ idx, int64_t rs, int64_t re, uint16_t* tab, int lane) {
+    for (int64_t p0 = rs; p0 < re; p0 += 128) {
+        int j[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t p = p0 + 32 * u + lane;
+            j[u] = (p < re) ? ld_stream_int(idx + p) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool valid = j[u] >= 0;
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            if (vmask == 0u) break;
+            const int k = valid ? (j[u] >> kTrLog) : -1;
+            const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
+            const bool head = valid && (lane == 0 || k != kprev);
+            const unsigned hmask = __ballot_sync(0xffffffffu, head);
+            const int nvalid = __popc(vmask);
+            // the run this lane heads ends at the next head (or at the end of the batch)
+            const unsigned above = hmask & ~((2u << lane) - 1u);
+            const int end = above ? (__ffs(above) - 1) : nvalid;
+            if (head) tab[k] = static_cast<uint16_t>(tab[k] + (end - lane));   // heads of a batch have distinct buckets
+            __syncwarp();
+        }
+    }
 }
 
-// A1: one warp streams a row (128 contiguous bytes per load, four loads in flight): run lengths per
-// bucket in a per-warp table.  For every share boundary it also records what the scatter pass
-// needs to start there: the bucket of the first entry and how many entries of that bucket's run
-// lie before the boundary (carry = bucket << 16 | count).
+// A1: one warp per slab (grid-stride in slab order): run lengths per (row, bucket) -- the scatter pass loads
+// them instead of streaming its rows twice -- and their sums per (slab, bucket).
 __global__ void __launch_bounds__(kTrWarps * 32)
-tr_rowcnt_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int NBp,
-                 uint16_t* __restrict__ rowcnt, uint32_t* __restrict__ carrytab) {
-    extern __shared__ __align__(16) uint16_t tr_pos[];   // kTrWarps x NBp
+tr_slabcnt_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int H, int SPT,
+                  int64_t n_slabs, int NBp, uint16_t* __restrict__ rowcnt, uint16_t* __restrict__ slabcnt) {
+    extern __shared__ __align__(16) uint16_t tr_tab[];   // kTrWarps x 2 x NBp: current row, slab sums
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint16_t* pos = tr_pos + static_cast<size_t>(warp) * NBp;
-    for (int i = lane; i < NBp; i += 32) pos[i] = 0;
+    uint16_t* tab = tr_tab + static_cast<size_t>(warp) * 2 * NBp;
+    uint16_t* acc = tab + NBp;
+    for (int i = lane; i < 2 * NBp; i += 32) tab[i] = 0;
     __syncwarp();
     const int64_t nw = static_cast<int64_t>(gridDim.x) * kTrWarps;
-    for (int64_t r = static_cast<int64_t>(blockIdx.x) * kTrWarps + warp; r < n; r += nw) {
-        const int64_t rs = ptr[r], re = ptr[r + 1];
-        const int64_t share = tr_share_len(re - rs);
-        int64_t next_cut = rs + share;
-        int cut = 1;
-        for (int64_t p0 = rs; p0 < re; p0 += 128) {
-            int j[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t p = p0 + 32 * u + lane;
-                j[u] = (p < re) ? ld_stream_int(idx + p) : -1;
+    for (int64_t sl = static_cast<int64_t>(blockIdx.x) * kTrWarps + warp; sl < n_slabs; sl += nw) {
+        const int64_t t = sl / SPT;
+        const int64_t r0 = t * H + (sl - t * SPT) * kTrSlab;
+        const int64_t r1 = min(min(r0 + kTrSlab, (t + 1) * H), n);
+        for (int64_t r = r0; r < r1; ++r) {
+            tr_count_row(idx, ptr[r], ptr[r + 1], tab, lane);
+            __syncwarp();
+            uint32_t* out = reinterpret_cast<uint32_t*>(rowcnt + r * NBp);      // NBp is a multiple of 32: rows are 64-byte aligned
+            uint32_t* t32 = reinterpret_cast<uint32_t*>(tab);
+            uint32_t* a32 = reinterpret_cast<uint32_t*>(acc);
+            for (int i = lane; i < NBp / 2; i += 32) {
+                const uint32_t v = t32[i];
+                out[i] = v;
+                a32[i] += v;          // two 16-bit sums per word; a slab holds at most 16 x 512 entries per bucket: no carry
+                t32[i] = 0u;
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const bool valid = j[u] >= 0;
-                const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-                if (vmask == 0u) break;
-                const int k = valid ? (j[u] >> kTrLog) : -1;
-                if (p0 + 32 * u == next_cut) {          // a share of the scatter pass starts with this batch
-                    if (lane == 0) carrytab[r * kTrGroup + cut] = (static_cast<uint32_t>(k) << 16) | pos[k];
-                    next_cut += share;
-                    ++cut;
-                }
-                const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
-                const bool head = valid && (lane == 0 || k != kprev);
-                const unsigned hmask = __ballot_sync(0xffffffffu, head);
-                const int nvalid = __popc(vmask);
-                // the run this lane heads ends at the next head (or at the end of the batch)
-                const unsigned above = hmask & ~((2u << lane) - 1u);
-                const int end = above ? (__ffs(above) - 1) : nvalid;
-                if (head) pos[k] = static_cast<uint16_t>(pos[k] + (end - lane));
-                __syncwarp();
-            }
+            __syncwarp();
         }
-        __syncwarp();
-        uint16_t* out = rowcnt + r * NBp;
+        uint16_t* out = slabcnt + sl * NBp;
         for (int i = lane; i < NBp; i += 32) {
-            out[i] = pos[i];
-            pos[i] = 0;
+            out[i] = acc[i];
+            acc[i] = 0;
         }
         __syncwarp();
     }
 }
 
-// A2: one CTA per (cell tile, group of 32 buckets): exclusive prefix over the tile's rows
+// A2: one CTA per (cell tile, group of 32 buckets): exclusive prefix over the tile's slabs
 __global__ void __launch_bounds__(1024)
 tr_rowscan_kernel(const uint16_t* __restrict__ rowcnt, int64_t n, int H, int NBp, uint32_t* __restrict__ rowoff,
                   int64_t* __restrict__ btot) {
@@ -475,79 +487,148 @@ tr_rowscan_kernel(const uint16_t* __restrict__ rowcnt, int64_t n, int H, int NBp
     }
 }
 
-// A3: one warp per (row, share) -- the shares of a row go to consecutive warps, so the rows in
-// flight (and with them the output windows that must stay in L2 until their 32-byte sectors are
-// complete) are kTrGroup times fewer than with a warp per row, and no warp waits for another.
-// The warp stages the destinations of the buckets its share touches (a contiguous range, rows are
-// sorted): bucket start inside the tile's tmp region + entries of earlier rows; the part of the
-// first bucket's run that lies before the share comes from A1's carry table.  A run that
-// continues from the previous batch is always the first of the batch, so its length so far travels
-// in two registers.
-__global__ void __launch_bounds__(kTrWarps * 32)
-tr_scatter_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int H, int NBp,
-                  const uint32_t* __restrict__ rowoff, const uint32_t* __restrict__ trel, const int64_t* __restrict__ tile_tmp0,
-                  const uint32_t* __restrict__ carrytab, uint32_t* __restrict__ tmp_all) {
-    extern __shared__ __align__(16) uint32_t tr_dst[];   // kTrWarps x NBp
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* dst0 = tr_dst + static_cast<size_t>(warp) * NBp;
-    const int64_t n_items = n * kTrGroup;
-    const int64_t stride = static_cast<int64_t>(gridDim.x) * kTrWarps;
-    for (int64_t item = static_cast<int64_t>(blockIdx.x) * kTrWarps + warp; item < n_items; item += stride) {
-        const int64_t r = item / kTrGroup;
-        const int wg = static_cast<int>(item - r * kTrGroup);
-        const int64_t rs = ptr[r], re = ptr[r + 1];
-        const int64_t share = tr_share_len(re - rs);
-        const int64_t cs = rs + wg * share;
-        if (cs >= re) continue;
-        const int64_t ce = min(re, cs + share);
-        const int64_t t = r / H;
-        const int k_first = idx[cs] >> kTrLog, k_last = idx[ce - 1] >> kTrLog;
-        int carry_k = -1;
-        uint32_t carry_cnt = 0;
-        if (wg > 0) {
-            const uint32_t cv = carrytab[r * kTrGroup + wg];
-            carry_k = static_cast<int>(cv >> 16);
-            carry_cnt = cv & 0xFFFFu;
-        }
-        {
-            const uint32_t* ro = rowoff + r * NBp + k_first;
-            const uint32_t* tr = trel + t * NBp + k_first;
-            for (int i = lane; i <= k_last - k_first; i += 32) dst0[i] = tr[i] + ro[i];
-        }
-        __syncwarp();
+// A3: one CTA per slab (persistent, slabs in order), one warp per row of the slab.  The run lengths per
+// (row, bucket) come from A1's table, so the rows are streamed once (eight loads in flight per warp).
+__global__ void __launch_bounds__(kTrWarps * 32, 1)
+tr_slab_scatter_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int H, int SPT,
+                       int64_t n_slabs, int NBp, int cap, const uint16_t* __restrict__ rowcnt,
+                       const uint32_t* __restrict__ slaboff, const uint32_t* __restrict__ trel,
+                       const int64_t* __restrict__ tile_tmp0, uint32_t* __restrict__ tmp_all, int* __restrict__ too_long) {
+    extern __shared__ __align__(16) unsigned char tr_sm[];
+    uint16_t* cnt = reinterpret_cast<uint16_t*>(tr_sm);                           // kTrSlab x NBp: run lengths, then row offsets
+    uint32_t* tot = reinterpret_cast<uint32_t*>(cnt + static_cast<size_t>(kTrSlab) * NBp);   // NBp: entries of the group per bucket
+    uint32_t* bstart = tot + NBp;                                                 // NBp: start of a bucket's piece in the staging
+    uint32_t* gbase = bstart + NBp;                                               // NBp: where the bucket's next piece goes in tmp
+    uint16_t* stage = reinterpret_cast<uint16_t*>(gbase + NBp);                   // cap entries: feature in bucket << 4 | row in slab
+    __shared__ uint32_t wsum[kTrWarps];
+    __shared__ int s_g1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t sl = blockIdx.x; sl < n_slabs; sl += gridDim.x) {
+        const int64_t t = sl / SPT;
+        const int64_t r0 = t * H + (sl - t * SPT) * kTrSlab;
+        const int nrows = static_cast<int>(max(static_cast<int64_t>(0), min(min(r0 + kTrSlab, (t + 1) * H), n) - r0));
+        if (nrows == 0) continue;
         uint32_t* tmp = tmp_all + tile_tmp0[t];
-        const uint32_t r_local = static_cast<uint32_t>(r - t * H);
-        for (int64_t p0 = cs; p0 < ce; p0 += 128) {
-            int j[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int64_t p = p0 + 32 * u + lane;
-                j[u] = (p < ce) ? ld_stream_int(idx + p) : -1;
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const bool valid = j[u] >= 0;
-                const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-                if (vmask == 0u) break;
-                const int k = valid ? (j[u] >> kTrLog) : -1;
-                const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
-                const bool head = valid && (lane == 0 || k != kprev);
-                const unsigned hmask = __ballot_sync(0xffffffffu, head);
-                const int nvalid = __popc(vmask);
-                uint32_t off = 0;
-                if (head) off = dst0[k - k_first] + ((lane == 0 && k == carry_k) ? carry_cnt : 0u);
-                const int h = 31 - __clz(hmask & ((2u << lane) - 1u));   // my run's head lane
-                const uint32_t base = __shfl_sync(0xffffffffu, off, h);
-                if (valid) tmp[base + (lane - h)] = (static_cast<uint32_t>(j[u] & (kTrF - 1)) << 14) | r_local;
-                // the last run of the batch may continue in the next one
-                const int hl = 31 - __clz(hmask);                        // head of the last run
-                const int kl = __shfl_sync(0xffffffffu, k, hl);
-                const uint32_t len_l = static_cast<uint32_t>(nvalid - hl);
-                carry_cnt = len_l + ((hl == 0 && kl == carry_k) ? carry_cnt : 0u);
-                carry_k = kl;
-            }
+        const uint32_t rl0 = static_cast<uint32_t>(r0 - t * H);
+        {
+            const uint32_t* so = slaboff + sl * NBp;
+            const uint32_t* tr = trel + t * NBp;
+            for (int i = tid; i < NBp; i += blockDim.x) gbase[i] = tr[i] + so[i];
         }
-        __syncwarp();   // dst0 is restaged for the next item
+        // rows [g0, g1) of the slab are staged together; almost always that is the whole slab
+        for (int g0 = 0; g0 < nrows;) {
+            __syncthreads();
+            if (tid == 0) {
+                int64_t acc = 0;
+                int g1 = g0;
+                while (g1 < nrows) {
+                    const int64_t len = ptr[r0 + g1 + 1] - ptr[r0 + g1];
+                    if (g1 > g0 && acc + len > cap) break;
+                    acc += len;
+                    ++g1;
+                }
+                s_g1 = g1;
+            }
+            {   // run lengths of the slab's rows: one coalesced copy of A1's table (rows of the slab are adjacent)
+                const uint4* src = reinterpret_cast<const uint4*>(rowcnt + r0 * NBp);
+                uint4* dst = reinterpret_cast<uint4*>(cnt);
+                const int n16 = nrows * NBp / 8;
+                for (int i = tid; i < n16; i += blockDim.x) dst[i] = src[i];
+            }
+            __syncthreads();
+            const int g1 = s_g1;
+            bool mine = warp >= g0 && warp < g1;
+            const int64_t rs = mine ? ptr[r0 + warp] : 0, re = mine ? ptr[r0 + warp + 1] : 0;
+            // a single row longer than the staging cannot be handled here: flagged, the caller falls back to the
+            // bitmap transpose
+            if (mine && re - rs > cap) {
+                mine = false;
+                if (lane == 0) *too_long = 1;
+            }
+            // prefix over the rows of every bucket, then over the buckets (two buckets per thread)
+            uint32_t pair = 0;
+            for (int q = 0; q < 2; ++q) {
+                const int k = 2 * tid + q;
+                if (k < NBp) {
+                    uint32_t off = 0;
+                    for (int w = g0; w < g1; ++w) {
+                        const uint16_t c0 = cnt[static_cast<size_t>(w) * NBp + k];
+                        cnt[static_cast<size_t>(w) * NBp + k] = static_cast<uint16_t>(off);
+                        off += c0;
+                    }
+                    tot[k] = off;
+                    pair += off;
+                }
+            }
+            uint32_t x = pair;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+                if (lane >= d) x += y;
+            }
+            if (lane == 31) wsum[warp] = x;
+            __syncthreads();
+            uint32_t before = 0;
+            for (int w = 0; w < warp; ++w) before += wsum[w];
+            {
+                const uint32_t excl = before + x - pair;
+                if (2 * tid < NBp) bstart[2 * tid] = excl;
+                if (2 * tid + 1 < NBp) bstart[2 * tid + 1] = excl + tot[2 * tid];
+            }
+            __syncthreads();
+            // scatter into the staging: a run that continues from the previous batch is the first of the batch
+            if (mine) {
+                const uint16_t* roff = cnt + static_cast<size_t>(warp) * NBp;
+                int carry_k = -1;
+                uint32_t carry_cnt = 0;
+                for (int64_t p0 = rs; p0 < re; p0 += 256) {
+                    int j[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int64_t p = p0 + 32 * u + lane;
+                        j[u] = (p < re) ? ld_stream_int(idx + p) : -1;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const bool valid = j[u] >= 0;
+                        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+                        if (vmask == 0u) break;
+                        const int k = valid ? (j[u] >> kTrLog) : -1;
+                        const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
+                        const bool head = valid && (lane == 0 || k != kprev);
+                        const unsigned hmask = __ballot_sync(0xffffffffu, head);
+                        const int nvalid = __popc(vmask);
+                        uint32_t off = 0;
+                        if (head) off = bstart[k] + roff[k] + ((lane == 0 && k == carry_k) ? carry_cnt : 0u);
+                        const int h = 31 - __clz(hmask & ((2u << lane) - 1u));   // my run's head lane
+                        const uint32_t base = __shfl_sync(0xffffffffu, off, h);
+                        if (valid) stage[base + (lane - h)] = static_cast<uint16_t>(((j[u] & (kTrF - 1)) << 4) | warp);
+                        const int hl = 31 - __clz(hmask);                        // head of the last run
+                        const int kl = __shfl_sync(0xffffffffu, k, hl);
+                        const uint32_t len_l = static_cast<uint32_t>(nvalid - hl);
+                        carry_cnt = len_l + ((hl == 0 && kl == carry_k) ? carry_cnt : 0u);
+                        carry_k = kl;
+                    }
+                }
+            }
+            __syncthreads();
+            // every bucket's piece leaves as one contiguous run
+            for (int k = warp; k < NBp; k += kTrWarps) {
+                const uint32_t len = tot[k];
+                if (len == 0) continue;
+                const uint16_t* src = stage + bstart[k];
+                const uint32_t gb = gbase[k];
+                uint32_t* dst = tmp + gb;
+                for (uint32_t i = lane; i < len; i += 32) {
+                    const uint32_t e = src[i];
+                    dst[i] = ((e >> 4) << 14) | (rl0 + (e & 15u));
+                }
+                __syncwarp();
+                if (lane == 0) gbase[k] = gb + len;
+            }
+            g0 = g1;
+        }
+        __syncthreads();
     }
 }
 
@@ -562,11 +643,12 @@ tr_scatter_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ i
 __global__ void __launch_bounds__(1024, 1)
 tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restrict__ tmp_base, const int64_t* __restrict__ btot,
                       const uint32_t* __restrict__ ureg, const int64_t* __restrict__ tile_base, int64_t m, int NB, int NBp,
-                      int64_t n_units, uint16_t* __restrict__ cnt, uint32_t* __restrict__ segoff,
+                      int64_t n_units, int cap, uint16_t* __restrict__ cnt, uint32_t* __restrict__ segoff,
                       uint16_t* __restrict__ ids, unsigned long long* __restrict__ counter) {
     extern __shared__ __align__(16) uint32_t bs_smem[];
     uint16_t* cw = reinterpret_cast<uint16_t*>(bs_smem);                 // 32 warps x kTrF counters, then running offsets
-    uint32_t* segstart = bs_smem + 32 * kTrF / 2;                        // kTrF
+    uint32_t* segstart = bs_smem + 32 * kTrF / 2;                        // kTrF: segment starts relative to the unit's output
+    uint16_t* stage = reinterpret_cast<uint16_t*>(segstart + kTrF);      // cap entries: the unit's output
     __shared__ uint32_t wsum[32];
     __shared__ long long s_unit;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -607,7 +689,7 @@ tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restric
                 for (int u2 = 0; u2 < 4; ++u2) {
                     const uint32_t e = cur[u2];
                     if (e != 0xFFFFFFFFu) {
-                        const uint32_t f = e >> 14;
+                        const uint32_t f = (e >> 14) & (kTrF - 1);
                         atomicAdd(&mine32[f >> 1], (f & 1u) ? 0x10000u : 1u);   // two 16-bit counters per word
                     }
                 }
@@ -617,6 +699,7 @@ tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restric
         }
         __syncthreads();
         // ---- per feature: exclusive prefix over the warps, segment length, padded exclusive scan
+        uint32_t out_len = 0;
         {
             uint32_t total = 0;
             if (tid < nf) {
@@ -646,13 +729,15 @@ tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restric
                 wsum[lane] = w;
             }
             __syncthreads();
-            const uint32_t excl = ureg[t * NBp + k] + (warp > 0 ? wsum[warp - 1] : 0u) + (x - v);
-            segstart[tid] = excl;
-            if (tid < nf) segoff[t * m + f0 + tid] = excl;
+            const uint32_t excl = (warp > 0 ? wsum[warp - 1] : 0u) + (x - v);
+            if (tid < kTrF) segstart[tid] = excl;
+            if (tid < nf) segoff[t * m + f0 + tid] = ureg[t * NBp + k] + excl;
+            out_len = wsum[31];            // padded size of the unit's output (a multiple of 8)
         }
         __syncthreads();
-        // ---- stable scatter
-        uint16_t* out = ids + tile_base[t];
+        // ---- stable scatter: into the staging if the unit fits (it almost always does), else straight to global
+        const bool staged = out_len <= static_cast<uint32_t>(cap);
+        uint16_t* out_g = ids + tile_base[t] + ureg[t * NBp + k];
         {
             uint32_t cur[4], nxt[4];
             if (a < b) load4(a, cur);
@@ -665,8 +750,6 @@ tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restric
                     const uint32_t e = cur[u2];
                     const uint32_t f = (e >> 14) & (kTrF - 1);
                     const bool valid = e != 0xFFFFFFFFu;
-                    // lanes with the same feature: one ballot per feature bit (no shared-memory traffic: the kernel is
-                    // bound by the L1 / shared-memory pipe, the ALU has room)
                     unsigned same = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
                     for (int bit = 0; bit < kTrLog; ++bit) {
@@ -682,17 +765,29 @@ tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restric
                         mine[f] = static_cast<uint16_t>(base + __popc(same));
                     }
                     base = __shfl_sync(0xffffffffu, base, leader);
-                    if (valid) out[segstart[f] + base + __popc(same & ((1u << lane) - 1u))] = static_cast<uint16_t>(e & 0x3FFFu);
+                    if (valid) {
+                        const uint32_t slot = segstart[f] + base + __popc(same & ((1u << lane) - 1u));
+                        const uint16_t row = static_cast<uint16_t>(e & 0x3FFFu);
+                        if (staged) stage[slot] = row; else out_g[slot] = row;
+                    }
                     __syncwarp();
                 }
 #pragma unroll
                 for (int u2 = 0; u2 < 4; ++u2) cur[u2] = nxt[u2];
             }
         }
+        if (staged) {
+            __syncthreads();
+            // the unit's whole output (segments of its features are adjacent) as one coalesced copy
+            const uint4* src = reinterpret_cast<const uint4*>(stage);
+            uint4* dst = reinterpret_cast<uint4*>(out_g);
+            for (uint32_t i = tid; i < out_len / 8; i += 1024) dst[i] = src[i];
+        }
     }
 }
 
-static void transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
+// returns false if a row did not fit the scatter pass's staging (the caller then uses the bitmap transpose)
+static bool transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
     const Csr& X = c->X;
     TileT& T = c->XtT;
     cudaStream_t st = c->stream;
@@ -708,41 +803,35 @@ static void transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
     mark(0);
     const int NB = static_cast<int>(ceil_div(m, kTrF));
     const int NBp = (NB + 31) / 32 * 32;
-    DevBuf<uint16_t> rowcnt;
-    DevBuf<uint32_t> rowoff, ureg, tmp, trel, carrytab;
-    DevBuf<int64_t> tile_tmp0;
-    DevBuf<int64_t> btot, tmp_base;
+    const int SPT = static_cast<int>(ceil_div(tile_rows, kTrSlab));      // slabs per cell tile
+    const int64_t n_slabs = static_cast<int64_t>(nt) * SPT;
+    DevBuf<uint16_t> slabcnt, rowcnt;
+    DevBuf<uint32_t> slaboff, ureg, tmp, trel;
+    DevBuf<int64_t> tile_tmp0, btot, tmp_base;
     DevBuf<unsigned long long> counter;
-    rowcnt.alloc(std::max<int64_t>(1, n * NBp));
-    rowoff.alloc(std::max<int64_t>(1, n * NBp));
+    DevBuf<int> too_long;
+    too_long.alloc(1);
+    SB_CUDA(cudaMemsetAsync(too_long.p, 0, sizeof(int), st));
+    slabcnt.alloc(n_slabs * NBp);
+    slaboff.alloc(n_slabs * NBp);
+    rowcnt.alloc(std::max<int64_t>(1, n) * NBp + 8);
     btot.alloc(static_cast<int64_t>(nt) * NBp);
     tmp_base.alloc(static_cast<int64_t>(nt) * NBp);
     ureg.alloc(static_cast<int64_t>(nt) * NBp);
     trel.alloc(static_cast<int64_t>(nt) * NBp);
-    carrytab.alloc(std::max<int64_t>(1, n * kTrGroup));
     tile_tmp0.alloc(nt);
     counter.alloc(1);
     SB_CUDA(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
-    SB_CUDA(cudaMemsetAsync(btot.p, 0, sizeof(int64_t) * nt * NBp, st));
-    const size_t smem_walk = static_cast<size_t>(kTrWarps) * NBp * sizeof(uint16_t);
-    const size_t smem_scat = static_cast<size_t>(kTrWarps) * NBp * sizeof(uint32_t);
-    static_assert(kTrF == 1024, "tr_bucket_sort_kernel scans one feature per thread of a 1024-thread CTA");
-    // A1 only reads: as many resident warps as fit.  A3 also scatters: the rows in flight bound the
-    // output windows that must stay in L2 until their sectors are complete (rows x ~40 B x buckets),
-    // so it runs with half the warps.
-    int cta_per_sm_a1 = 4, cta_per_sm_a3 = 4;
-    if (const char* e = getenv("SNAPB200_TR_CTAS")) cta_per_sm_a3 = std::max(1, atoi(e));
-    const int walk_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, kTrWarps), c->num_sms * cta_per_sm_a1)));
-    const int scat_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n * kTrGroup, kTrWarps), c->num_sms * cta_per_sm_a3)));
-    if (n > 0) {
-        SB_CUDA(cudaFuncSetAttribute(tr_rowcnt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_walk)));
-        tr_rowcnt_kernel<<<walk_grid, kTrWarps * 32, smem_walk, st>>>(X.ptr.p, X.idx.p, n, NBp, rowcnt.p, carrytab.p);
-        SB_LAUNCH_CHECK();
-        mark(1);
-        tr_rowscan_kernel<<<static_cast<unsigned>(static_cast<int64_t>(nt) * (NBp / 32)), 1024, 0, st>>>(rowcnt.p, n, tile_rows, NBp,
-                                                                                                      rowoff.p, btot.p);
-        SB_LAUNCH_CHECK();
-    }
+    const size_t smem_cnt = static_cast<size_t>(kTrWarps) * 2 * NBp * sizeof(uint16_t);
+    const int walk_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_slabs, kTrWarps), c->num_sms * 4)));
+    SB_CUDA(cudaFuncSetAttribute(tr_slabcnt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cnt)));
+    tr_slabcnt_kernel<<<walk_grid, kTrWarps * 32, smem_cnt, st>>>(X.ptr.p, X.idx.p, n, tile_rows, SPT, n_slabs, NBp, rowcnt.p,
+                                                                  slabcnt.p);
+    SB_LAUNCH_CHECK();
+    mark(1);
+    tr_rowscan_kernel<<<static_cast<unsigned>(static_cast<int64_t>(nt) * (NBp / 32)), 1024, 0, st>>>(slabcnt.p, n_slabs, SPT, NBp,
+                                                                                                  slaboff.p, btot.p);
+    SB_LAUNCH_CHECK();
     mark(2);
     // ---- bucket bases (host: nt x NB numbers): exact offsets into tmp, worst-case padded regions of the output
     std::vector<int64_t> hb(static_cast<size_t>(nt) * NBp), htb(static_cast<size_t>(nt) * NBp), tb(nt + 1);
@@ -779,18 +868,28 @@ static void transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
     T.ids.alloc(tb[nt] + 8);
     tmp.alloc(std::max<int64_t>(1, X.nnz));
     if (n > 0 && X.nnz > 0) {
-        SB_CUDA(cudaFuncSetAttribute(tr_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_scat)));
-        tr_scatter_kernel<<<scat_grid, kTrWarps * 32, smem_scat, st>>>(X.ptr.p, X.idx.p, n, tile_rows, NBp, rowoff.p, trel.p,
-                                                                       tile_tmp0.p, carrytab.p, tmp.p);
+        const size_t tables = static_cast<size_t>(kTrSlab) * NBp * sizeof(uint16_t) + 3 * static_cast<size_t>(NBp) * sizeof(uint32_t);
+        const int cap = static_cast<int>((kTrSmemMax - 256 - tables) / sizeof(uint16_t));
+        const size_t smem = tables + static_cast<size_t>(cap) * sizeof(uint16_t);
+        SB_CUDA(cudaFuncSetAttribute(tr_slab_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        const int grid = static_cast<int>(std::min<int64_t>(n_slabs, c->num_sms));
+        tr_slab_scatter_kernel<<<grid, kTrWarps * 32, smem, st>>>(X.ptr.p, X.idx.p, n, tile_rows, SPT, n_slabs, NBp, cap, rowcnt.p,
+                                                                  slaboff.p, trel.p, tile_tmp0.p, tmp.p, too_long.p);
         SB_LAUNCH_CHECK();
+        int h_long = 0;
+        SB_CUDA(cudaMemcpyAsync(&h_long, too_long.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (h_long) return false;
     }
     mark(3);
     {
         const int64_t n_units = static_cast<int64_t>(nt) * NB;
-        const size_t smem = static_cast<size_t>(32) * kTrF * sizeof(uint16_t) + kTrF * sizeof(uint32_t);
+        const size_t tables = static_cast<size_t>(32) * kTrF * sizeof(uint16_t) + kTrF * sizeof(uint32_t);
+        const int cap = static_cast<int>((kTrSmemMax - 512 - tables) / sizeof(uint16_t)) / 8 * 8;
+        const size_t smem = tables + static_cast<size_t>(cap) * sizeof(uint16_t);
         SB_CUDA(cudaFuncSetAttribute(tr_bucket_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         const int grid = static_cast<int>(std::min<int64_t>(n_units, c->num_sms));
-        tr_bucket_sort_kernel<<<grid, 1024, smem, st>>>(tmp.p, tmp_base.p, btot.p, ureg.p, T.tile_base.p, m, NB, NBp, n_units,
+        tr_bucket_sort_kernel<<<grid, 1024, smem, st>>>(tmp.p, tmp_base.p, btot.p, ureg.p, T.tile_base.p, m, NB, NBp, n_units, cap,
                                                         T.cnt.p, T.segoff.p, T.ids.p, counter.p);
         SB_LAUNCH_CHECK();
     }
@@ -814,11 +913,12 @@ static void transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
         float ms[5] = {};
         for (int i = 0; i < 5; ++i)
             if (dbg[i] && dbg[i + 1]) cudaEventElapsedTime(&ms[i], dbg[i], dbg[i + 1]);
-        fprintf(stderr, "[snapb200] bucketed transpose: rowcnt %.2f  rowscan %.2f  host tables+alloc %.2f  scatter %.2f  bucket sort %.2f  "
-                        "df/vals %.2f ms\n", ms[0], ms[1], 0.0f, ms[2] + 0.0f, ms[3], ms[4]);
+        fprintf(stderr, "[snapb200] bucketed transpose: slabcnt %.2f  scan %.2f  host tables %.2f  slab scatter %.2f  bucket sort %.2f ms\n",
+                ms[0], ms[1], 0.0f, ms[2], ms[3]);
         for (auto& e : dbg) if (e) cudaEventDestroy(e);
     }
     T.built = true;
+    return true;
 }
 
 }  // namespace
@@ -848,8 +948,7 @@ void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
     bool bucketed = X.nnz < 1000000000ll;
     if (tr_mode != nullptr && tr_mode[0] == 'b') bucketed = tr_mode[1] == 'u';
     if (bucketed && ceil_div(m, kTrF) <= kTrMaxBuckets && tile_rows <= (1 << 14)) {
-        transpose_bucketed(c, tile_rows, df_local);
-        return;
+        if (transpose_bucketed(c, tile_rows, df_local)) return;
     }
     DevBuf<unsigned long long> counter;
     DevBuf<int64_t> totals;

@@ -191,3 +191,31 @@ def test_bucketed_transpose_equals_legacy_bitmap_transpose(engine, monkeypatch):
         np.testing.assert_array_equal(outs[0][0], outs[1][0])
         np.testing.assert_array_equal(outs[0][1], outs[1][1])
         np.testing.assert_array_equal(outs[0][2], outs[1][2])
+
+
+def test_bucketed_transpose_dense_rows_and_hot_features(engine, monkeypatch):
+    """Rows longer than the scatter pass's shared-memory staging (the bucketed transpose must hand over to the
+    bitmap one) and a feature present in every cell (one bucket far above the average): same operator as the
+    CSR-gather path."""
+    rng = np.random.default_rng(3)
+    n, m = 700, 120000
+    X = sp.random(n, m, density=0.002, format="csr", random_state=7, dtype=np.float32)
+    X.data[:] = 1.0
+    dense_row = sp.csr_matrix(np.ones((1, m), dtype=np.float32))       # 120000 entries > staging capacity
+    hot = sp.csr_matrix((np.ones(n + 1, np.float32), (np.arange(n + 1), np.full(n + 1, 77))), shape=(n + 1, m))
+    Y = sp.csr_matrix(sp.vstack([X, dense_row]).maximum(hot))
+    Y.sum_duplicates()
+    Y.data[:] = 1.0
+    V = rng.standard_normal((n + 1, 4)).astype(np.float32)
+    res = {}
+    for mode, tr in (("csr", "bitmap"), ("tiled", "bucketed"), ("tiled", "bitmap")):
+        monkeypatch.setenv("SNAPB200_TRANSPOSE", tr)
+        engine.set_spmm_mode(mode)
+        engine.load_csr(Y)
+        engine.set_feature_weights(None)
+        engine.prepare(want_outputs=False)
+        res[(mode, tr)] = engine.operator_apply(V)
+    engine.set_spmm_mode("auto")
+    np.testing.assert_array_equal(res[("tiled", "bucketed")], res[("tiled", "bitmap")])
+    ref = res[("csr", "bitmap")]
+    assert np.abs(res[("tiled", "bucketed")] - ref).max() <= 2e-5 * np.abs(ref).max()
