@@ -358,7 +358,7 @@ tile_vals_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ id
 }
 
 // ==========================================================================
-// Bucketed transpose (default for shards below 1e9 stored entries; m <= kTrF * kTrMaxBuckets features).
+// Bucketed transpose (default; m <= kTrF * kTrMaxBuckets features).
 //
 // The emit kernel above walks the CSR rows of a cell tile once per 1024-feature range and finds
 // ~10 entries per (row, range): one thread per row with a handful of entries each, then one thread
@@ -393,24 +393,31 @@ constexpr int kTrSlab = 16;                // rows per slab (= warps of an A3 CT
 constexpr int kTrSmemMax = 232448;         // 227 KB of dynamic shared memory per CTA
 
 // Run lengths of one row per bucket, streamed by one warp: tab[k] += entries of the row in bucket k.
-__device__ __forceinline__ void tr_count_row(const int32_t* __restrict__ idx, int64_t rs, int64_t re, uint16_t* tab, int lane) {
-    for (int64_t p0 = rs; p0 < re; p0 += 128) {
+// The scatter pass hands the two halves of a row to two warps; the second half starts at entry
+// tr_mid(len) (a multiple of 32, so it starts a batch) and needs to know how many entries of its
+// first bucket's run lie in the first half: *mid_carry = bucket << 16 | count.
+__device__ __forceinline__ int tr_mid(int len) { return ((len + 1) / 2 + 31) & ~31; }
+
+__device__ __forceinline__ void tr_count_row(const int32_t* __restrict__ idx, int64_t rs, int64_t re, uint16_t* tab, int lane,
+                                             uint32_t* mid_carry) {
+    const int32_t* __restrict__ row = idx + rs;
+    const int len = static_cast<int>(re - rs);          // a row has fewer than 2^31 entries (m < 2^31, no duplicates)
+    const int mid = tr_mid(len);
+    for (int o = lane; o < len + lane; o += 128) {      // (warp-uniform trip count: o - lane < len)
         int j[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int64_t p = p0 + 32 * u + lane;
-            j[u] = (p < re) ? ld_stream_int(idx + p) : -1;
-        }
+        for (int u = 0; u < 4; ++u) j[u] = (o + 32 * u < len) ? ld_stream_int(row + o + 32 * u) : -1;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const bool valid = j[u] >= 0;
-            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-            if (vmask == 0u) break;
+            const int nvalid = min(32, len - (o - lane) - 32 * u);   // valid lanes are a prefix of the warp
+            if (nvalid <= 0) break;
+            const bool valid = lane < nvalid;
             const int k = valid ? (j[u] >> kTrLog) : -1;
+            if (mid_carry != nullptr && (o - lane) + 32 * u == mid && lane == 0)
+                *mid_carry = (static_cast<uint32_t>(k) << 16) | tab[k];          // tab holds this row's counts so far
             const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
             const bool head = valid && (lane == 0 || k != kprev);
             const unsigned hmask = __ballot_sync(0xffffffffu, head);
-            const int nvalid = __popc(vmask);
             // the run this lane heads ends at the next head (or at the end of the batch)
             const unsigned above = hmask & ~((2u << lane) - 1u);
             const int end = above ? (__ffs(above) - 1) : nvalid;
@@ -424,7 +431,8 @@ __device__ __forceinline__ void tr_count_row(const int32_t* __restrict__ idx, in
 // them instead of streaming its rows twice -- and their sums per (slab, bucket).
 __global__ void __launch_bounds__(kTrWarps * 32)
 tr_slabcnt_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int H, int SPT,
-                  int64_t n_slabs, int NBp, uint16_t* __restrict__ rowcnt, uint16_t* __restrict__ slabcnt) {
+                  int64_t n_slabs, int NBp, uint16_t* __restrict__ rowcnt, uint16_t* __restrict__ slabcnt,
+                  uint32_t* __restrict__ midcarry) {
     extern __shared__ __align__(16) uint16_t tr_tab[];   // kTrWarps x 2 x NBp: current row, slab sums
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t* tab = tr_tab + static_cast<size_t>(warp) * 2 * NBp;
@@ -437,7 +445,7 @@ tr_slabcnt_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ i
         const int64_t r0 = t * H + (sl - t * SPT) * kTrSlab;
         const int64_t r1 = min(min(r0 + kTrSlab, (t + 1) * H), n);
         for (int64_t r = r0; r < r1; ++r) {
-            tr_count_row(idx, ptr[r], ptr[r + 1], tab, lane);
+            tr_count_row(idx, ptr[r], ptr[r + 1], tab, lane, midcarry + r);
             __syncwarp();
             uint32_t* out = reinterpret_cast<uint32_t*>(rowcnt + r * NBp);      // NBp is a multiple of 32: rows are 64-byte aligned
             uint32_t* t32 = reinterpret_cast<uint32_t*>(tab);
@@ -487,22 +495,25 @@ tr_rowscan_kernel(const uint16_t* __restrict__ rowcnt, int64_t n, int H, int NBp
     }
 }
 
-// A3: one CTA per slab (persistent, slabs in order), one warp per row of the slab.  The run lengths per
-// (row, bucket) come from A1's table, so the rows are streamed once (eight loads in flight per warp).
-__global__ void __launch_bounds__(kTrWarps * 32, 1)
+// A3: one CTA per slab (persistent, slabs in order), two warps per row of the slab (the kernel is bound by
+// instruction issue: 32 resident warps instead of 16).  The run lengths per (row, bucket) come from A1's
+// table, so the rows are streamed once (eight loads in flight per warp).
+__global__ void __launch_bounds__(kTrWarps * 64, 1)
 tr_slab_scatter_kernel(const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx, int64_t n, int H, int SPT,
                        int64_t n_slabs, int NBp, int cap, const uint16_t* __restrict__ rowcnt,
                        const uint32_t* __restrict__ slaboff, const uint32_t* __restrict__ trel,
-                       const int64_t* __restrict__ tile_tmp0, uint32_t* __restrict__ tmp_all, int* __restrict__ too_long) {
+                       const int64_t* __restrict__ tile_tmp0, const uint32_t* __restrict__ midcarry,
+                       uint32_t* __restrict__ tmp_all, int* __restrict__ too_long) {
     extern __shared__ __align__(16) unsigned char tr_sm[];
     uint16_t* cnt = reinterpret_cast<uint16_t*>(tr_sm);                           // kTrSlab x NBp: run lengths, then row offsets
     uint32_t* tot = reinterpret_cast<uint32_t*>(cnt + static_cast<size_t>(kTrSlab) * NBp);   // NBp: entries of the group per bucket
     uint32_t* bstart = tot + NBp;                                                 // NBp: start of a bucket's piece in the staging
     uint32_t* gbase = bstart + NBp;                                               // NBp: where the bucket's next piece goes in tmp
     uint16_t* stage = reinterpret_cast<uint16_t*>(gbase + NBp);                   // cap entries: feature in bucket << 4 | row in slab
-    __shared__ uint32_t wsum[kTrWarps];
-    __shared__ int s_g1;
+    __shared__ uint32_t wsum[2 * kTrWarps];
+    __shared__ int s_g1, s_long;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wrow = warp >> 1, half = warp & 1;     // row of the slab and half of it this warp streams
     for (int64_t sl = blockIdx.x; sl < n_slabs; sl += gridDim.x) {
         const int64_t t = sl / SPT;
         const int64_t r0 = t * H + (sl - t * SPT) * kTrSlab;
@@ -520,14 +531,16 @@ tr_slab_scatter_kernel(const int64_t* __restrict__ ptr, const int32_t* __restric
             __syncthreads();
             if (tid == 0) {
                 int64_t acc = 0;
-                int g1 = g0;
+                int g1 = g0, any_long = 0;
                 while (g1 < nrows) {
                     const int64_t len = ptr[r0 + g1 + 1] - ptr[r0 + g1];
                     if (g1 > g0 && acc + len > cap) break;
+                    if (len > cap) any_long = 1;     // staged alone, skipped and flagged below
                     acc += len;
                     ++g1;
                 }
                 s_g1 = g1;
+                s_long = any_long;
             }
             {   // run lengths of the slab's rows: one coalesced copy of A1's table (rows of the slab are adjacent)
                 const uint4* src = reinterpret_cast<const uint4*>(rowcnt + r0 * NBp);
@@ -537,30 +550,30 @@ tr_slab_scatter_kernel(const int64_t* __restrict__ ptr, const int32_t* __restric
             }
             __syncthreads();
             const int g1 = s_g1;
-            bool mine = warp >= g0 && warp < g1;
-            const int64_t rs = mine ? ptr[r0 + warp] : 0, re = mine ? ptr[r0 + warp + 1] : 0;
+            bool mine = wrow >= g0 && wrow < g1;
+            const int64_t rs = mine ? ptr[r0 + wrow] : 0, re = mine ? ptr[r0 + wrow + 1] : 0;
             // a single row longer than the staging cannot be handled here: flagged, the caller falls back to the
             // bitmap transpose
             if (mine && re - rs > cap) {
                 mine = false;
                 if (lane == 0) *too_long = 1;
+                if (half == 0)
+                    for (int i = lane; i < NBp; i += 32) cnt[static_cast<size_t>(wrow) * NBp + i] = 0;   // nothing of it is staged
             }
-            // prefix over the rows of every bucket, then over the buckets (two buckets per thread)
-            uint32_t pair = 0;
-            for (int q = 0; q < 2; ++q) {
-                const int k = 2 * tid + q;
-                if (k < NBp) {
-                    uint32_t off = 0;
-                    for (int w = g0; w < g1; ++w) {
-                        const uint16_t c0 = cnt[static_cast<size_t>(w) * NBp + k];
-                        cnt[static_cast<size_t>(w) * NBp + k] = static_cast<uint16_t>(off);
-                        off += c0;
-                    }
-                    tot[k] = off;
-                    pair += off;
+            if (s_long) __syncthreads();
+            // prefix over the rows of every bucket, then over the buckets (one bucket per thread)
+            uint32_t mine_tot = 0;
+            if (tid < NBp) {
+                uint32_t off = 0;
+                for (int w = g0; w < g1; ++w) {
+                    const uint16_t c0 = cnt[static_cast<size_t>(w) * NBp + tid];
+                    cnt[static_cast<size_t>(w) * NBp + tid] = static_cast<uint16_t>(off);
+                    off += c0;
                 }
+                tot[tid] = off;
+                mine_tot = off;
             }
-            uint32_t x = pair;
+            uint32_t x = mine_tot;
 #pragma unroll
             for (int d = 1; d < 32; d <<= 1) {
                 const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
@@ -570,39 +583,41 @@ tr_slab_scatter_kernel(const int64_t* __restrict__ ptr, const int32_t* __restric
             __syncthreads();
             uint32_t before = 0;
             for (int w = 0; w < warp; ++w) before += wsum[w];
-            {
-                const uint32_t excl = before + x - pair;
-                if (2 * tid < NBp) bstart[2 * tid] = excl;
-                if (2 * tid + 1 < NBp) bstart[2 * tid + 1] = excl + tot[2 * tid];
-            }
+            if (tid < NBp) bstart[tid] = before + x - mine_tot;
             __syncthreads();
             // scatter into the staging: a run that continues from the previous batch is the first of the batch
             if (mine) {
-                const uint16_t* roff = cnt + static_cast<size_t>(warp) * NBp;
+                const uint16_t* roff = cnt + static_cast<size_t>(wrow) * NBp;
                 int carry_k = -1;
                 uint32_t carry_cnt = 0;
-                for (int64_t p0 = rs; p0 < re; p0 += 256) {
+                const int full = static_cast<int>(re - rs);
+                const int mid = min(full, tr_mid(full));
+                const int32_t* __restrict__ row = idx + rs + (half ? mid : 0);
+                const int len = half ? full - mid : mid;
+                if (half && len > 0) {       // the part of the first bucket's run that the other warp writes
+                    const uint32_t cv = midcarry[r0 + wrow];
+                    carry_k = static_cast<int>(cv >> 16);
+                    carry_cnt = cv & 0xFFFFu;
+                }
+                const uint16_t tagw = static_cast<uint16_t>(wrow);
+                for (int o = lane; o < len + lane; o += 256) {
                     int j[8];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        const int64_t p = p0 + 32 * u + lane;
-                        j[u] = (p < re) ? ld_stream_int(idx + p) : -1;
-                    }
+                    for (int u = 0; u < 8; ++u) j[u] = (o + 32 * u < len) ? ld_stream_int(row + o + 32 * u) : -1;
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const bool valid = j[u] >= 0;
-                        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-                        if (vmask == 0u) break;
+                        const int nvalid = min(32, len - (o - lane) - 32 * u);   // valid lanes are a prefix of the warp
+                        if (nvalid <= 0) break;
+                        const bool valid = lane < nvalid;
                         const int k = valid ? (j[u] >> kTrLog) : -1;
                         const int kprev = __shfl_up_sync(0xffffffffu, k, 1);
                         const bool head = valid && (lane == 0 || k != kprev);
                         const unsigned hmask = __ballot_sync(0xffffffffu, head);
-                        const int nvalid = __popc(vmask);
                         uint32_t off = 0;
                         if (head) off = bstart[k] + roff[k] + ((lane == 0 && k == carry_k) ? carry_cnt : 0u);
                         const int h = 31 - __clz(hmask & ((2u << lane) - 1u));   // my run's head lane
                         const uint32_t base = __shfl_sync(0xffffffffu, off, h);
-                        if (valid) stage[base + (lane - h)] = static_cast<uint16_t>(((j[u] & (kTrF - 1)) << 4) | warp);
+                        if (valid) stage[base + (lane - h)] = static_cast<uint16_t>(((j[u] & (kTrF - 1)) << 4) | tagw);
                         const int hl = 31 - __clz(hmask);                        // head of the last run
                         const int kl = __shfl_sync(0xffffffffu, k, hl);
                         const uint32_t len_l = static_cast<uint32_t>(nvalid - hl);
@@ -613,7 +628,7 @@ tr_slab_scatter_kernel(const int64_t* __restrict__ ptr, const int32_t* __restric
             }
             __syncthreads();
             // every bucket's piece leaves as one contiguous run
-            for (int k = warp; k < NBp; k += kTrWarps) {
+            for (int k = warp; k < NBp; k += 2 * kTrWarps) {
                 const uint32_t len = tot[k];
                 if (len == 0) continue;
                 const uint16_t* src = stage + bstart[k];
@@ -669,19 +684,20 @@ tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restric
         for (int i = tid; i < 32 * kTrF / 2; i += 1024) bs_smem[i] = 0u;
         __syncthreads();
         // ---- counts per (warp slice, feature); slices are consecutive, so slice order = row order
-        const int64_t per = ((E + 31) / 32 + 127) / 128 * 128;
-        const int64_t a = min(E, warp * per), b = min(E, a + per);
-        auto load4 = [&](int64_t p0, uint32_t* e) {
+        const int En = static_cast<int>(E);                      // a unit has at most tile rows x kTrF entries
+        const int per = ((En + 31) / 32 + 127) / 128 * 128;
+        const int a = min(En, warp * per), b = min(En, a + per);
+        auto load4 = [&](int p0, uint32_t* e) {
 #pragma unroll
             for (int u2 = 0; u2 < 4; ++u2) {
-                const int64_t p = p0 + 32 * u2 + lane;
+                const int p = p0 + 32 * u2 + lane;
                 e[u2] = (p < b) ? __ldg(in + p) : 0xFFFFFFFFu;   // a stored entry never has its top byte set
             }
         };
         {
             uint32_t cur[4], nxt[4];
             if (a < b) load4(a, cur);
-            for (int64_t p0 = a; p0 < b; p0 += 128) {
+            for (int p0 = a; p0 < b; p0 += 128) {
 #pragma unroll
                 for (int u2 = 0; u2 < 4; ++u2) nxt[u2] = 0xFFFFFFFFu;
                 if (p0 + 128 < b) load4(p0 + 128, nxt);
@@ -741,7 +757,7 @@ tr_bucket_sort_kernel(const uint32_t* __restrict__ tmp, const int64_t* __restric
         {
             uint32_t cur[4], nxt[4];
             if (a < b) load4(a, cur);
-            for (int64_t p0 = a; p0 < b; p0 += 128) {
+            for (int p0 = a; p0 < b; p0 += 128) {
 #pragma unroll
                 for (int u2 = 0; u2 < 4; ++u2) nxt[u2] = 0xFFFFFFFFu;
                 if (p0 + 128 < b) load4(p0 + 128, nxt);
@@ -806,7 +822,7 @@ static bool transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
     const int SPT = static_cast<int>(ceil_div(tile_rows, kTrSlab));      // slabs per cell tile
     const int64_t n_slabs = static_cast<int64_t>(nt) * SPT;
     DevBuf<uint16_t> slabcnt, rowcnt;
-    DevBuf<uint32_t> slaboff, ureg, tmp, trel;
+    DevBuf<uint32_t> slaboff, ureg, tmp, trel, midcarry;
     DevBuf<int64_t> tile_tmp0, btot, tmp_base;
     DevBuf<unsigned long long> counter;
     DevBuf<int> too_long;
@@ -815,6 +831,7 @@ static bool transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
     slabcnt.alloc(n_slabs * NBp);
     slaboff.alloc(n_slabs * NBp);
     rowcnt.alloc(std::max<int64_t>(1, n) * NBp + 8);
+    midcarry.alloc(std::max<int64_t>(1, n));
     btot.alloc(static_cast<int64_t>(nt) * NBp);
     tmp_base.alloc(static_cast<int64_t>(nt) * NBp);
     ureg.alloc(static_cast<int64_t>(nt) * NBp);
@@ -826,7 +843,7 @@ static bool transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
     const int walk_grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(n_slabs, kTrWarps), c->num_sms * 4)));
     SB_CUDA(cudaFuncSetAttribute(tr_slabcnt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_cnt)));
     tr_slabcnt_kernel<<<walk_grid, kTrWarps * 32, smem_cnt, st>>>(X.ptr.p, X.idx.p, n, tile_rows, SPT, n_slabs, NBp, rowcnt.p,
-                                                                  slabcnt.p);
+                                                                  slabcnt.p, midcarry.p);
     SB_LAUNCH_CHECK();
     mark(1);
     tr_rowscan_kernel<<<static_cast<unsigned>(static_cast<int64_t>(nt) * (NBp / 32)), 1024, 0, st>>>(slabcnt.p, n_slabs, SPT, NBp,
@@ -873,8 +890,8 @@ static bool transpose_bucketed(snapb200_ctx* c, int tile_rows, int64_t* df_local
         const size_t smem = tables + static_cast<size_t>(cap) * sizeof(uint16_t);
         SB_CUDA(cudaFuncSetAttribute(tr_slab_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         const int grid = static_cast<int>(std::min<int64_t>(n_slabs, c->num_sms));
-        tr_slab_scatter_kernel<<<grid, kTrWarps * 32, smem, st>>>(X.ptr.p, X.idx.p, n, tile_rows, SPT, n_slabs, NBp, cap, rowcnt.p,
-                                                                  slaboff.p, trel.p, tile_tmp0.p, tmp.p, too_long.p);
+        tr_slab_scatter_kernel<<<grid, kTrWarps * 64, smem, st>>>(X.ptr.p, X.idx.p, n, tile_rows, SPT, n_slabs, NBp, cap, rowcnt.p,
+                                                                  slaboff.p, trel.p, tile_tmp0.p, midcarry.p, tmp.p, too_long.p);
         SB_LAUNCH_CHECK();
         int h_long = 0;
         SB_CUDA(cudaMemcpyAsync(&h_long, too_long.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -938,15 +955,12 @@ void transpose_tiled(snapb200_ctx* c, int tile_rows, int64_t* df_local) {
     T.cnt.alloc(static_cast<int64_t>(nt) * m);
     T.segoff.alloc(static_cast<int64_t>(nt) * m);
     T.tile_base.alloc(nt + 1);
-    // Two transposes with the same output, bit for bit: the bitmap transpose above and the bucketed one
-    // below.  Measured on a B200 (profiles/README.md): 80 vs 88 ms on C3 (4.9e9 stored entries: the bucketed
-    // scatter pays a DRAM fill for every partially written 32-byte sector and its per-bucket sort is bound by
-    // the L1 / shared-memory pipe), 11.7 vs 10.4 ms on a 1/8 shard of it (6.1e8 entries: the bitmap kernel's
-    // per-unit costs weigh more).  Default: bucketed below 1e9 stored entries, bitmap above;
-    // SNAPB200_TRANSPOSE=bitmap|bucketed forces one.
+    // Two transposes with the same output, bit for bit: the bitmap transpose above (round 1) and the bucketed
+    // one below (round 2, default: 64 vs 80 ms on C3, 8.4 vs 11.7 ms on a 1/8 shard; profiles/README.md).
+    // The bitmap transpose remains for matrices with more than kTrF * kTrMaxBuckets features or rows longer
+    // than the scatter pass's staging, and under SNAPB200_TRANSPOSE=bitmap.
     const char* tr_mode = getenv("SNAPB200_TRANSPOSE");
-    bool bucketed = X.nnz < 1000000000ll;
-    if (tr_mode != nullptr && tr_mode[0] == 'b') bucketed = tr_mode[1] == 'u';
+    const bool bucketed = !(tr_mode != nullptr && tr_mode[0] == 'b' && tr_mode[1] == 'i');
     if (bucketed && ceil_div(m, kTrF) <= kTrMaxBuckets && tile_rows <= (1 << 14)) {
         if (transpose_bucketed(c, tile_rows, df_local)) return;
     }

@@ -196,3 +196,36 @@ def test_two_rank_gloo_sharding(tmp_path):
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0, o
         assert f"ok {r}" in o
+
+
+def test_row_blocks_sources():
+    """tl.RowBlocks: a backed element with chunked(), a row-sliceable lazy array and a plain iterable of CSR
+    blocks all yield the matrix's rows in order (what Engine.load_blocks assembles on the device)."""
+    X = sp.random(53, 40, density=0.2, format="csr", random_state=1)
+
+    class Backed:
+        shape = X.shape
+
+        def chunked(self, chunk_size):
+            for i in range(0, X.shape[0], chunk_size):
+                yield X[i:i + chunk_size], i, min(i + chunk_size, X.shape[0])
+
+    class Sliceable:
+        shape = X.shape
+
+        def __getitem__(self, key):
+            return X[key]
+
+    for src in (Backed(), Sliceable(), (X[i:i + 7] for i in range(0, 53, 7)), [X[:20], X[20:]]):
+        blocks = list(tl.RowBlocks(src, 40).blocks(16))
+        got = sp.vstack(blocks, format="csr")
+        assert (got != X).nnz == 0 and got.shape == X.shape
+
+    class FakeAnn:
+        def __init__(self, x):
+            self.X, self.n_vars, self.n_obs = x, 40, 53
+
+    assert isinstance(tl._get_csr(FakeAnn(Backed())), tl.RowBlocks)
+    assert sp.issparse(tl._get_csr(FakeAnn(X)))
+    with pytest.raises(ValueError):
+        tl._get_csr(FakeAnn(X.tocsc()))
