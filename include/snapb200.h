@@ -99,6 +99,16 @@ int  snapb200_load_csr(snapb200_ctx* ctx, int64_t n_local, int64_t n_global, int
                        const void* indices, int indices_bits,
                        const void* values, int value_kind, int on_device);
 
+/* Deferred value scan.  With set_defer_value_scan(1), snapb200_load_csr on host arrays loads the pattern only
+ * and starts the scan of the value array on background threads, so that the check "is every stored
+ * value 1?" overlaps the GPU's work on the matrix instead of preceding it (C3: 19.6 GB of values, ~140 ms).
+ * The caller must keep the value array alive and ask for the verdict before it trusts any result:
+ * values_verdict joins the scan (*all_ones = 1: the pattern-only result stands); otherwise it ships the
+ * values with load_values (f32 on the device; invalidates prepare) and repeats prepare / eigsh. */
+int  snapb200_set_defer_value_scan(snapb200_ctx* ctx, int on);
+int  snapb200_values_verdict(snapb200_ctx* ctx, int* all_ones);
+int  snapb200_load_values(snapb200_ctx* ctx, const void* values, int value_kind);
+
 /* The same load, block by block: the matrix arrives as a sequence of CSR row blocks (the chunks a
  * backed AnnData yields -- the reference iterates `chunked_X`, embedding.rs:76-84 -- or any iterator
  * of scipy CSR blocks) and is assembled on the device, so the host never holds more than one block.

@@ -19,6 +19,7 @@ SYMBOLS = [
     "snapb200_last_error", "snapb200_version", "snapb200_create", "snapb200_destroy",
     "snapb200_comm_unique_id", "snapb200_comm_init", "snapb200_load_csr",
     "snapb200_load_begin", "snapb200_load_append", "snapb200_load_end", "snapb200_set_geometry",
+    "snapb200_set_defer_value_scan", "snapb200_values_verdict", "snapb200_load_values",
     "snapb200_select_features", "snapb200_generate", "snapb200_shape", "snapb200_export_csr",
     "snapb200_set_feature_weights", "snapb200_prepare", "snapb200_view_norms",
     "snapb200_attach_view", "snapb200_view_frobenius", "snapb200_combine_views", "snapb200_get_vector",
@@ -75,6 +76,9 @@ def load() -> C.CDLL:
         "snapb200_load_append": [vp, i64, vp, i32, vp, i32, vp, i32],
         "snapb200_load_end": [vp, i64, i64],
         "snapb200_set_geometry": [vp, i64, i64],
+        "snapb200_set_defer_value_scan": [vp, i32],
+        "snapb200_values_verdict": [vp, C.POINTER(i32)],
+        "snapb200_load_values": [vp, vp, i32],
         "snapb200_select_features": [vp, vp, i64],
         "snapb200_generate": [vp, i64, i64, i64, i64, i32, i32, C.c_uint64, vp, vp, vp, vp],
         "snapb200_shape": [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)],

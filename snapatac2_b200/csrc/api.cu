@@ -96,6 +96,15 @@ __global__ void rows_sorted_kernel(const int64_t* __restrict__ ptr, const int32_
     if (wrong) atomicOr(bad, 2);
 }
 
+// waits for a deferred value scan (if any); returns true if every scanned value was 1
+bool join_value_scan(snapb200_ctx* c) {
+    if (c->scan_pending) {
+        if (c->scan_thread.joinable()) c->scan_thread.join();
+        c->scan_pending = false;
+    }
+    return c->scan_not_one.load() == 0;
+}
+
 void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, int64_t m, const void* indptr,
               int indptr_bits, const void* indices, int indices_bits, const void* values, int value_kind,
               int on_device) {
@@ -105,6 +114,8 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     SB_CHECK(indices_bits == 32 || indices_bits == 64, "load_csr: indices_bits must be 32 or 64");
     SB_CHECK(indptr != nullptr, "load_csr: null indptr");
     cudaStream_t st = c->stream;
+    join_value_scan(c);
+    c->scan_not_one.store(0);
     const auto wall0 = std::chrono::steady_clock::now();
     const bool dev = on_device != 0;
     // device-resident input was produced on the caller's stream(s), which this library's private
@@ -176,7 +187,15 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     X.val.release();
     if (values != nullptr && nnz > 0) {
         value_size(value_kind);
-        if (!dev) {
+        if (!dev && c->defer_value_scan) {
+            // optimistic: load the pattern only and let a background team scan the values while the GPU
+            // already works on the matrix; the caller asks for the verdict before it trusts the result
+            // (snapb200_values_verdict) and ships the values then if some were not 1
+            c->scan_pending = true;
+            c->scan_thread = std::thread([c, values, value_kind, nnz] {
+                if (!host_values_all_ones(c, values, value_kind, nnz)) c->scan_not_one.store(1);
+            });
+        } else if (!dev) {
             if (!host_values_all_ones(c, values, value_kind, nnz)) {
                 X.val.alloc(nnz);
                 stage_values(c, values, value_kind, nnz, X.val.p);
@@ -384,6 +403,7 @@ int snapb200_destroy(snapb200_ctx* c) {
     return guarded([&] {
         if (!c) return;
         cudaSetDevice(c->device);
+        join_value_scan(c);
         cudaStreamSynchronize(c->stream);
         if (c->borrowed) {   // a view context: stream and communicator belong to its main context
             c->comm = nullptr;
@@ -436,6 +456,41 @@ int snapb200_load_append(snapb200_ctx* c, int64_t n_rows, const void* indptr, in
 }
 int snapb200_load_end(snapb200_ctx* c, int64_t n_global, int64_t row0) {
     return guarded([&] { bind(c); load_end(c, n_global, row0); });
+}
+
+int snapb200_set_defer_value_scan(snapb200_ctx* c, int on) {
+    return guarded([&] {
+        SB_CHECK(c != nullptr, "null context");
+        c->defer_value_scan = on != 0;
+    });
+}
+
+int snapb200_values_verdict(snapb200_ctx* c, int* all_ones) {
+    return guarded([&] {
+        SB_CHECK(c != nullptr && all_ones != nullptr, "values_verdict: null argument");
+        *all_ones = join_value_scan(c) ? 1 : 0;
+    });
+}
+
+int snapb200_load_values(snapb200_ctx* c, const void* values, int value_kind) {
+    return guarded([&] {
+        bind(c);
+        SB_CHECK(c->loaded, "load_values: no matrix loaded");
+        SB_CHECK(values != nullptr, "load_values: null values");
+        join_value_scan(c);
+        value_size(value_kind);
+        Csr& X = c->X;
+        if (X.nnz > 0) {
+            X.val.alloc(X.nnz);
+            stage_values(c, values, value_kind, X.nnz, X.val.p);
+        }
+        c->scan_not_one.store(0);
+        c->prepared = false;
+        c->proj_ready = false;
+        c->views.clear();
+        c->S1.clear(); c->S2.clear(); c->Xt.clear(); c->xt_built = false; c->XtT.clear();
+        c->stats.bytes_h2d += 4 * X.nnz;
+    });
 }
 
 int snapb200_set_geometry(snapb200_ctx* c, int64_t n_global, int64_t row0) {

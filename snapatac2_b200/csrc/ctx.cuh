@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "../../include/snapb200.h"
 
+#include <atomic>
+#include <thread>
 #include <vector>
 
 namespace snapb {
@@ -167,6 +169,14 @@ struct snapb200_ctx {
     // 16-byte bank group, half the shared-memory traffic per entry of b = 8; the solver needs ~1.6x the
     // operator applications but each costs less than half.
     int block = 4;
+
+    // deferred scan of the host value array (load_csr with defer_value_scan): the matrix is loaded as a
+    // pattern, a background team checks that every stored value is 1 while the GPU already works;
+    // values_verdict() joins it
+    bool defer_value_scan = false;
+    bool scan_pending = false;
+    std::thread scan_thread;
+    std::atomic<int> scan_not_one{0};
 
     // block-wise load in progress (load_begin / load_append / load_end): rows and entries appended so far
     bool appending = false;

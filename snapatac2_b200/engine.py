@@ -78,17 +78,24 @@ class Engine:
             _lib.ptr(values), int(vk), 1 if on_device else 0))
         self.n_local, self.n_global, self.row0, self.m = int(n_local), int(n_global), int(row0), int(m)
 
-    def load_csr(self, X, n_global=None, row0=0, binarized: bool | None = None):
+    def load_csr(self, X, n_global=None, row0=0, binarized: bool | None = None, defer_value_scan: bool = False):
         """Load a scipy CSR row shard as it is: int32 or int64 index arrays and any supported value
         dtype go to the library untouched (pageable memory is fine -- the library stages them with
         a thread team, narrows 64-bit indices on the way and recognises an all-ones value array
         without shipping it).  ``binarized=True`` skips even the scan of the values (caller
         guarantees every stored entry is 1).  Rows must be sorted and duplicate-free; the device
-        checks that, and a matrix that fails the check is canonicalised on the host and retried."""
+        checks that, and a matrix that fails the check is canonicalised on the host and retried.
+        ``defer_value_scan=True``: the pattern is loaded at once and the all-ones scan of the values
+        runs on background threads while the caller goes on (prepare, eigsh); the caller must call
+        :meth:`values_all_ones` before trusting a result and :meth:`load_values` + recompute if it
+        returns False.  ``X`` must stay alive until then."""
         if not sp.issparse(X):
             X = sp.csr_matrix(np.asarray(X))
         if X.format != "csr":
             raise ValueError("X must be a CSR matrix (the reference rejects CSC input as well)")
+
+        _lib.check(self._lib.snapb200_set_defer_value_scan(self._ctx, 1 if defer_value_scan else 0))
+        self._pending_values = None
 
         def attempt(M):
             indptr = np.ascontiguousarray(M.indptr)
@@ -99,6 +106,7 @@ class Engine:
                 if _lib.value_kind(values.dtype) is None:
                     values = values.astype(np.float64)
             self.load_arrays(indptr, indices, values, M.shape[0], M.shape[1], n_global, row0)
+            self._pending_values = values if defer_value_scan else None
 
         try:
             attempt(X)
@@ -108,6 +116,20 @@ class Engine:
             X = X.copy()
             X.sum_duplicates()      # sorts the rows and merges duplicates (scipy's canonical format)
             attempt(X)
+
+    def values_all_ones(self) -> bool:
+        """Verdict of a deferred value scan (joins it).  True: the loaded pattern is the matrix."""
+        ok = C.c_int()
+        _lib.check(self._lib.snapb200_values_verdict(self._ctx, C.byref(ok)))
+        return bool(ok.value)
+
+    def load_values(self, values=None):
+        """Ship the value array of the loaded pattern after all (deferred scan found values other than 1)."""
+        values = self._pending_values if values is None else np.ascontiguousarray(values)
+        if _lib.value_kind(values.dtype) is None:
+            values = values.astype(np.float64)
+        _lib.check(self._lib.snapb200_load_values(self._ctx, _lib.ptr(values), int(_lib.value_kind(values.dtype))))
+        self._pending_values = None
 
     def load_blocks(self, blocks, m, n_global=None, row0=0, rows_hint=0, nnz_hint=0):
         """Assemble this rank's shard on the device from an iterable of scipy CSR row blocks (the

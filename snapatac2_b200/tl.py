@@ -163,13 +163,37 @@ def spectral_embedding(engine: Engine, X, selected_features, n_components, rando
         if n_global is not None:
             engine.set_geometry(n_global, row0)
     else:
-        engine.load_csr(X, n_global=n_global, row0=row0, binarized=binarized)
-    if mask is not None:
-        engine.select_features(mask)
-    engine.set_feature_weights(fw)
-    idf, degree = engine.prepare(want_outputs=return_parts)
-    evals, evecs = engine.eigsh(n_components, seed=random_state, tol=tol, block=block,
-                                max_basis=max_basis, max_ops=max_ops, scale_by_sqrt_eval=scale_by_sqrt_eval)
+        # the all-ones scan of X.data runs on background threads while the GPU prepares and solves; the verdict
+        # is collected before the result is returned (values other than 1: ship them and compute again)
+        engine.load_csr(X, n_global=n_global, row0=row0, binarized=binarized, defer_value_scan=not binarized)
+
+    def compute():
+        if mask is not None:
+            engine.select_features(mask)
+        engine.set_feature_weights(fw)
+        idf_, degree_ = engine.prepare(want_outputs=return_parts)
+        ev_, evec_ = engine.eigsh(n_components, seed=random_state, tol=tol, block=block,
+                                  max_basis=max_basis, max_ops=max_ops, scale_by_sqrt_eval=scale_by_sqrt_eval)
+        return ev_, evec_, idf_, degree_
+
+    def all_ones():                     # the verdict must be the same on every rank: the recomputation is collective
+        ok = engine.values_all_ones()
+        if dist.world()[1] > 1:
+            ok = bool(dist.allreduce_array(np.array([1.0 if ok else 0.0]), "min")[0] > 0.5)
+        return ok
+
+    try:
+        evals, evecs, idf, degree = compute()
+    except Exception:
+        if blocks or binarized or engine.values_all_ones():
+            raise
+        evals = None                    # the pattern-only attempt may fail where the valued matrix does not
+    if not blocks and not binarized and not all_ones():
+        if mask is not None:            # the resident pattern is already column-selected: select the values the same way
+            engine.load_csr(X, n_global=n_global, row0=row0, binarized=False)
+        else:
+            engine.load_values()
+        evals, evecs, idf, degree = compute()
     if return_parts:
         return evals, evecs, idf, degree
     return evals, evecs

@@ -419,6 +419,36 @@ def test_blockwise_ingest_equals_in_memory(engine, name):
         np.testing.assert_array_equal(got[1], want[1])
 
 
+def test_deferred_value_scan(engine):
+    """tl.spectral loads the pattern first and scans X.data in the background: a matrix whose values are all 1
+    (any dtype) stays pattern-only; one with real counts is recomputed with its values -- same numbers as the
+    synchronous load either way, also with a feature mask."""
+    X, z = load_golden("counts_300x1000")
+    k = int(z["k"])
+    ev, evec, idf, deg = tl.spectral_embedding(engine, X, None, k, 0, return_parts=True)
+    np.testing.assert_allclose(deg, z["degree"], rtol=TOL_VEC)                  # the counts were used
+    _check_against(z["evals"], z["evecs"], ev, evec)
+    mask = np.arange(1000) % 4 != 0
+    ev_m, _ = tl.spectral_embedding(engine, X, mask, k, 0)
+    ev_o, _ = oracle.spectral_embedding(X, mask, k, 0)
+    np.testing.assert_allclose(ev_m, ev_o, rtol=TOL_EVAL)
+    # binarised copy: float64 ones -> pattern-only kernels, no value array on the device
+    B = X.copy()
+    B.data[:] = 1.0
+    ev_b, evec_b, _, deg_b = tl.spectral_embedding(engine, B, None, k, 0, return_parts=True)
+    assert engine.values_all_ones()
+    ev_ob, evec_ob, _, deg_ob = oracle.spectral_embedding(B, None, k, 0, return_parts=True)
+    np.testing.assert_allclose(deg_b, deg_ob, rtol=TOL_VEC)
+    _check_against(ev_ob, evec_ob, ev_b, evec_b)
+    # the low-level switch: verdict and late shipment of the values
+    engine.load_csr(X, defer_value_scan=True)
+    assert not engine.values_all_ones()
+    engine.load_values()
+    engine.set_feature_weights(None)
+    _, deg2 = engine.prepare()
+    np.testing.assert_allclose(deg2, z["degree"], rtol=TOL_VEC)
+
+
 def test_row_gather_between_contexts(engine):
     from snapatac2_b200 import Engine
     spec = synth.make_spec(900, 5000, 120, n_clusters=6, seed=3)
