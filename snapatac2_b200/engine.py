@@ -61,7 +61,8 @@ class Engine:
         self.rank, self.nranks = int(rank), int(nranks)
 
     # ------------------------------------------------------------ data in
-    def load_arrays(self, indptr, indices, values, n_local, m, n_global=None, row0=0, on_device=False):
+    def load_arrays(self, indptr, indices, values, n_local, m, n_global=None, row0=0, on_device=False,
+                    defer_value_scan=False):
         """Load a CSR row shard from raw arrays (numpy, or torch CUDA tensors
         with ``on_device=True``).  ``values=None`` means a binarised pattern."""
         n_global = n_local if n_global is None else n_global
@@ -72,6 +73,8 @@ class Engine:
             vk = _lib.value_kind(dt)
             if vk is None:
                 raise TypeError(f"unsupported value dtype {dt}")
+        # (the switch is per load: a context never keeps it on for a later caller)
+        _lib.check(self._lib.snapb200_set_defer_value_scan(self._ctx, 1 if (defer_value_scan and not on_device) else 0))
         _lib.check(self._lib.snapb200_load_csr(
             self._ctx, int(n_local), int(n_global), int(row0), int(m),
             _lib.ptr(indptr), bits(indptr), _lib.ptr(indices), bits(indices),
@@ -94,7 +97,6 @@ class Engine:
         if X.format != "csr":
             raise ValueError("X must be a CSR matrix (the reference rejects CSC input as well)")
 
-        _lib.check(self._lib.snapb200_set_defer_value_scan(self._ctx, 1 if defer_value_scan else 0))
         self._pending_values = None
 
         def attempt(M):
@@ -105,7 +107,8 @@ class Engine:
                 values = np.ascontiguousarray(M.data)
                 if _lib.value_kind(values.dtype) is None:
                     values = values.astype(np.float64)
-            self.load_arrays(indptr, indices, values, M.shape[0], M.shape[1], n_global, row0)
+            self.load_arrays(indptr, indices, values, M.shape[0], M.shape[1], n_global, row0,
+                             defer_value_scan=defer_value_scan)
             self._pending_values = values if defer_value_scan else None
 
         try:
