@@ -20,6 +20,7 @@
 // 4b bytes of shared-memory bandwidth, which is what bounds the kernel.
 #include "ctx.cuh"
 
+#include <stdlib.h>
 #include <algorithm>
 
 namespace snapb {
@@ -143,8 +144,8 @@ __device__ __noinline__ void store_partial(float4 a, float4 b, int row, int lane
 // the chunk's metadata, the epilogue and its store cost about as much as kChunkCost groups); ranges
 // of many short chunks would otherwise take longer than ranges of few long ones (ncu on a 1/8
 // shard of C3: slowest SM 1.45x the average in pass 1).
-constexpr int64_t kChunkCost = 3;
-__device__ int64_t chunk_lower_bound(const int64_t* __restrict__ chunk_off, int64_t n, int64_t target) {
+constexpr int64_t kChunkCostDefault = 3;
+__device__ int64_t chunk_lower_bound(const int64_t* __restrict__ chunk_off, int64_t n, int64_t target, int64_t kChunkCost) {
     int64_t lo = 0, hi = n;
     while (lo < hi) {
         const int64_t mid = (lo + hi) >> 1;
@@ -152,13 +153,21 @@ __device__ int64_t chunk_lower_bound(const int64_t* __restrict__ chunk_off, int6
     }
     return lo;
 }
+// (SNAPB200_CHUNK_COST overrides the per-chunk charge: tuning aid)
+static int64_t chunk_cost() {
+    static const int64_t v = [] {
+        const char* e = getenv("SNAPB200_CHUNK_COST");
+        return e ? static_cast<int64_t>(atoi(e)) : kChunkCostDefault;
+    }();
+    return v;
+}
 
 template <int B, bool HAS_VAL, int U>
 __global__ void __launch_bounds__(kTiledThreads, 1)
 sell_spmm_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restrict__ chunk_groups,
                  const int64_t* __restrict__ chunk_off, const uint16_t* __restrict__ data, const float* __restrict__ vals,
                  const float* __restrict__ in, float* __restrict__ partial, int64_t n_chunks, int64_t chunks_per_tile,
-                 int tile_cols, int64_t ncols, int64_t nrows) {
+                 int tile_cols, int64_t ncols, int64_t nrows, int64_t kChunkCost) {
     constexpr int RB = 4 * B;   // bytes per dense row
     extern __shared__ __align__(128) unsigned char smem[];
     float* tile = reinterpret_cast<float*>(smem);
@@ -176,8 +185,8 @@ sell_spmm_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restri
         const int64_t groups = chunk_off[n_chunks] + kChunkCost * n_chunks;
         const int64_t g_lo = static_cast<int64_t>((static_cast<__int128>(groups) * blockIdx.x) / gridDim.x);
         const int64_t g_hi = static_cast<int64_t>((static_cast<__int128>(groups) * (blockIdx.x + 1)) / gridDim.x);
-        range[0] = (blockIdx.x == 0) ? 0 : chunk_lower_bound(chunk_off, n_chunks, g_lo);
-        range[1] = (blockIdx.x == gridDim.x - 1) ? n_chunks : chunk_lower_bound(chunk_off, n_chunks, g_hi);
+        range[0] = (blockIdx.x == 0) ? 0 : chunk_lower_bound(chunk_off, n_chunks, g_lo, kChunkCost);
+        range[1] = (blockIdx.x == gridDim.x - 1) ? n_chunks : chunk_lower_bound(chunk_off, n_chunks, g_hi, kChunkCost);
     }
     __syncthreads();
     const int64_t c_begin = range[0], c_end = range[1];
@@ -318,7 +327,7 @@ __global__ void __launch_bounds__(kTiledThreads, 1)
 sell_spmv64_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __restrict__ chunk_groups,
                    const int64_t* __restrict__ chunk_off, const uint16_t* __restrict__ data, const float* __restrict__ vals,
                    const double* __restrict__ in, double* __restrict__ partial, int64_t n_chunks, int64_t chunks_per_tile,
-                   int tile_cols, int64_t ncols, int64_t nrows) {
+                   int tile_cols, int64_t ncols, int64_t nrows, int64_t kChunkCost) {
     constexpr int U = 2;
     extern __shared__ __align__(128) unsigned char smem[];
     double* tile = reinterpret_cast<double*>(smem);
@@ -332,8 +341,8 @@ sell_spmv64_kernel(const int32_t* __restrict__ chunk_rows, const int32_t* __rest
         const int64_t groups = chunk_off[n_chunks] + kChunkCost * n_chunks;
         const int64_t g_lo = static_cast<int64_t>((static_cast<__int128>(groups) * blockIdx.x) / gridDim.x);
         const int64_t g_hi = static_cast<int64_t>((static_cast<__int128>(groups) * (blockIdx.x + 1)) / gridDim.x);
-        range[0] = (blockIdx.x == 0) ? 0 : chunk_lower_bound(chunk_off, n_chunks, g_lo);
-        range[1] = (blockIdx.x == gridDim.x - 1) ? n_chunks : chunk_lower_bound(chunk_off, n_chunks, g_hi);
+        range[0] = (blockIdx.x == 0) ? 0 : chunk_lower_bound(chunk_off, n_chunks, g_lo, kChunkCost);
+        range[1] = (blockIdx.x == gridDim.x - 1) ? n_chunks : chunk_lower_bound(chunk_off, n_chunks, g_hi, kChunkCost);
     }
     __syncthreads();
     const int64_t c_begin = range[0], c_end = range[1];
@@ -433,12 +442,12 @@ void spmm_impl(snapb200_ctx* c, const Sell& S, const float* in, float* out, cons
         auto k = sell_spmm_kernel<B, true, 1>;
         SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         k<<<grid, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_groups.p, S.chunk_off.p, S.data.p, S.vals.p, in,
-                                            c->partial.p, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols, S.nrows);
+                                            c->partial.p, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols, S.nrows, chunk_cost());
     } else {
         auto k = sell_spmm_kernel<B, false, 2>;
         SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         k<<<grid, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_groups.p, S.chunk_off.p, S.data.p, nullptr, in,
-                                            c->partial.p, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols, S.nrows);
+                                            c->partial.p, S.n_chunks, S.chunks_per_tile, S.tile_cols, S.ncols, S.nrows, chunk_cost());
     }
     SB_LAUNCH_CHECK();
     const unsigned rb = static_cast<unsigned>(ceil_div(S.nrows * (B / 4), 256));
@@ -508,7 +517,7 @@ void sell_spmv64(snapb200_ctx* c, const Sell& S, const double* x, int mode, cons
         SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));         \
         k<<<c->num_sms, kTiledThreads, smem, st>>>(S.chunk_rows.p, S.chunk_groups.p, S.chunk_off.p, S.data.p,          \
                                                    S.vals.p, x, part, S.n_chunks, S.chunks_per_tile, S.tile_cols,      \
-                                                   S.ncols, S.nrows);                                                  \
+                                                   S.ncols, S.nrows, chunk_cost());                                    \
     } while (0)
     if (S.vals.p) { if (sq) SB_SPMV64(true, true); else SB_SPMV64(true, false); }
     else          SB_SPMV64(false, false);
