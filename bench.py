@@ -491,7 +491,7 @@ def run_ours(args):
             "solver": {kk: stats[kk] for kk in ("n_ops", "n_restarts", "basis_cols", "max_residual", "ms_transpose",
                                                 "ms_prepare", "ms_format", "ms_eigsh", "ms_spmm", "ms_ortho", "ms_comm", "ms_host",
                                                 "spmm_tiled", "ms_prepare_wall", "ms_pool", "pool_mallocs", "converged",
-                                                "n_spec_ops", "ms_d2h")},
+                                                "n_spec_ops", "ms_d2h", "fused_allreduce")},
             "evals_head": [float(x) for x in evals[:4]],
         }
         print(json.dumps(line), flush=True)

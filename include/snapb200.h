@@ -67,6 +67,8 @@ typedef struct snapb200_stats {
     double ms_d2h;         /* last eigsh: final rotation + copy of the eigenvectors to the host            */
     int64_t bytes_h2d;     /* last load_csr: bytes that crossed PCIe (indptr + int32 indices [+ f32 values]) */
     int64_t host_threads;  /* last load_csr: size of the host staging team                                 */
+    int64_t fused_allreduce; /* last eigsh: 1 = the small fp64 all-reduces of the block step ran inside the Gram
+                              kernels over NVLink peer memory (csrc/peer.cuh), 0 = NCCL (or a single rank)   */
 } snapb200_stats;
 
 /* Library / error plumbing. */
@@ -79,7 +81,10 @@ int  snapb200_destroy(snapb200_ctx* ctx);
 
 /* Multi-GPU (one rank per context).  `id` is an opaque 128-byte NCCL unique
  * id produced on rank 0 and distributed by the caller (torch.distributed,
- * MPI, a file ...).  Without comm_init the context is a single-rank job. */
+ * MPI, a file ...).  Without comm_init the context is a single-rank job.
+ * comm_init also sets up CUDA-IPC mailboxes in every rank's memory for the small all-reduces that are
+ * fused into the eigensolver's Gram kernels (plain stores over NVLink); if that is not possible
+ * (ranks in one process, no peer access, SNAPB200_NO_PEER set) those go through NCCL. */
 int  snapb200_comm_unique_id(char id[128]);
 int  snapb200_comm_init(snapb200_ctx* ctx, int rank, int nranks, const char id[128]);
 

@@ -136,7 +136,8 @@ struct Sell {
 constexpr int kSellTileBytes = 196608;     // 192 KB of shared memory: 6144 rows (b=8) / 12288 rows (b=4)
 constexpr int kSellWindowRows = 8192;      // rows sorted together (one CTA-wide sort)
 
-struct Comm;  // NCCL wrapper (comm.cu)
+struct Comm;     // NCCL wrapper (comm.cu)
+struct PeerBox;  // mailboxes of the fused small all-reduce over peer memory (peer.cuh)
 
 }  // namespace snapb
 
@@ -228,6 +229,10 @@ namespace snapb {
 void comm_unique_id(char id[128]);
 void comm_init(snapb200_ctx* c, int rank, int nranks, const char id[128]);
 void comm_destroy(snapb200_ctx* c);
+void peer_setup(snapb200_ctx* c);
+// descriptor of the next fused exchange (advances the sequence number); false: use NCCL
+bool peer_box(snapb200_ctx* c, PeerBox* out);
+bool peer_error(snapb200_ctx* c);
 void allreduce_f32(snapb200_ctx* c, float* buf, int64_t count);
 void allreduce_f64(snapb200_ctx* c, double* buf, int64_t count);
 void allreduce_i64(snapb200_ctx* c, int64_t* buf, int64_t count);

@@ -10,6 +10,7 @@
 // the solver is bitwise reproducible.
 #include "ctx.cuh"
 #include "dense.cuh"
+#include "peer.cuh"
 
 #include <cmath>
 #include <vector>
@@ -95,7 +96,7 @@ template <int B>
 __global__ void __launch_bounds__(kGramWarps * 32)
 gram_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const float* __restrict__ Zx, int64_t ldzx, int nzx,
             const float* __restrict__ Z, int64_t ldz, int64_t n, double* __restrict__ partial,
-            double* __restrict__ out, unsigned* __restrict__ counter) {
+            double* __restrict__ out, unsigned* __restrict__ counter, const PeerBox box) {
     constexpr int NT = (B + 7) / 8;
     __shared__ double red[kGramWarps][NT][64];
     __shared__ double lastred[kLastRedSlots];
@@ -165,7 +166,9 @@ gram_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const float* __re
         }
         __syncthreads();
     }
-    last_cta_reduce(partial, gridDim.x, ncx * B, out, counter, gridDim.x * gridDim.y, lastred);
+    // the CTA that sums the partials also sums over the ranks: all-reduce through the peers' mailboxes (peer.cuh)
+    if (last_cta_reduce(partial, gridDim.x, ncx * B, out, counter, gridDim.x * gridDim.y, lastred))
+        peer_allreduce(box, out, ncx * B);
 }
 
 // --------------------------------------------------------------------------
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(kPcaWarps * 32)
 project_chol_apply_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, const double* __restrict__ Hext,
                           const double* __restrict__ G0, float* __restrict__ Z, int64_t n,
                           double* __restrict__ chol1_out, double* __restrict__ partial, double* __restrict__ G3,
-                          unsigned* __restrict__ counter) {
+                          unsigned* __restrict__ counter, const PeerBox box) {
     constexpr int NT = (B + 7) / 8;
     constexpr int BB = B * B;
     extern __shared__ __align__(16) double pca_smem[];
@@ -350,7 +353,7 @@ project_chol_apply_kernel(const float* __restrict__ Q, int64_t ldq, int ncq, con
         for (int w = 0; w < kPcaWarps; ++w) t += sred[w * BB + e];
         partial[static_cast<int64_t>(blockIdx.x) * BB + e] = t;
     }
-    last_cta_reduce(partial, gridDim.x, BB, G3, counter, gridDim.x, lastred);
+    if (last_cta_reduce(partial, gridDim.x, BB, G3, counter, gridDim.x, lastred)) peer_allreduce(box, G3, BB);
 }
 
 // --------------------------------------------------------------------------
@@ -532,15 +535,16 @@ void DenseOps<B>::reserve(snapb200_ctx* c, int64_t n, int ld) {
 
 template <int B>
 void DenseOps<B>::gram_ext(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Zx, int64_t ldzx, int nzx,
-                           const float* Z, int64_t ldz, int64_t n, double* H) {
+                           const float* Z, int64_t ldz, int64_t n, double* H, const PeerBox* box) {
     SB_CHECK(ncq % 4 == 0 && ldq % 4 == 0 && nzx % 4 == 0 && ldzx % 4 == 0, "gram: widths must be multiples of 4");
     const int ncx = ncq + nzx;
     const int parts = row_chunks(c, n);
     reserve(c, n, 0);
     partial.ensure(static_cast<int64_t>(parts) * ncx * B);
     dim3 grid(parts, static_cast<unsigned>(ceil_div(ncx, kGramCols)));
+    SB_CHECK(box == nullptr || box->nranks <= 1 || ncx * B <= kPeerMaxLen, "gram: vector too long for the peer mailboxes");
     gram_kernel<B><<<grid, kGramWarps * 32, 0, c->stream>>>(Q, ldq, ncq, Zx, ldzx, nzx, Z, ldz, n, partial.p, H,
-                                                            counters.p);
+                                                            counters.p, box ? *box : PeerBox());
     SB_LAUNCH_CHECK();
     count_launch(c);
 }
@@ -548,12 +552,12 @@ void DenseOps<B>::gram_ext(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq
 template <int B>
 void DenseOps<B>::gram(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Z, int64_t ldz, int64_t n,
                        double* H) {
-    gram_ext(c, Q, ldq, ncq, nullptr, 4, 0, Z, ldz, n, H);
+    gram_ext(c, Q, ldq, ncq, nullptr, 4, 0, Z, ldz, n, H, nullptr);
 }
 
 template <int B>
 void DenseOps<B>::project_chol_apply(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const double* Hext,
-                                     const double* G0, float* Z, int64_t n, double* chol1, double* G3) {
+                                     const double* G0, float* Z, int64_t n, double* chol1, double* G3, const PeerBox* box) {
     SB_CHECK(ncq % 4 == 0 && ldq % 4 == 0, "project: basis width must be a multiple of 4");
     const int blocks = pca_blocks(c, n);
     reserve(c, n, 0);
@@ -563,7 +567,8 @@ void DenseOps<B>::project_chol_apply(snapb200_ctx* c, const float* Q, int64_t ld
         SB_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         pca_smem_set = static_cast<int>(smem);
     }
-    k<<<blocks, kPcaWarps * 32, smem, c->stream>>>(Q, ldq, ncq, Hext, G0, Z, n, chol1, partial_g.p, G3, counters.p + 1);
+    k<<<blocks, kPcaWarps * 32, smem, c->stream>>>(Q, ldq, ncq, Hext, G0, Z, n, chol1, partial_g.p, G3, counters.p + 1,
+                                                   box ? *box : PeerBox());
     SB_LAUNCH_CHECK();
     count_launch(c);
 }
@@ -650,10 +655,10 @@ static double ortho_selftest_impl(snapb200_ctx* c, int64_t n, int ncols) {
     for (int nb = 0; nb + B <= ncols; nb += B) {
         ops.random_block(c, Z.p, B, n, 77, 1000 + nb);
         const int nbq = std::max(nb, 4);   // the kernels want at least one float4 column group of basis
-        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, H1.p);
+        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, H1.p, nullptr);
         ops.project_out(c, Q.p, ld, nbq, H1.p, n, Z.p, B);
-        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, H2.p);
-        ops.project_chol_apply(c, Q.p, ld, nbq, H2.p, H1.p + static_cast<int64_t>(nbq) * B, Z.p, n, chol1.p, G3.p);
+        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, H2.p, nullptr);
+        ops.project_chol_apply(c, Q.p, ld, nbq, H2.p, H1.p + static_cast<int64_t>(nbq) * B, Z.p, n, chol1.p, G3.p, nullptr);
         ops.chol_append(c, G3.p, chol1.p, Z.p, n, Q.p + nb, ld, ones.p, Vr.p, out.p, true);
         SB_CUDA(cudaMemcpyAsync(hout.data(), out.p, sizeof(double) * (B * B + B), cudaMemcpyDeviceToHost, c->stream));
         SB_CUDA(cudaStreamSynchronize(c->stream));

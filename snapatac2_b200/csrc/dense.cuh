@@ -2,6 +2,7 @@
 #pragma once
 
 #include "ctx.cuh"
+#include "peer.cuh"
 
 namespace snapb {
 
@@ -17,8 +18,9 @@ struct DenseOps {
     void reserve(snapb200_ctx* c, int64_t n, int ld);
 
     // H[(ncq + nzx) x B] = [Q[:, 0:ncq] | Zx[:, 0:nzx]]^T Z   (one kernel; Zx = Z gives Q^T Z and Z^T Z at once)
+    // box (optional): the result is also summed over the ranks through the peers' mailboxes, inside the kernel
     void gram_ext(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Zx, int64_t ldzx, int nzx,
-                  const float* Z, int64_t ldz, int64_t n, double* H);
+                  const float* Z, int64_t ldz, int64_t n, double* H, const PeerBox* box);
     // H[ncq x B] = Q[:, 0:ncq]^T Z
     void gram(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const float* Z, int64_t ldz, int64_t n, double* H);
     // Z -= Q[:, 0:ncq] H
@@ -26,7 +28,7 @@ struct DenseOps {
     // Z (packed n x B) <- (Z - Q H) R1^-1 with R1 = chol(G' - H^T H), Hext = [H ; G'];  chol1 = {R1[B*B], flags[B]};
     // G3 = Gram of the result.  G0 (optional): Gram of the block before any projection (dependence test).
     void project_chol_apply(snapb200_ctx* c, const float* Q, int64_t ldq, int ncq, const double* Hext, const double* G0,
-                            float* Z, int64_t n, double* chol1, double* G3);
+                            float* Z, int64_t n, double* chol1, double* G3, const PeerBox* box);
     // R2 = chol(G3); dst = Z R2^-1 (leading dimension ldd), Vr = rscale .* dst (if rscale);
     // out = {Rtot = R2 R1 [B*B], flags[B]}.  rows_too = false: factorisation and `out` only.
     void chol_append(snapb200_ctx* c, const double* G3, const double* chol1, const float* Z, int64_t n, float* dst,

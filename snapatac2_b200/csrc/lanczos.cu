@@ -20,6 +20,7 @@
 //   residual of a Ritz pair = || R s_last ||  with R the CholQR factor.
 #include "ctx.cuh"
 #include "dense.cuh"
+#include "peer.cuh"
 
 #include <stdlib.h>
 #include <algorithm>
@@ -235,13 +236,20 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
 
     // everything after the operator, up to (and, if `append_at` >= 0, including) the append
     auto ortho_block = [&](int nbq, int append_at) {
-        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, dH1);
-        allreduce_f64(c, dH1, static_cast<int64_t>(nbq + B) * B);
+        // the three small all-reduces: fused into the producing kernels over peer memory (peer.cuh) when the
+        // mailboxes are up, NCCL otherwise
+        PeerBox box;
+        bool fused = peer_box(c, &box);
+        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, dH1, fused ? &box : nullptr);
+        if (!fused) allreduce_f64(c, dH1, static_cast<int64_t>(nbq + B) * B);
         ops.project_out(c, Q.p, ld, nbq, dH1, n, Z.p, B);
-        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, dH2);
-        allreduce_f64(c, dH2, static_cast<int64_t>(nbq + B) * B);
-        ops.project_chol_apply(c, Q.p, ld, nbq, dH2, dH1 + static_cast<int64_t>(nbq) * B, Z.p, n, dChol1.p, dG3.p);
-        allreduce_f64(c, dG3.p, B * B);
+        fused = peer_box(c, &box);
+        ops.gram_ext(c, Q.p, ld, nbq, Z.p, B, B, Z.p, B, n, dH2, fused ? &box : nullptr);
+        if (!fused) allreduce_f64(c, dH2, static_cast<int64_t>(nbq + B) * B);
+        fused = peer_box(c, &box);
+        ops.project_chol_apply(c, Q.p, ld, nbq, dH2, dH1 + static_cast<int64_t>(nbq) * B, Z.p, n, dChol1.p, dG3.p,
+                               fused ? &box : nullptr);
+        if (!fused) allreduce_f64(c, dG3.p, B * B);
         if (append_at >= 0)
             ops.chol_append(c, dG3.p, dChol1.p, Z.p, n, Q.p + append_at, ld, c->r.p, c->Vr.p, dOut, true);
         else
@@ -461,6 +469,7 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
     SB_CUDA(cudaStreamSynchronize(st));
     for (auto& es : evs)
         for (auto& e : es) cudaEventDestroy(e);
+    SB_CHECK(!peer_error(c), "eigsh: a rank never arrived at a fused all-reduce (peer mailbox timed out)");
 
     c->stats.ms_eigsh = wall.ms();
     c->stats.ms_spmm = ms_spmm;
@@ -473,6 +482,10 @@ void eigsh_impl(snapb200_ctx* c, int k, int64_t seed, double tol, int max_basis,
     c->stats.basis_cols = nb;
     c->stats.block = B;
     c->stats.n_spec_ops = n_spec;
+    {
+        PeerBox probe;
+        c->stats.fused_allreduce = (c->nranks > 1 && peer_box(c, &probe)) ? 1 : 0;   // (advances the sequence on every rank alike)
+    }
     // converged: every wanted pair met the tolerance, or the Krylov space is exhausted (the Ritz
     // pairs are then exact).  Not converged: max_ops reached first -- scipy's eigsh raises
     // ArpackNoConvergence there; the Python mirror does the same from this flag.
