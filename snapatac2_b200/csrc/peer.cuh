@@ -75,6 +75,7 @@ __device__ __forceinline__ void peer_allreduce(const PeerBox& box, double* vec, 
                 break;
             }
         }
+        __threadfence_system();
     }
     __syncthreads();
     const double* base = box.data[box.rank] + static_cast<size_t>(slot) * box.nranks * kPeerMaxLen;
