@@ -69,6 +69,8 @@ typedef struct snapb200_stats {
     int64_t host_threads;  /* last load_csr: size of the host staging team                                 */
     int64_t fused_allreduce; /* last eigsh: 1 = the small fp64 all-reduces of the block step ran inside the Gram
                               kernels over NVLink peer memory (csrc/peer.cuh), 0 = NCCL (or a single rank)   */
+    int64_t bytes_h2d_indices; /* last index transfer: bytes that crossed PCIe for the column indices (2 per entry when
+                              delta-encoded, see csrc/ingest.cu; 4 otherwise)                               */
 } snapb200_stats;
 
 /* Library / error plumbing. */
@@ -252,6 +254,12 @@ int  snapb200_get_stream(snapb200_ctx* ctx, void** stream);
  * Rayleigh-Ritz eigensolver (a: n x n row-major, destroyed; eigenvalues
  * ascending in w, eigenvectors in the columns of a) and needs no GPU. */
 int  snapb200_dense_selftest(snapb200_ctx* ctx, int64_t n, int ncq, int p, double* max_rel_err);
+/* Host-only replay of the delta encoding the index transfer uses (csrc/ingest.cu: 2 bytes per stored
+ * entry over PCIe, decoded by a kernel): encodes `count` indices chunk by chunk and decodes them with a
+ * scalar loop.  Returns 0 = identical, 1 = a chunk would fall back to plain int32, -1 = mismatch, -2 = bad
+ * arguments.  No device work; test infrastructure for the CPU suite. */
+int  snapb200_delta_selftest_host(const void* indices, int index_bits, int64_t count, int64_t* n_side);
+
 /* ortho_selftest builds an orthonormal basis of `ncols` columns from random blocks of width `block`
  * with the eigensolver's fused orthogonalisation kernels and returns max |Q^T Q - I|. */
 int  snapb200_ortho_selftest(snapb200_ctx* ctx, int64_t n, int ncols, int block, double* max_err);

@@ -161,6 +161,7 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     SB_CHECK(nnz == 0 || indices != nullptr, "load_csr: null indices");
     X.nnz = nnz;
     X.idx.alloc(std::max<int64_t>(1, nnz));
+    c->stats.bytes_h2d_indices = 0;
 
     DevBuf<int> bad;
     bad.alloc(1);
@@ -244,7 +245,7 @@ void load_csr(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, 
     SB_CHECK(!(hbad & 1), "load_csr: column index out of range");
     SB_CHECK(!(hbad & 2), "load_csr: column indices must be strictly increasing within every row (sorted, no duplicates)");
     c->stats.ms_load = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
-    c->stats.bytes_h2d = dev ? 0 : static_cast<int64_t>((indptr_bits / 8) * (n_local + 1) + 4 * nnz + (X.has_values() ? 4 * nnz : 0));
+    c->stats.bytes_h2d = dev ? 0 : static_cast<int64_t>((indptr_bits / 8) * (n_local + 1) + (X.has_values() ? 4 * nnz : 0)) + c->stats.bytes_h2d_indices;
     c->stats.host_threads = dev ? 0 : host_threads(c);
     c->n_local = n_local;
     c->n_global = n_global;
@@ -284,6 +285,7 @@ void load_begin(snapb200_ctx* c, int64_t m, int64_t rows_hint, int64_t nnz_hint)
     c->appending = true;
     c->app_rows = c->app_nnz = 0;
     c->stats.bytes_h2d = 0;
+    c->stats.bytes_h2d_indices = 0;
 }
 
 void load_append(snapb200_ctx* c, int64_t n_rows, const void* indptr, int indptr_bits, const void* indices,
@@ -294,6 +296,7 @@ void load_append(snapb200_ctx* c, int64_t n_rows, const void* indptr, int indptr
     SB_CHECK(indices_bits == 32 || indices_bits == 64, "load_append: indices_bits must be 32 or 64");
     Csr& X = c->X;
     cudaStream_t st = c->stream;
+    const int64_t idx_bytes0 = c->stats.bytes_h2d_indices;
     auto at = [&](int64_t i) -> int64_t {
         return indptr_bits == 64 ? static_cast<const int64_t*>(indptr)[i] : static_cast<const int32_t*>(indptr)[i];
     };
@@ -329,7 +332,7 @@ void load_append(snapb200_ctx* c, int64_t n_rows, const void* indptr, int indptr
     SB_CUDA(cudaStreamSynchronize(st));   // hp is a host temporary
     c->app_rows += n_rows;
     c->app_nnz += nnz;
-    c->stats.bytes_h2d += 8 * n_rows + 4 * nnz + (X.has_values() ? 4 * nnz : 0);
+    c->stats.bytes_h2d += 8 * n_rows + (X.has_values() ? 4 * nnz : 0) + (c->stats.bytes_h2d_indices - idx_bytes0);
 }
 
 void load_end(snapb200_ctx* c, int64_t n_global, int64_t row0) {
@@ -745,6 +748,15 @@ int snapb200_get_stream(snapb200_ctx* c, void** stream) {
 }
 
 // ---- test hooks (not part of the reference-facing surface) -----------------
+int snapb200_delta_selftest_host(const void* indices, int index_bits, int64_t count, int64_t* n_side) {
+    int verdict = -2;
+    const int rc = guarded([&] {
+        SB_CHECK(index_bits == 32 || index_bits == 64, "index_bits must be 32 or 64");
+        verdict = delta_selftest_host(indices, index_bits, count, n_side);
+    });
+    return rc != 0 ? -2 : verdict;
+}
+
 int snapb200_ortho_selftest(snapb200_ctx* c, int64_t n, int ncols, int block, double* max_err) {
     return guarded([&] { bind(c); *max_err = ortho_selftest(c, n, ncols, block); });
 }

@@ -211,6 +211,7 @@ struct snapb200_ctx {
     snapb::PinBuf<unsigned char> pinned;
     snapb::PinBuf<unsigned char> ring;          // pinned ring of the host staging team (ingest.cu)
     std::vector<cudaEvent_t> ring_events;
+    snapb::DevBuf<unsigned char> ring_dev;      // device side of the ring (delta-encoded index chunks before decoding)
 
     // multi-view (multi_spectral): further views chained behind this context by combine_views();
     // they share this context's stream and communicator (attach_view) and are owned by the caller
@@ -240,6 +241,7 @@ void allreduce_i64(snapb200_ctx* c, int64_t* buf, int64_t count);
 // ---- ingest.cu: threaded staging between pageable host arrays and the device
 int host_threads(const snapb200_ctx* c);
 bool stage_indices(snapb200_ctx* c, const void* src, int bits, int64_t count, int32_t* dst_dev);
+int delta_selftest_host(const void* src, int bits, int64_t count, int64_t* n_side);
 bool host_values_all_ones(snapb200_ctx* c, const void* values, int kind, int64_t count);
 void stage_values(snapb200_ctx* c, const void* src, int kind, int64_t count, float* dst_dev);
 void copy_to_host(snapb200_ctx* c, void* dst, const void* src_dev, size_t bytes);

@@ -12,6 +12,7 @@
 // only ever carries 4 bytes per stored entry.  Whether the values are all ones is decided by a
 // threaded scan on the host: a binarised matrix never ships its values at all.
 #include "ctx.cuh"
+#include "delta_encode.h"
 
 #include <immintrin.h>
 #include <stdlib.h>
@@ -19,6 +20,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -57,6 +59,12 @@ Ring ring_of(snapb200_ctx* c, int threads) {
     return Ring{c, slots, c->ring.p, c->ring_events};
 }
 
+// wall-clock accounting of the staging team (printed under SNAPB200_DEBUG): nanoseconds summed over threads
+std::atomic<int64_t> g_ns_wait{0}, g_ns_work{0}, g_ns_api{0};
+inline int64_t now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // Run `work(j)` for j in [0, n_chunks) on a team of threads; chunk j uses ring slot j % slots and
 // may only touch it once chunk j - slots has released it (release order is tracked per slot).
 // `work(j, slot_ptr, event)` must leave the slot's last device operation recorded in `event`
@@ -76,6 +84,7 @@ void run_ring(Ring& r, int64_t n_chunks, int threads, Work work) {
                 if (j >= n_chunks) break;
                 const int s = static_cast<int>(j % r.slots);
                 const int64_t want = j - r.slots;
+                const int64_t t_w0 = now_ns();
                 if (want >= 0) {
                     while (released[s].load(std::memory_order_acquire) != want) {
                         if (failed.load()) return;
@@ -83,6 +92,7 @@ void run_ring(Ring& r, int64_t n_chunks, int threads, Work work) {
                     }
                     SB_CUDA(cudaEventSynchronize(r.ev[s]));
                 }
+                g_ns_wait.fetch_add(now_ns() - t_w0, std::memory_order_relaxed);
                 work(j, r.slot(s), r.ev[s]);
                 released[s].store(j, std::memory_order_release);
             }
@@ -187,7 +197,114 @@ void to_f32_kind(const void* v, int kind, int64_t off, int64_t n, float* out) {
     }
 }
 
+// ---- delta-encoded index transfer: encoder in delta_encode.h, decoder here ---------------------------
+// one CTA per tile: segmented inclusive prefix sum (a marker restarts the sum at its side value)
+__global__ void __launch_bounds__(256)
+decode_deltas_kernel(const unsigned char* __restrict__ chunk, int32_t* __restrict__ out) {
+    const DeltaHeader* hd = reinterpret_cast<const DeltaHeader*>(chunk);
+    const int n = static_cast<int>(hd->n_entries), n_tiles = static_cast<int>(hd->n_tiles);
+    const uint16_t* d16 = reinterpret_cast<const uint16_t*>(chunk + sizeof(DeltaHeader));
+    const size_t d_bytes = (static_cast<size_t>(n) * 2 + 31) & ~static_cast<size_t>(31);
+    const uint32_t* tile_side = reinterpret_cast<const uint32_t*>(chunk + sizeof(DeltaHeader) + d_bytes);
+    const int32_t* side = reinterpret_cast<const int32_t*>(tile_side + n_tiles + 1);
+    __shared__ int32_t s_out[kDeltaTile];
+    __shared__ int s_wv[8], s_wf[8], s_wc[8];
+    const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int a = t * kDeltaTile;
+    const int e0 = a + tid * 8;
+    // thread-local fold of 8 consecutive entries: value since the last marker (or the plain sum), marker seen?, markers
+    int dv[8];
+    unsigned marks = 0;
+    int v = 0, f = 0, cnt = 0;
+    uint4 raw = make_uint4(0, 0, 0, 0);
+    if (e0 < n) raw = *reinterpret_cast<const uint4*>(d16 + e0);        // 16-byte aligned; the delta area is padded to 32 B
+    const unsigned rw[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const int i = e0 + q;
+        dv[q] = (i < n) ? static_cast<int>((rw[q >> 1] >> ((q & 1) * 16)) & 0xFFFFu) : 0;
+        if (dv[q] == 0xFFFF) { f = 1; ++cnt; marks |= 1u << q; }        // the side value is placed once its rank is known
+    }
+    // my markers' side values: rank = markers before me in the tile
+    int c_incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, c_incl, d);
+        if (lane >= d) c_incl += y;
+    }
+    if (lane == 31) s_wc[warp] = c_incl;
+    __syncthreads();
+    int c_before = c_incl - cnt;
+    for (int w = 0; w < warp; ++w) c_before += s_wc[w];
+    const int32_t* my_side = side + tile_side[t] + c_before;
+    // redo the local fold with the side values in place
+    int k = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (marks >> q & 1u) v = my_side[k++];
+        else v += dv[q];
+        dv[q] = v;                                                      // running value since the thread's start / last marker
+    }
+    // warp scan of (f, v) with  (f1,v1) o (f2,v2) = (f1|f2, f2 ? v2 : v1 + v2)
+    int sv = v, sf = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int yv = __shfl_up_sync(0xffffffffu, sv, d), yf = __shfl_up_sync(0xffffffffu, sf, d);
+        if (lane >= d) { sv = sf ? sv : yv + sv; sf = sf | yf; }
+    }
+    if (lane == 31) { s_wv[warp] = sv; s_wf[warp] = sf; }
+    __syncthreads();
+    // carry into this thread = scan over the previous warps, then over the previous lanes of this warp
+    int cv = 0, cf = 0;
+    for (int w = 0; w < warp; ++w) { cv = s_wf[w] ? s_wv[w] : cv + s_wv[w]; cf |= s_wf[w]; }
+    const int pv = __shfl_up_sync(0xffffffffu, sv, 1), pf = __shfl_up_sync(0xffffffffu, sf, 1);
+    if (lane > 0) { cv = pf ? pv : cv + pv; }
+    // apply the carry to the entries before the thread's first marker
+    bool seen = false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        seen = seen || (marks >> q & 1u);
+        s_out[tid * 8 + q] = seen ? dv[q] : dv[q] + cv;
+    }
+    __syncthreads();
+    const int cnt_tile = min(kDeltaTile, n - a);
+    for (int i = tid; i < cnt_tile; i += 256) out[a + i] = s_out[i];
+}
+
 }  // namespace
+
+// Host-only check of the encoder (no device work: usable by the CPU test suite): encode `count`
+// indices chunk by chunk exactly as stage_indices does and replay the chunk format with a scalar
+// loop.  0 = every index came back, 1 = a chunk overflowed its side list (stage_indices would ship
+// plain int32), -1 = mismatch.  `n_side` receives the number of side-list entries.
+int delta_selftest_host(const void* src, int bits, int64_t count, int64_t* n_side) {
+    std::vector<unsigned char> slot_store(kChunkBytes + 64);
+    unsigned char* slot = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(slot_store.data()) + 63) & ~static_cast<uintptr_t>(63));
+    std::vector<int32_t> back(static_cast<size_t>(std::min<int64_t>(count, kDeltaPer)));
+    int64_t total_side = 0;
+    for (int64_t off = 0; off < count; off += kDeltaPer) {
+        const int64_t len = std::min(kDeltaPer, count - off);
+        uint64_t o = 0;
+        size_t used = 0;
+        const bool ok = (bits == 64)
+            ? encode_deltas(static_cast<const int64_t*>(src) + off, len, slot, kChunkBytes, o, used)
+            : encode_deltas(static_cast<const int32_t*>(src) + off, len, slot, kChunkBytes, o, used);
+        if (!ok) return 1;
+        if (used > kChunkBytes) return -1;
+        if (!decode_deltas_host(slot, len, back.data())) return -1;
+        uint64_t want_or = 0;
+        for (int64_t i = 0; i < len; ++i) {
+            const int64_t want = (bits == 64) ? static_cast<const int64_t*>(src)[off + i]
+                                              : static_cast<int64_t>(static_cast<const int32_t*>(src)[off + i]);
+            want_or |= static_cast<uint64_t>(want);
+            if (back[i] != static_cast<int32_t>(want)) return -1;
+        }
+        if ((want_or >> 31 != 0) != (o >> 31 != 0)) return -1;      // the range verdict is part of the contract
+        total_side += reinterpret_cast<const DeltaHeader*>(slot)->n_side;
+    }
+    if (n_side) *n_side = total_side;
+    return 0;
+}
 
 // indices (int32 or int64, pageable or pinned host memory) -> int32 on the device.
 // Returns false if some 64-bit index does not fit 31 bits (the range check against m runs on the device).
@@ -195,13 +312,63 @@ bool stage_indices(snapb200_ctx* c, const void* src, int bits, int64_t count, in
     if (count == 0) return true;
     const int threads = host_threads(c);
     Ring r = ring_of(c, threads);
-    const int64_t per = static_cast<int64_t>(kChunkBytes / 4);
-    const int64_t n_chunks = ceil_div(count, per);
     std::atomic<uint64_t> orall{0};
     cudaStream_t st = c->stream;
+    const bool no_delta = getenv("SNAPB200_NO_DELTA") != nullptr;
+    const int64_t t_all0 = now_ns();
+    g_ns_work.store(0); g_ns_api.store(0); g_ns_wait.store(0);
+    if (!no_delta) {
+        // 2 bytes per entry over PCIe: deltas + markers, decoded on the device (see above)
+        c->ring_dev.ensure(static_cast<int64_t>(r.slots) * static_cast<int64_t>(kChunkBytes));
+        const int64_t n_chunks = ceil_div(count, kDeltaPer);
+        std::atomic<int> overflow{0};
+        std::atomic<int64_t> shipped{0};
+        run_ring(r, n_chunks, threads, [&](int64_t j, unsigned char* slot, cudaEvent_t ev) {
+            const int64_t off = j * kDeltaPer, len = std::min(kDeltaPer, count - off);
+            if (overflow.load()) {
+                SB_CUDA(cudaEventRecord(ev, st));
+                return;
+            }
+            uint64_t o = 0;
+            size_t used = 0;
+            const int64_t t_e0 = now_ns();
+            const bool ok = (bits == 64)
+                ? encode_deltas(static_cast<const int64_t*>(src) + off, len, slot, kChunkBytes, o, used)
+                : encode_deltas(static_cast<const int32_t*>(src) + off, len, slot, kChunkBytes, o, used);
+            const int64_t t_e1 = now_ns();
+            g_ns_work.fetch_add(t_e1 - t_e0, std::memory_order_relaxed);
+            if (o >> 31) orall.fetch_or(o);
+            if (!ok) {
+                overflow.store(1);
+                SB_CUDA(cudaEventRecord(ev, st));
+                return;
+            }
+            unsigned char* dslot = c->ring_dev.p + static_cast<size_t>(j % r.slots) * kChunkBytes;
+            shipped.fetch_add(static_cast<int64_t>(used));
+            SB_CUDA(cudaMemcpyAsync(dslot, slot, used, cudaMemcpyHostToDevice, st));
+            decode_deltas_kernel<<<static_cast<unsigned>(ceil_div(len, kDeltaTile)), 256, 0, st>>>(dslot, dst_dev + off);
+            SB_CUDA(cudaGetLastError());
+            SB_CUDA(cudaEventRecord(ev, st));      // the slot (host and device side) is free once the decode has run
+            g_ns_api.fetch_add(now_ns() - t_e1, std::memory_order_relaxed);
+        });
+        const int64_t t_s0 = now_ns();
+        SB_CUDA(cudaStreamSynchronize(st));
+        if (getenv("SNAPB200_DEBUG"))
+            fprintf(stderr, "[snapb200] stage_indices(delta): %lld entries, %d threads, wall %.1f ms (tail sync %.1f); per-thread sums: encode %.1f ms, "
+                    "cuda calls %.1f ms, slot waits %.1f ms\n", static_cast<long long>(count), threads, (now_ns() - t_all0) * 1e-6,
+                    (now_ns() - t_s0) * 1e-6, g_ns_work.exchange(0) * 1e-6, g_ns_api.exchange(0) * 1e-6, g_ns_wait.exchange(0) * 1e-6);
+        if (!overflow.load()) {
+            c->stats.bytes_h2d_indices += shipped.load();
+            return (orall.load() >> 31) == 0;
+        }
+        orall.store(0);     // pathological gaps: ship plain int32 instead
+    }
+    const int64_t per = static_cast<int64_t>(kChunkBytes / 4);
+    const int64_t n_chunks = ceil_div(count, per);
     run_ring(r, n_chunks, threads, [&](int64_t j, unsigned char* slot, cudaEvent_t ev) {
         const int64_t off = j * per, len = std::min(per, count - off);
         int32_t* out = reinterpret_cast<int32_t*>(slot);
+        const int64_t t_e0 = now_ns();
         if (bits == 64) {
             uint64_t o = 0;
             narrow_i64(static_cast<const int64_t*>(src) + off, out, len, o);
@@ -209,10 +376,19 @@ bool stage_indices(snapb200_ctx* c, const void* src, int bits, int64_t count, in
         } else {
             memcpy(out, static_cast<const int32_t*>(src) + off, sizeof(int32_t) * len);
         }
+        const int64_t t_e1 = now_ns();
+        g_ns_work.fetch_add(t_e1 - t_e0, std::memory_order_relaxed);
         SB_CUDA(cudaMemcpyAsync(dst_dev + off, out, sizeof(int32_t) * len, cudaMemcpyHostToDevice, st));
         SB_CUDA(cudaEventRecord(ev, st));
+        g_ns_api.fetch_add(now_ns() - t_e1, std::memory_order_relaxed);
     });
+    const int64_t t_s0 = now_ns();
     SB_CUDA(cudaStreamSynchronize(st));
+    if (getenv("SNAPB200_DEBUG"))
+        fprintf(stderr, "[snapb200] stage_indices(plain): %lld entries, %d threads, wall %.1f ms (tail sync %.1f); per-thread sums: convert %.1f ms, "
+                "cuda calls %.1f ms, slot waits %.1f ms\n", static_cast<long long>(count), threads, (now_ns() - t_all0) * 1e-6,
+                (now_ns() - t_s0) * 1e-6, g_ns_work.exchange(0) * 1e-6, g_ns_api.exchange(0) * 1e-6, g_ns_wait.exchange(0) * 1e-6);
+    c->stats.bytes_h2d_indices += 4 * count;
     return (orall.load() >> 31) == 0;
 }
 

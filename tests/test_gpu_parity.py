@@ -231,6 +231,53 @@ def test_int64_indices_and_count_dtypes(engine):
     np.testing.assert_allclose(deg, z["degree"], rtol=TOL_VEC)
 
 
+@pytest.mark.parametrize("dtype", [np.int32, np.int64])
+def test_delta_encoded_index_transfer_equals_plain_transfer(engine, monkeypatch, dtype):
+    """csrc/ingest.cu ships the column indices as 16-bit differences and rebuilds them with a kernel; the
+    plain int32 transfer (SNAPB200_NO_DELTA) must leave the same matrix on the device: identical IDF,
+    degrees and spectrum, on matrices whose gaps sit on either side of the 16-bit limit."""
+    def spread(n, m, vocab, per_row, seed):
+        # rows draw `per_row` columns from a vocabulary of `vocab` columns scattered over [0, m): wide gaps between
+        # consecutive stored columns, yet every column is shared by many rows (no degenerate cells)
+        rng = np.random.default_rng(seed)
+        cols = np.sort(rng.choice(m, size=vocab, replace=False))
+        pick = np.sort(np.argpartition(rng.random((n, vocab)), per_row, axis=1)[:, :per_row], axis=1)
+        return sp.csr_matrix((np.ones(n * per_row, np.float32), cols[pick].ravel(), np.arange(n + 1) * per_row), shape=(n, m))
+
+    cases = [spread(3000, 3_000_000, 5000, 40, 8),                                         # gaps ~75k: most entries are markers
+             synth.generate_csr(synth.make_spec(6000, 200_000, 300, n_clusters=4, seed=9)),  # gaps ~700: markers at row / tile starts
+             spread(2500, 1_500_000, 3000, 60, 10)]                                        # gaps ~25k: both kinds mixed
+    for ci, X in enumerate(cases):
+        out = {}
+        for mode in ("delta", "plain"):
+            if mode == "plain":
+                monkeypatch.setenv("SNAPB200_NO_DELTA", "1")
+            else:
+                monkeypatch.delenv("SNAPB200_NO_DELTA", raising=False)
+            engine.load_arrays(X.indptr.astype(np.int64), X.indices.astype(dtype), X.data.astype(np.float32), *X.shape)
+            shipped = engine.stats()["bytes_h2d_indices"]
+            if mode == "plain":
+                assert shipped == 4 * X.nnz
+            else:       # 2 bytes per entry + 4 per marker (row starts, tile starts, gaps >= 0xFFFF) + chunk header
+                assert 2 * X.nnz < shipped != 4 * X.nnz
+                if ci == 1:
+                    assert shipped < 2.1 * X.nnz
+            engine.set_feature_weights(None)
+            idf, deg = engine.prepare()
+            out[mode] = [idf.copy(), deg.copy()]
+            if ci == 1:         # (the scattered matrices have a flat spectrum: nothing to learn from solving them)
+                out[mode] += [a.copy() for a in engine.eigsh(6, seed=1)]
+        for a, b in zip(out["delta"], out["plain"]):
+            np.testing.assert_array_equal(a, b)
+    monkeypatch.delenv("SNAPB200_NO_DELTA", raising=False)
+    # a negative / too large index is still refused
+    X = cases[1]
+    bad = X.indices.astype(np.int64)
+    bad[1234] = -3
+    with pytest.raises(RuntimeError):
+        engine.load_arrays(X.indptr.astype(np.int64), bad, X.data.astype(np.float32), *X.shape)
+
+
 def _two_views(n, seed):
     s1 = synth.make_spec(n, 6000, 250, n_clusters=10, seed=seed)
     s2 = synth.make_spec(n, 900, 60, n_clusters=10, seed=seed)          # same planted labels (keyed by seed,row)

@@ -229,3 +229,41 @@ def test_row_blocks_sources():
     assert sp.issparse(tl._get_csr(FakeAnn(X)))
     with pytest.raises(ValueError):
         tl._get_csr(FakeAnn(X.tocsc()))
+
+
+def _delta_selftest(idx):
+    import ctypes as C
+    from snapatac2_b200 import _lib
+    lib = _lib.load()
+    n_side = C.c_int64(-1)
+    idx = np.ascontiguousarray(idx)
+    rc = lib.snapb200_delta_selftest_host(_lib.ptr(idx), 8 * idx.dtype.itemsize, idx.size, C.byref(n_side))
+    return rc, n_side.value
+
+
+@pytest.mark.parametrize("dtype", [np.int32, np.int64])
+def test_delta_encoding_of_the_index_transfer_round_trips(dtype):
+    """csrc/ingest.cu ships column indices as 16-bit differences + a side list of absolute values
+    (markers at tile starts, row starts and gaps >= 0xFFFF); the host-only replay must give back every
+    index, whatever the gaps."""
+    from snapatac2_b200 import synth
+    rng = np.random.default_rng(5)
+    # (1) a realistic CSR: sorted rows, mixed lengths
+    X = synth.generate_csr(synth.make_spec(700, 500_000, 900, n_clusters=5, seed=3))
+    rc, n_side = _delta_selftest(X.indices.astype(dtype))
+    assert rc == 0
+    # markers: one per 2048-entry tile + about one per row (+ rare wide gaps)
+    assert n_side <= X.nnz // 2048 + 1 + X.shape[0] + X.nnz // 50
+    # (2) adversarial gaps around the 16-bit limit, equal neighbours, descending runs, tiny and ragged sizes
+    base = np.cumsum(rng.choice([0, 1, 7, 65534, 65535, 65536, 70000], size=40_000)).astype(np.int64) % (2**31 - 1)
+    for arr in (base, base[::-1].copy(), base[:1], base[:7], base[:2047], base[:2048], base[:2049], base[:4099],
+                np.zeros(5000, np.int64), np.full(3000, 2**31 - 1, np.int64)):
+        rc, n_side = _delta_selftest(arr.astype(dtype))
+        assert rc == 0, arr[:8]
+        assert n_side >= (arr.size + 2047) // 2048
+    # (3) more than one 3 Mi-entry chunk
+    big = np.sort(rng.integers(0, 2**31 - 1, size=(3 << 20) + 12345)).astype(dtype)
+    assert _delta_selftest(big)[0] == 0
+    # (4) nothing but wide gaps: the side list cannot hold a chunk -> the caller is told to ship plain int32
+    wide = (np.arange(3 << 20, dtype=np.int64) % 2) * 100_000
+    assert _delta_selftest(wide.astype(dtype))[0] == 1
