@@ -71,6 +71,8 @@ typedef struct snapb200_stats {
                               kernels over NVLink peer memory (csrc/peer.cuh), 0 = NCCL (or a single rank)   */
     int64_t bytes_h2d_indices; /* last index transfer: bytes that crossed PCIe for the column indices (2 per entry when
                               delta-encoded, see csrc/ingest.cu; 4 otherwise)                               */
+    double ms_knn;         /* last knn: device time of centring + filter/exact scan (CUDA events)          */
+    double ms_knn_wall;    /* last knn: wall clock of the call, uploads and the copy of the result included */
 } snapb200_stats;
 
 /* Library / error plumbing. */
@@ -254,6 +256,20 @@ int  snapb200_get_stream(snapb200_ctx* ctx, void** stream);
  * Rayleigh-Ritz eigensolver (a: n x n row-major, destroyed; eigenvalues
  * ascending in w, eigenvectors in the columns of a) and needs no GPU. */
 int  snapb200_dense_selftest(snapb200_ctx* ctx, int64_t n, int ncq, int p, double* max_rel_err);
+/* Exact k-nearest-neighbour graph of an embedding: replaces `nearest_neighbour_graph`
+ * (snapatac2-core/src/utils/knn.rs:9-33, bound as `internal.nearest_neighbour_graph(data, k)` at
+ * snapatac2-python/src/knn.rs:8-16 and called from preprocessing/_knn.py:80).  `points` is the n x d float64
+ * row-major matrix (host memory, or device memory when on_device != 0; d <= 64).  The queries are the points
+ * [q0, q0 + nq) -- a rank of a row-sharded run passes all points and its own row range.  Per query the
+ * K = min(k, n - 1) nearest other points (Euclidean, the query's own index excluded, ties at the K-th distance
+ * broken by the smaller index): out_indices / out_distances are nq x K host arrays, each row sorted by index,
+ * i.e. the `indices` / `data` of the reference's CSR result with indptr = K * arange(nq + 1).  Distances are
+ * bit-identical to sqrt(squared_euclidean) of the reference's kd-tree crate (left-to-right float64 sum).
+ * K <= 100 (84 when d > 32). */
+int  snapb200_knn(snapb200_ctx* ctx, int64_t n, int d, const double* points, int on_device, int64_t q0, int64_t nq,
+                  int k, int32_t* out_indices, double* out_distances);
+int  snapb200_knn_limits(int* max_neighbors, int* max_dim);
+
 /* Host-only replay of the delta encoding the index transfer uses (csrc/ingest.cu: 2 bytes per stored
  * entry over PCIe, decoded by a kernel): encodes `count` indices chunk by chunk and decodes them with a
  * scalar loop.  Returns 0 = identical, 1 = a chunk would fall back to plain int32, -1 = mismatch, -2 = bad

@@ -39,3 +39,4 @@ from .reference_restatement import (  # noqa: F401
     orthogonalize,
     spectral_embedding_nystrom,
 )
+from . import knn_restatement as knn  # noqa: F401  (pp.knn: the consumer next to the path)

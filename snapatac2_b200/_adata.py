@@ -2,8 +2,8 @@
 
 ``anndata`` is not installed in this image; the reference's boundary only uses
 ``X`` (scipy CSR), ``var[...]``, ``shape`` / ``n_obs`` / ``n_vars``, ``obsm``,
-``uns`` and ``isbacked`` (tools/_embedding.py:223-293), so this is all the
-mirror needs.  A real ``anndata.AnnData`` works with ``tl.spectral`` as well.
+``uns`` and ``isbacked`` (tools/_embedding.py:223-293), plus ``obsp`` for the
+neighbour graph (preprocessing/_knn.py:85), so this is all the mirror needs.  A real ``anndata.AnnData`` works with ``tl.spectral`` as well.
 """
 
 from __future__ import annotations
@@ -22,6 +22,7 @@ class MiniAnnData:
         self.obs = obs if obs is not None else pd.DataFrame(index=pd.RangeIndex(n).astype(str))
         self.var = var if var is not None else pd.DataFrame(index=pd.RangeIndex(m).astype(str))
         self.obsm: dict = {}
+        self.obsp: dict = {}
         self.uns: dict = {}
         self.isbacked = False
 

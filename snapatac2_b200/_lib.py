@@ -27,7 +27,7 @@ SYMBOLS = [
     "snapb200_prepare_projection", "snapb200_project",
     "snapb200_operator_apply", "snapb200_operator_time", "snapb200_eigsh", "snapb200_get_stats",
     "snapb200_get_stream", "snapb200_set_spmm_mode", "snapb200_set_block",
-    "snapb200_dense_selftest", "snapb200_ortho_selftest", "snapb200_delta_selftest_host", "snapb200_sym_eig",
+    "snapb200_dense_selftest", "snapb200_ortho_selftest", "snapb200_delta_selftest_host", "snapb200_knn", "snapb200_knn_limits", "snapb200_sym_eig",
 ]
 
 
@@ -43,6 +43,7 @@ class Stats(C.Structure):
         ("ms_pool", C.c_double), ("pool_mallocs", C.c_int64),
         ("converged", C.c_int64), ("n_spec_ops", C.c_int64), ("ms_d2h", C.c_double),
         ("bytes_h2d", C.c_int64), ("host_threads", C.c_int64), ("fused_allreduce", C.c_int64), ("bytes_h2d_indices", C.c_int64),
+        ("ms_knn", C.c_double), ("ms_knn_wall", C.c_double),
     ]
 
     def as_dict(self):
@@ -103,6 +104,8 @@ def load() -> C.CDLL:
         "snapb200_dense_selftest": [vp, i64, i32, i32, C.POINTER(dbl)],
         "snapb200_ortho_selftest": [vp, i64, i32, i32, C.POINTER(dbl)],
         "snapb200_delta_selftest_host": [vp, i32, i64, C.POINTER(i64)],
+        "snapb200_knn": [vp, i64, i32, vp, i32, i64, i64, i32, vp, vp],
+        "snapb200_knn_limits": [C.POINTER(i32), C.POINTER(i32)],
         "snapb200_sym_eig": [i32, vp, vp],
     }
     for name, argtypes in sigs.items():

@@ -19,7 +19,7 @@ CSRC = HERE / "csrc"
 BUILD = HERE / "_build"
 LIB = HERE / "libsnapb200.so"
 
-SOURCES = ["api.cu", "ingest.cu", "pool.cu", "comm.cu", "util.cu", "synth.cu", "prep.cu", "transpose_tiled.cu", "spmm.cu", "sell_build.cu", "spmm_tiled.cu", "dense.cu", "lanczos.cu"]
+SOURCES = ["api.cu", "ingest.cu", "pool.cu", "comm.cu", "util.cu", "synth.cu", "prep.cu", "transpose_tiled.cu", "spmm.cu", "sell_build.cu", "spmm_tiled.cu", "dense.cu", "lanczos.cu", "knn.cu"]
 
 
 def _nccl_paths():

@@ -748,6 +748,21 @@ int snapb200_get_stream(snapb200_ctx* c, void** stream) {
 }
 
 // ---- test hooks (not part of the reference-facing surface) -----------------
+int snapb200_knn(snapb200_ctx* c, int64_t n, int d, const double* points, int on_device, int64_t q0, int64_t nq, int k,
+                 int32_t* out_indices, double* out_distances) {
+    return guarded([&] {
+        SB_CHECK(c != nullptr, "knn: null context");
+        bind(c);
+        knn(c, n, d, points, on_device, q0, nq, k, out_indices, out_distances);
+    });
+}
+
+int snapb200_knn_limits(int* max_neighbors, int* max_dim) {
+    if (max_neighbors) *max_neighbors = knn_max_neighbors();
+    if (max_dim) *max_dim = knn_max_dim();
+    return 0;
+}
+
 int snapb200_delta_selftest_host(const void* indices, int index_bits, int64_t count, int64_t* n_side) {
     int verdict = -2;
     const int rc = guarded([&] {

@@ -246,6 +246,12 @@ bool host_values_all_ones(snapb200_ctx* c, const void* values, int kind, int64_t
 void stage_values(snapb200_ctx* c, const void* src, int kind, int64_t count, float* dst_dev);
 void copy_to_host(snapb200_ctx* c, void* dst, const void* src_dev, size_t bytes);
 
+// ---- knn.cu: exact k-nearest-neighbour graph of an n x d float64 point set (the consumer of X_spectral)
+void knn(snapb200_ctx* c, int64_t n, int d, const double* points, int on_device, int64_t q0, int64_t nq, int k,
+         int32_t* out_indices, double* out_distances);
+int knn_max_neighbors();
+int knn_max_dim();
+
 // ---- synth.cu
 void generate_rows(snapb200_ctx* c, int64_t n_local, int64_t n_global, int64_t row0, int64_t m,
                    int nnz_row, int n_clusters, uint64_t seed, const uint64_t* feat_cdf,

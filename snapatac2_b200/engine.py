@@ -346,6 +346,22 @@ class Engine:
         _lib.check(self._lib.snapb200_get_stream(self._ctx, C.byref(h)))
         return int(h.value or 0)
 
+    def knn(self, points, n_neighbors, q0=0, nq=None):
+        """Exact neighbour graph of ``points`` (n x d float64): for the queries ``points[q0:q0+nq]`` the
+        ``K = min(n_neighbors, n - 1)`` nearest other points.  Returns ``(indices int32, distances float64)``,
+        both ``nq x K`` with every row sorted by index (``snapb200_knn``; knn.rs:9-33)."""
+        P = np.ascontiguousarray(points, dtype=np.float64)
+        if P.ndim != 2:
+            raise ValueError("points must be a 2-d array")
+        n, d = P.shape
+        nq = n - q0 if nq is None else int(nq)
+        K = max(0, min(int(n_neighbors), n - 1))
+        idx = np.empty((nq, K), dtype=np.int32)
+        dist = np.empty((nq, K), dtype=np.float64)
+        _lib.check(self._lib.snapb200_knn(self._ctx, n, d, _lib.ptr(P), 0, int(q0), nq, int(n_neighbors),
+                                          _lib.ptr(idx), _lib.ptr(dist)))
+        return idx, dist
+
     def ortho_selftest(self, n=5000, ncols=64, block=4) -> float:
         err = C.c_double()
         _lib.check(self._lib.snapb200_ortho_selftest(self._ctx, int(n), int(ncols), int(block), C.byref(err)))
