@@ -265,7 +265,7 @@ int  snapb200_dense_selftest(snapb200_ctx* ctx, int64_t n, int ncq, int p, doubl
  * broken by the smaller index): out_indices / out_distances are nq x K host arrays, each row sorted by index,
  * i.e. the `indices` / `data` of the reference's CSR result with indptr = K * arange(nq + 1).  Distances are
  * bit-identical to sqrt(squared_euclidean) of the reference's kd-tree crate (left-to-right float64 sum).
- * K <= 100 (84 when d > 32). */
+ * K <= 100 (74 when d > 32). */
 int  snapb200_knn(snapb200_ctx* ctx, int64_t n, int d, const double* points, int on_device, int64_t q0, int64_t nq,
                   int k, int32_t* out_indices, double* out_distances);
 int  snapb200_knn_limits(int* max_neighbors, int* max_dim);

@@ -1,0 +1,9 @@
+#!/bin/bash
+# kNN after the branch-free candidate mask: parity, timing, cycle accounting
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_knn.py -m gpu -q -x 2>&1 | tail -3
+for n in 1000000 200000; do
+timeout 600 python scripts/bench_knn.py --n $n --steps 2 --no-cpu > gpurun_out/r2t_knn_$n.json 2> gpurun_out/r2t_knn_$n.err; python -c "
+import json; d=json.loads(open('gpurun_out/r2t_knn_$n.json').read()); print($n, 'ms', d['ms_per_step'], 'frac', d['roofline']['frac'], 'e2e ms', d['e2e']['ms_per_step'])"
+done
+SNAPB200_KNN_PROBE=4 timeout 600 python scripts/bench_knn.py --n 1000000 --steps 1 --warmup 0 --no-cpu 2>&1 >/dev/null | grep "knn probe"

@@ -24,6 +24,7 @@
 // obvious next step and is not done here.
 #include "ctx.cuh"
 
+#include <cuda_pipeline.h>
 #include <math_constants.h>
 
 #include <chrono>
@@ -32,9 +33,6 @@ namespace snapb {
 namespace {
 
 constexpr int kT = 128;               // queries per CTA = points per staged tile
-constexpr int kKnnThreads = 256;
-constexpr int kOwnerQueries = 16;     // warp w owns queries [16 w, 16 w + 16)
-constexpr int kQueueCap = kOwnerQueries * kT;   // every pair of a tile can pass (first tiles)
 constexpr int kKnnMaxK = 100;
 constexpr int kKnnMaxDim = 64;
 
@@ -63,12 +61,15 @@ __global__ void __launch_bounds__(256) knn_colsum_kernel(const double* __restric
     if (threadIdx.x < d) atomicAdd(&sum[threadIdx.x], s_sum[threadIdx.x]);
 }
 
-// centred float32 copy, dimension-major (Pt[k * npad + j]), and the float64 squared norm of the centred
-// point; columns j >= n are padding: zeros with a NaN norm (a NaN bound never passes the filter)
+// Per point: the centred float32 copy, dimension-major (Pt[k * npad + j]); the float64 squared norm of the
+// centred point and its shrunk float32 lower bound; the original float64 row padded to DP terms (P64p, the
+// exact stage reads it with compile-time trip counts: trailing (0 - 0)^2 terms add +0.0, which changes no sum).
+// Columns j >= n are padding: zeros with NaN norms (a NaN bound never passes the filter).
 template <int DP>
 __global__ void __launch_bounds__(256) knn_prep_kernel(const double* __restrict__ P, int64_t n, int64_t npad, int d,
-                                                       const double* __restrict__ sum, float* __restrict__ Pt,
-                                                       double* __restrict__ nrm64) {
+                                                       const double* __restrict__ sum, double shrink, float* __restrict__ Pt,
+                                                       double* __restrict__ nrm64, float* __restrict__ nlo32,
+                                                       double* __restrict__ P64p) {
     const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (j >= npad) return;
     double nn = 0.0;
@@ -76,73 +77,162 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const double* __restrict_
         const double* row = P + j * d;
 #pragma unroll
         for (int k = 0; k < DP; ++k) {
-            double a = 0.0;
-            if (k < d) a = row[k] - sum[k] / static_cast<double>(n);
+            double v = 0.0, a = 0.0;
+            if (k < d) {
+                v = row[k];
+                a = v - sum[k] / static_cast<double>(n);
+            }
             nn += a * a;
             Pt[k * npad + j] = static_cast<float>(a);
+            P64p[j * DP + k] = v;
         }
     } else {
 #pragma unroll
-        for (int k = 0; k < DP; ++k) Pt[k * npad + j] = 0.f;
+        for (int k = 0; k < DP; ++k) {
+            Pt[k * npad + j] = 0.f;
+            P64p[j * DP + k] = 0.0;
+        }
         nn = CUDART_NAN;
     }
     nrm64[j] = nn;
+    nlo32[j] = __double2float_rd(nn * shrink);
 }
+
+constexpr int kProducers = 8;          // warps 0-7: the float32 filter
+constexpr int kConsumers = 8;          // warps 8-15: exact distances + lists; warp 8 + c owns queries [16 c, 16 c + 16)
+constexpr int kScanThreads = 32 * (kProducers + kConsumers);
+constexpr int kConsQueries = kT / kConsumers;
+constexpr int kQueueSlots = 512;       // per consumer and buffer; a tile that passes more flags the query for a full re-check
 
 struct KnnSmem {
     // byte offsets into the dynamic shared memory of knn_scan_kernel
-    int tau64, nlo64, list_d, As, Bs, Bn, Tq, tauj, argmax, cnt, qcnt, list_j, queue, total;
+    int nlo64, list_d, q64, As, Bs, Bn, Tq, qcnt, redo, list_j, queue, total;
 };
 
-inline KnnSmem knn_smem_layout(int DP, int K) {
+// `stage_q`: the padded float64 rows of the CTA's queries are kept in shared memory (row stride DP + 2 doubles)
+inline KnnSmem knn_smem_layout(int DP, int K, bool stage_q) {
     KnnSmem s;
     int o = 0;
     auto take = [&](int bytes) { const int at = o; o += (bytes + 15) & ~15; return at; };
-    s.tau64 = take(kT * 8);
     s.nlo64 = take(kT * 8);
     s.list_d = take(kT * K * 8);
+    s.q64 = take(stage_q ? kT * (DP + 2) * 8 : 0);
     s.As = take(DP * kT * 4);
-    s.Bs = take(DP * kT * 4);
-    s.Bn = take(kT * 4);
+    s.Bs = take(2 * DP * kT * 4);
+    s.Bn = take(2 * kT * 4);
     s.Tq = take(kT * 4);
-    s.tauj = take(kT * 4);
-    s.argmax = take(kT * 4);
-    s.cnt = take(kT * 4);
-    s.qcnt = take((kKnnThreads / 32) * 4);
+    s.qcnt = take(2 * kConsumers * 4);
+    s.redo = take(2 * kConsumers * 4);
     s.list_j = take(kT * K * 4);
-    s.queue = take((kKnnThreads / 32) * kQueueCap * 2);
+    s.queue = take(2 * kConsumers * kQueueSlots * 2);
     s.total = o;
     return s;
 }
 
-// One CTA = 128 consecutive queries, swept over every tile of 128 points.
+// kdtree 0.7 `squared_euclidean`: ((x - y) * (x - y)) summed left to right, one rounding per operation.
+// Both rows are padded to DP terms and 16-byte aligned: the point row is fetched with DP / 2 independent
+// 16-byte loads (one round trip), the arithmetic keeps the reference's order.
 template <int DP>
-__global__ void __launch_bounds__(kKnnThreads, 1)
-knn_scan_kernel(const float* __restrict__ Pt, const double* __restrict__ nrm64, const double* __restrict__ P64,
-                int64_t n, int64_t npad, int d, int64_t q0, int64_t nq, int K, double shrink, KnnSmem L,
-                int32_t* __restrict__ out_j, double* __restrict__ out_d) {
+__device__ __forceinline__ double exact_d2(const double* __restrict__ x, const double* __restrict__ y) {
+    double2 yv[DP / 2];
+#pragma unroll
+    for (int u = 0; u < DP / 2; ++u) yv[u] = __ldg(reinterpret_cast<const double2*>(y) + u);
+    double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < DP / 2; ++u) {
+        const double2 xv = *(reinterpret_cast<const double2*>(x) + u);
+        const double d0 = __dsub_rn(xv.x, yv[u].x);
+        s = __dadd_rn(s, __dmul_rn(d0, d0));
+        const double d1 = __dsub_rn(xv.y, yv[u].y);
+        s = __dadd_rn(s, __dmul_rn(d1, d1));
+    }
+    return s;
+}
+
+// Per-query lists of the CTA's 128 queries (shared memory, touched by the consumer warps only): K entries
+// (distance^2, index) kept in ascending order, empty slots = (+inf, INT_MAX); the K-th is the bound.
+struct KnnLists {
+    double* list_d;    // [q][K]
+    int* list_j;       // [q][K]
+    float* Tq;         // float32 bound the filter compares with (rounded up)
+    const double* nlo64;
+    int K;
+};
+
+__device__ __forceinline__ bool knn_before(double a, int aj, double b, int bj) { return a < b || (a == b && aj < bj); }
+
+// One warp offers up to 32 candidates (one per lane: `ok`, query q, point j, exact distance^2 d2) to the lists
+// of its own queries.  Insertions are serial, in lane order; one insertion is a parallel shift: every lane
+// owns the slots lane, lane + 32, ... and takes its left neighbour's entry where that one moves up.
+__device__ __forceinline__ void knn_offer(const KnnLists& S, bool ok, int q, int j, double d2, int lane) {
+    const int K = S.K;
+    unsigned pend = __ballot_sync(0xffffffffu, ok && knn_before(d2, j, S.list_d[q * K + K - 1], S.list_j[q * K + K - 1]));
+    while (pend) {
+        const int src = __ffs(pend) - 1;
+        pend &= pend - 1;
+        const int qq = __shfl_sync(0xffffffffu, q, src);
+        const int jn = __shfl_sync(0xffffffffu, j, src);
+        const double dd = __shfl_sync(0xffffffffu, d2, src);
+        double* ld = S.list_d + qq * K;
+        int* lj = S.list_j + qq * K;
+        if (!knn_before(dd, jn, ld[K - 1], lj[K - 1])) continue;      // an earlier insertion tightened the bound
+        double nv[4];
+        int nj[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int s = lane + 32 * r;
+            if (s < K) {
+                const double v = ld[s];
+                const int vj = lj[s];
+                const bool left_moves = s > 0 && knn_before(dd, jn, ld[s - 1], lj[s - 1]);     // left neighbour is behind the newcomer
+                if (left_moves) { nv[r] = ld[s - 1]; nj[r] = lj[s - 1]; }
+                else if (knn_before(dd, jn, v, vj)) { nv[r] = dd; nj[r] = jn; }
+                else { nv[r] = v; nj[r] = vj; }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int s = lane + 32 * r;
+            if (s < K) { ld[s] = nv[r]; lj[s] = nj[r]; }
+        }
+        __syncwarp();
+        if (lane == 0) *reinterpret_cast<volatile float*>(S.Tq + qq) = __double2float_ru(ld[K - 1] - S.nlo64[qq]);
+    }
+}
+
+// One CTA = 128 consecutive queries, swept over every tile of 128 points.  Eight producer warps run the
+// float32 filter of tile t (and fetch tile t + 1 with asynchronous copies) while eight consumer warps settle
+// what tile t - 1 let through (exact distances, lists); one barrier per tile hands the candidate queue over.
+// The bound the producers read may therefore be one tile old -- it only ever decreases, so a stale bound
+// lets a few more candidates through, never fewer.
+template <int DP, bool DBG>
+__global__ void __launch_bounds__(kScanThreads, 1)
+knn_scan_kernel(const float* __restrict__ Pt, const double* __restrict__ nrm64, const float* __restrict__ nlo32,
+                const double* __restrict__ P64p, int64_t n, int64_t npad, int64_t q0, int64_t nq, int K, double shrink,
+                KnnSmem L, int32_t* __restrict__ out_j, double* __restrict__ out_d, int probe, int stage_q,
+                unsigned long long* __restrict__ dbg) {
     extern __shared__ __align__(16) unsigned char smem[];
-    double* tau64 = reinterpret_cast<double*>(smem + L.tau64);
     double* nlo64 = reinterpret_cast<double*>(smem + L.nlo64);
     double* list_d = reinterpret_cast<double*>(smem + L.list_d);
+    double* Q64 = reinterpret_cast<double*>(smem + L.q64);
     float* As = reinterpret_cast<float*>(smem + L.As);
     float* Bs = reinterpret_cast<float*>(smem + L.Bs);
     float* Bn = reinterpret_cast<float*>(smem + L.Bn);
     float* Tq = reinterpret_cast<float*>(smem + L.Tq);
-    int* tauj = reinterpret_cast<int*>(smem + L.tauj);
-    int* argmax = reinterpret_cast<int*>(smem + L.argmax);
-    int* cnt = reinterpret_cast<int*>(smem + L.cnt);
     int* qcnt = reinterpret_cast<int*>(smem + L.qcnt);
+    unsigned* redo = reinterpret_cast<unsigned*>(smem + L.redo);
     int* list_j = reinterpret_cast<int*>(smem + L.list_j);
     unsigned short* queue = reinterpret_cast<unsigned short*>(smem + L.queue);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ty = tid >> 4, tx = tid & 15;
+    const bool producer = warp < kProducers;
+    const int ty = (tid >> 4) & 15, tx = tid & 15;
     const int64_t qlocal0 = static_cast<int64_t>(blockIdx.x) * kT;     // first query of this CTA, relative to q0
     const int64_t qbase = q0 + qlocal0;                                 // ... as a point index
 
     // ---- the query tile and the per-query state
-    for (int e = tid; e < DP * kT; e += kKnnThreads) {
+    for (int e = tid; e < DP * kT; e += kScanThreads) {
         const int k = e >> 7, q = e & (kT - 1);
         const int64_t i = qbase + q;
         As[e] = (qlocal0 + q < nq && i < n) ? Pt[k * npad + i] : 0.f;
@@ -150,194 +240,230 @@ knn_scan_kernel(const float* __restrict__ Pt, const double* __restrict__ nrm64, 
     if (tid < kT) {
         const int64_t i = qbase + tid;
         const bool valid = qlocal0 + tid < nq && i < n;
-        tau64[tid] = CUDART_INF;
-        tauj[tid] = 0x7fffffff;
-        argmax[tid] = 0;
-        cnt[tid] = 0;
         nlo64[tid] = valid ? nrm64[i] * shrink : 0.0;
         Tq[tid] = valid ? CUDART_INF_F : -CUDART_INF_F;    // a query outside the range accepts nothing
     }
-    if (tid < kKnnThreads / 32) qcnt[tid] = 0;
+    if (tid < 2 * kConsumers) { qcnt[tid] = 0; redo[tid] = 0u; }
+    for (int e = tid; e < kT * K; e += kScanThreads) {
+        list_d[e] = CUDART_INF;
+        list_j[e] = 0x7fffffff;
+    }
+    constexpr int kQStride = DP + 2;
+    if (stage_q) {
+        for (int e = tid; e < kT * DP; e += kScanThreads) {
+            const int q = e / DP, k = e % DP;
+            Q64[q * kQStride + k] = (qbase + q < npad) ? P64p[(qbase + q) * DP + k] : 0.0;
+        }
+    }
+    const double* qrows = stage_q ? Q64 : P64p + qbase * DP;     // row q of the CTA's queries: qrows + q * qstride
+    const int qstride = stage_q ? kQStride : DP;
 
     const int64_t n_tiles = npad / kT;
-    constexpr int kPre = DP / 8;          // float4 per thread of one point tile (DP * 128 / 4 / 256)
-    float4 pre[kPre];
-    float pre_n = 0.f;
+    // tile t -> Bs[t & 1], Bn[t & 1]: 16-byte asynchronous copies issued by the producer threads
     auto fetch = [&](int64_t t) {
         const int64_t tile0 = t * kT;
+        float* B = Bs + (t & 1) * DP * kT;
 #pragma unroll
-        for (int r = 0; r < kPre; ++r) {
-            const int e4 = tid + kKnnThreads * r;           // float4 index inside the tile: 32 per dimension
+        for (int r = 0; r < DP / 8; ++r) {
+            const int e4 = tid + 32 * kProducers * r;       // float4 index inside the tile: 32 per dimension
             const int k = e4 >> 5, c4 = e4 & 31;
-            pre[r] = *reinterpret_cast<const float4*>(Pt + k * npad + tile0 + c4 * 4);
+            __pipeline_memcpy_async(B + e4 * 4, Pt + k * npad + tile0 + c4 * 4, 16);
         }
-        if (tid < kT) pre_n = __double2float_rd(nrm64[tile0 + tid] * shrink);
+        if (tid < kT / 4) __pipeline_memcpy_async(Bn + (t & 1) * kT + tid * 4, nlo32 + tile0 + tid * 4, 16);
+        __pipeline_commit();
     };
-    fetch(0);
+    if (producer) {
+        fetch(0);
+        __pipeline_wait_prior(0);
+    }
     __syncthreads();
 
-    for (int64_t t = 0; t < n_tiles; ++t) {
-        const int64_t tile0 = t * kT;
-#pragma unroll
-        for (int r = 0; r < kPre; ++r) {
-            const int e4 = tid + kKnnThreads * r;
-            *reinterpret_cast<float4*>(Bs + e4 * 4) = pre[r];
-        }
-        if (tid < kT) Bn[tid] = pre_n;
-        __syncthreads();
-        if (t + 1 < n_tiles) fetch(t + 1);
+    const KnnLists S{list_d, list_j, Tq, nlo64, K};
 
-        // ---- 8 x 8 dot products per thread
-        float acc[8][8];
+    // iteration t: producers filter tile t into queue[t & 1]; consumers settle queue[(t - 1) & 1] (tile t - 1)
+    long long c_work = 0, c_wait = 0, c_cand = 0, c_redo = 0;      // (probe 4: cycle accounting of warp 0 / warp 8)
+    for (int64_t t = 0; t <= n_tiles; ++t) {
+        const int buf = static_cast<int>(t & 1);
+        const long long t_begin = DBG ? clock64() : 0;
+        if (producer) {
+            if (t < n_tiles) {
+                if (t + 1 < n_tiles) fetch(t + 1);          // the other buffer: last read in iteration t - 1
+                const float* B = Bs + buf * DP * kT;
+                // ---- 8 x 8 dot products per thread
+                float acc[8][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+                    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 #pragma unroll 4
-        for (int k = 0; k < DP; ++k) {
-            const float4 a0 = *reinterpret_cast<const float4*>(As + k * kT + ty * 4);
-            const float4 a1 = *reinterpret_cast<const float4*>(As + k * kT + 64 + ty * 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * kT + tx * 4);
-            const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * kT + 64 + tx * 4);
-            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                for (int k = 0; k < DP; ++k) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(As + k * kT + ty * 4);
+                    const float4 a1 = *reinterpret_cast<const float4*>(As + k * kT + 64 + ty * 4);
+                    const float4 b0 = *reinterpret_cast<const float4*>(B + k * kT + tx * 4);
+                    const float4 b1 = *reinterpret_cast<const float4*>(B + k * kT + 64 + tx * 4);
+                    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                    const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        }
-        // ---- filter: lower bound of the squared distance against the query's current k-th distance
-        {
-            const float4 n0 = *reinterpret_cast<const float4*>(Bn + tx * 4);
-            const float4 n1 = *reinterpret_cast<const float4*>(Bn + 64 + tx * 4);
-            const float bn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
-            const float4 t0 = *reinterpret_cast<const float4*>(Tq + ty * 4);
-            const float4 t1 = *reinterpret_cast<const float4*>(Tq + 64 + ty * 4);
-            const float tq[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
-            bool any = false;                      // the common case: nothing passes, one branch for the 64 pairs
+                        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                }
+                // ---- filter: lower bound of the squared distance against the query's current K-th distance
+                const float4 n0 = *reinterpret_cast<const float4*>(Bn + buf * kT + tx * 4);
+                const float4 n1 = *reinterpret_cast<const float4*>(Bn + buf * kT + 64 + tx * 4);
+                const float bn[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+                float tq[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+                for (int i = 0; i < 8; ++i)
+                    tq[i] = *reinterpret_cast<volatile float*>(Tq + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4)));
+                bool any = false;                      // the common case: nothing passes, one branch for the 64 pairs
 #pragma unroll
-                for (int j = 0; j < 8; ++j) any |= fmaf(-2.f, acc[i][j], bn[j]) <= tq[i];
-            if (any) {
+                for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int q = (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+                    for (int j = 0; j < 8; ++j) any |= fmaf(-2.f, acc[i][j], bn[j]) <= tq[i];
+                if (any && probe != 1) {      // (probe 1: timing of the bare filter loop, results are meaningless)
+                    // which of the 64 pairs: two 32-bit masks built without branches, then one push per set bit
+                    // (64 separately guarded pushes cost ~3000 cycles of convergence barriers per warp and tile)
+                    unsigned m0 = 0u, m1 = 0u;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (fmaf(-2.f, acc[i][j], bn[j]) <= tq[i]) {
-                            const int p = (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
-                            const int owner = q / kOwnerQueries;
-                            const int pos = atomicAdd(&qcnt[owner], 1);
-                            queue[owner * kQueueCap + pos] = static_cast<unsigned short>((q << 7) | p);
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            m0 |= (fmaf(-2.f, acc[i][j], bn[j]) <= tq[i] ? 1u : 0u) << (i * 8 + j);
+                            m1 |= (fmaf(-2.f, acc[i + 4][j], bn[j]) <= tq[i + 4] ? 1u : 0u) << (i * 8 + j);
+                        }
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        unsigned m = half ? m1 : m0;
+                        while (m) {
+                            const int bit = __ffs(m) - 1;
+                            m &= m - 1;
+                            const int q = half * 64 + ty * 4 + (bit >> 3);
+                            const int jj = bit & 7;
+                            const int p = (jj >> 2) * 64 + tx * 4 + (jj & 3);
+                            const int owner = q / kConsQueries;
+                            const int pos = atomicAdd(&qcnt[buf * kConsumers + owner], 1);
+                            if (pos < kQueueSlots) queue[(buf * kConsumers + owner) * kQueueSlots + pos] = static_cast<unsigned short>((q << 7) | p);
+                            else atomicOr(&redo[buf * kConsumers + owner], 1u << (q % kConsQueries));     // no room: re-check the whole tile for q
                         }
                     }
                 }
+                __pipeline_wait_prior(0);
+            }
+        } else if (t > 0) {
+            // ---- consumer warp: exact float64 distances, 32 candidates at a time, then serial insertion
+            const int cw = warp - kProducers;
+            const int pb = buf ^ 1;
+            const int64_t tile0 = (t - 1) * kT;
+            const int ne = min(qcnt[pb * kConsumers + cw], kQueueSlots);
+            const unsigned flagged = redo[pb * kConsumers + cw];
+            if (DBG) {
+                c_cand += ne;
+                c_redo += __popc(flagged);
+            }
+            const unsigned short* Q = queue + (pb * kConsumers + cw) * kQueueSlots;
+            for (int base = 0; base < ne; base += 32) {
+                const int e = base + lane;
+                const bool have = e < ne;
+                const int code = have ? Q[e] : (cw * kConsQueries) << 7;
+                const int q = code >> 7, p = code & (kT - 1);
+                const int64_t i = qbase + q, j = tile0 + p;
+                const bool ok = have && j < n && j != i && !((flagged >> (q % kConsQueries)) & 1u);
+                double d2 = CUDART_INF;
+                if (ok) d2 = exact_d2<DP>(qrows + q * qstride, P64p + j * DP);
+                knn_offer(S, ok, q, static_cast<int>(j), d2, lane);
+            }
+            // queries whose candidates did not all fit the queue: every point of the tile, exactly
+            for (unsigned f = flagged; f; f &= f - 1) {
+                const int q = cw * kConsQueries + (__ffs(f) - 1);
+                const int64_t i = qbase + q;
+                for (int p = lane; p < kT; p += 32) {
+                    const int64_t j = tile0 + p;
+                    const bool ok = j < n && j != i;
+                    double d2 = CUDART_INF;
+                    if (ok) d2 = exact_d2<DP>(qrows + q * qstride, P64p + j * DP);
+                    knn_offer(S, ok, q, static_cast<int>(j), d2, lane);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                qcnt[pb * kConsumers + cw] = 0;
+                redo[pb * kConsumers + cw] = 0u;
             }
         }
+        const long long t_mid = DBG ? clock64() : 0;
         __syncthreads();
-
-        // ---- the owner warp: exact float64 distances, 32 candidates at a time, then serial insertion
-        const int ne = qcnt[warp];
-        for (int base = 0; base < ne; base += 32) {
-            const int e = base + lane;
-            const bool have = e < ne;
-            const int code = have ? queue[warp * kQueueCap + e] : 0;
-            const int q = code >> 7, p = code & (kT - 1);
-            const int64_t i = qbase + q, j = tile0 + p;
-            const bool ok = have && j < n && j != i;
-            double d2 = CUDART_INF;
-            if (ok) {
-                const double* x = P64 + i * d;
-                const double* y = P64 + j * d;
-                double s = 0.0;
-                for (int k = 0; k < d; ++k) {             // the reference's fold: ((x - y) * (x - y)) summed left to right
-                    const double df = __dsub_rn(x[k], y[k]);
-                    s = __dadd_rn(s, __dmul_rn(df, df));
-                }
-                d2 = s;
-            }
-            const int jj32 = static_cast<int>(j);
-            unsigned pend = __ballot_sync(0xffffffffu, ok && (d2 < tau64[q] || (d2 == tau64[q] && jj32 < tauj[q])));
-            while (pend) {
-                const int src = __ffs(pend) - 1;
-                pend &= pend - 1;
-                const int qq = __shfl_sync(0xffffffffu, q, src);
-                const int jn = __shfl_sync(0xffffffffu, jj32, src);
-                const double dd = __shfl_sync(0xffffffffu, d2, src);
-                const double tcur = tau64[qq];
-                if (!(dd < tcur || (dd == tcur && jn < tauj[qq]))) continue;      // an earlier insertion tightened the bound
-                const int c = cnt[qq];
-                const int slot = c < K ? c : argmax[qq];
-                __syncwarp();
-                if (lane == 0) {
-                    list_d[qq * K + slot] = dd;
-                    list_j[qq * K + slot] = jn;
-                    if (c < K) cnt[qq] = c + 1;
-                }
-                __syncwarp();
-                if (c + 1 >= K) {
-                    // the list is full: its largest (distance, index) is the new bound
-                    double bd = -1.0;
-                    int bj = -1, bs = 0;
-                    for (int s = lane; s < K; s += 32) {
-                        const double v = list_d[qq * K + s];
-                        const int vj = list_j[qq * K + s];
-                        if (v > bd || (v == bd && vj > bj)) { bd = v; bj = vj; bs = s; }
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-                        const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
-                        const int os = __shfl_xor_sync(0xffffffffu, bs, o);
-                        if (od > bd || (od == bd && oj > bj)) { bd = od; bj = oj; bs = os; }
-                    }
-                    if (lane == 0) {
-                        tau64[qq] = bd;
-                        tauj[qq] = bj;
-                        argmax[qq] = bs;
-                        Tq[qq] = __double2float_ru(bd - nlo64[qq]);
-                    }
-                    __syncwarp();
-                }
-            }
+        if (DBG) {
+            c_work += t_mid - t_begin;
+            c_wait += clock64() - t_mid;
         }
-        if (lane == 0) qcnt[warp] = 0;
-        __syncthreads();
+    }
+    if (DBG && lane == 0) {
+        if (warp == 0) { atomicAdd(dbg + 0, static_cast<unsigned long long>(c_work)); atomicAdd(dbg + 1, static_cast<unsigned long long>(c_wait)); }
+        if (warp == kProducers) { atomicAdd(dbg + 2, static_cast<unsigned long long>(c_work)); atomicAdd(dbg + 3, static_cast<unsigned long long>(c_wait)); }
+        if (!producer) { atomicAdd(dbg + 4, static_cast<unsigned long long>(c_cand)); atomicAdd(dbg + 5, static_cast<unsigned long long>(c_redo)); }
+        if (warp == 0) atomicAdd(dbg + 6, 1ull);
     }
 
     // ---- rows of the result: sorted by column, distances as square roots (knn.rs:27, :65)
-    for (int q = warp * kOwnerQueries; q < (warp + 1) * kOwnerQueries; ++q) {
-        if (qlocal0 + q >= nq || cnt[q] != K) continue;
-        for (int s = lane; s < K; s += 32) {
-            const int j = list_j[q * K + s];
-            int rank = 0;
-            for (int u = 0; u < K; ++u) rank += list_j[q * K + u] < j;
-            out_j[(qlocal0 + q) * K + rank] = j;
-            out_d[(qlocal0 + q) * K + rank] = sqrt(list_d[q * K + s]);
+    if (!producer) {
+        const int cw = warp - kProducers;
+        for (int q = cw * kConsQueries; q < (cw + 1) * kConsQueries; ++q) {
+            if (qlocal0 + q >= nq || list_j[q * K + K - 1] == 0x7fffffff) continue;
+            for (int s = lane; s < K; s += 32) {
+                const int j = list_j[q * K + s];
+                int rank = 0;
+                for (int u = 0; u < K; ++u) rank += list_j[q * K + u] < j;
+                out_j[(qlocal0 + q) * K + rank] = j;
+                out_d[(qlocal0 + q) * K + rank] = sqrt(list_d[q * K + s]);
+            }
         }
     }
 }
 
 template <int DP>
 void knn_run(snapb200_ctx* c, const double* P64, int64_t n, int64_t npad, int d, int64_t q0, int64_t nq, int K,
-             float* Pt, double* nrm64, double* colsum, int32_t* out_j, double* out_d) {
+             float* Pt, double* nrm64, float* nlo32, double* P64p, double* colsum, int32_t* out_j, double* out_d) {
     cudaStream_t st = c->stream;
+    const double shrink = 1.0 - static_cast<double>(DP + 8) * 5.9604644775390625e-08;   // (DP + 8) * 2^-24
     SB_CUDA(cudaMemsetAsync(colsum, 0, sizeof(double) * kKnnMaxDim, st));
     knn_colsum_kernel<DP><<<c->num_sms * 2, 256, 0, st>>>(P64, n, d, colsum);
     SB_LAUNCH_CHECK();
-    knn_prep_kernel<DP><<<static_cast<unsigned>(ceil_div(npad, 256)), 256, 0, st>>>(P64, n, npad, d, colsum, Pt, nrm64);
+    knn_prep_kernel<DP><<<static_cast<unsigned>(ceil_div(npad, 256)), 256, 0, st>>>(P64, n, npad, d, colsum, shrink, Pt, nrm64, nlo32, P64p);
     SB_LAUNCH_CHECK();
-    const KnnSmem L = knn_smem_layout(DP, K);
-    SB_CHECK(L.total <= 232448, "knn: n_neighbors does not fit the shared-memory lists (at most 100; 84 with more than 32 dimensions)");
-    SB_CUDA(cudaFuncSetAttribute(knn_scan_kernel<DP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
-    const double shrink = 1.0 - static_cast<double>(DP + 8) * 5.9604644775390625e-08;   // (DP + 8) * 2^-24
-    knn_scan_kernel<DP><<<static_cast<unsigned>(ceil_div(nq, kT)), kKnnThreads, L.total, st>>>(
-        Pt, nrm64, P64, n, npad, d, q0, nq, K, shrink, L, out_j, out_d);
+    constexpr int kSmemMax = 232448;
+    const int probe = getenv("SNAPB200_KNN_PROBE") ? atoi(getenv("SNAPB200_KNN_PROBE")) : 0;
+    bool stage_q = true;
+    KnnSmem L = knn_smem_layout(DP, K, true);
+    if (L.total > kSmemMax) {
+        stage_q = false;
+        L = knn_smem_layout(DP, K, false);
+    }
+    SB_CHECK(L.total <= kSmemMax, "knn: n_neighbors does not fit the shared-memory lists (at most 100; 74 with more than 32 dimensions)");
+    DevBuf<unsigned long long> dbg;
+    const unsigned grid = static_cast<unsigned>(ceil_div(nq, kT));
+    if (probe == 4) {
+        dbg.alloc(8);
+        SB_CUDA(cudaMemsetAsync(dbg.p, 0, 64, st));
+        SB_CUDA(cudaFuncSetAttribute(knn_scan_kernel<DP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        knn_scan_kernel<DP, true><<<grid, kScanThreads, L.total, st>>>(
+            Pt, nrm64, nlo32, P64p, n, npad, q0, nq, K, shrink, L, out_j, out_d, probe, stage_q ? 1 : 0, dbg.p);
+    } else {
+        SB_CUDA(cudaFuncSetAttribute(knn_scan_kernel<DP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+        knn_scan_kernel<DP, false><<<grid, kScanThreads, L.total, st>>>(
+            Pt, nrm64, nlo32, P64p, n, npad, q0, nq, K, shrink, L, out_j, out_d, probe, stage_q ? 1 : 0, nullptr);
+    }
     SB_LAUNCH_CHECK();
-    count_launch(c);
-    count_launch(c);
-    count_launch(c);
+    if (probe == 4) {
+        unsigned long long h[8];
+        SB_CUDA(cudaMemcpyAsync(h, dbg.p, 64, cudaMemcpyDeviceToHost, st));
+        SB_CUDA(cudaStreamSynchronize(st));
+        const double ctas = static_cast<double>(h[6]), tiles = ctas * static_cast<double>(npad / kT + 1);
+        fprintf(stderr, "[snapb200] knn probe: %.0f CTAs x %lld tiles; per CTA-tile cycles: producer work %.0f wait %.0f | consumer(0) work %.0f wait %.0f | "
+                "queued candidates %.2f, flagged queries %.4f (stage_q=%d)\n", ctas, static_cast<long long>(npad / kT), h[0] / tiles, h[1] / tiles,
+                h[2] / tiles, h[3] / tiles, h[4] / tiles, h[5] / tiles, stage_q ? 1 : 0);
+    }
+    count_launch(c, 3);
 }
 
 }  // namespace
@@ -361,8 +487,8 @@ void knn(snapb200_ctx* c, int64_t n, int d, const double* points, int on_device,
     const auto wall0 = std::chrono::steady_clock::now();
     cudaStream_t st = c->stream;
     const int64_t npad = ceil_div(n, kT) * kT;
-    DevBuf<double> P64, nrm64, colsum, out_d;
-    DevBuf<float> Pt;
+    DevBuf<double> P64, P64p, nrm64, colsum, out_d;
+    DevBuf<float> Pt, nlo32;
     DevBuf<int32_t> out_j;
     const double* Pdev = points;
     if (!on_device) {
@@ -372,16 +498,18 @@ void knn(snapb200_ctx* c, int64_t n, int d, const double* points, int on_device,
     }
     const int DP = d <= 8 ? 8 : d <= 16 ? 16 : d <= 32 ? 32 : 64;
     Pt.alloc(npad * DP);
+    P64p.alloc(npad * DP);
     nrm64.alloc(npad);
+    nlo32.alloc(npad);
     colsum.alloc(kKnnMaxDim);
     out_j.alloc(nq * K);
     out_d.alloc(nq * K);
     SB_CUDA(cudaEventRecord(c->ev0, st));
     switch (DP) {
-        case 8: knn_run<8>(c, Pdev, n, npad, d, q0, nq, K, Pt.p, nrm64.p, colsum.p, out_j.p, out_d.p); break;
-        case 16: knn_run<16>(c, Pdev, n, npad, d, q0, nq, K, Pt.p, nrm64.p, colsum.p, out_j.p, out_d.p); break;
-        case 32: knn_run<32>(c, Pdev, n, npad, d, q0, nq, K, Pt.p, nrm64.p, colsum.p, out_j.p, out_d.p); break;
-        default: knn_run<64>(c, Pdev, n, npad, d, q0, nq, K, Pt.p, nrm64.p, colsum.p, out_j.p, out_d.p); break;
+        case 8: knn_run<8>(c, Pdev, n, npad, d, q0, nq, K, Pt.p, nrm64.p, nlo32.p, P64p.p, colsum.p, out_j.p, out_d.p); break;
+        case 16: knn_run<16>(c, Pdev, n, npad, d, q0, nq, K, Pt.p, nrm64.p, nlo32.p, P64p.p, colsum.p, out_j.p, out_d.p); break;
+        case 32: knn_run<32>(c, Pdev, n, npad, d, q0, nq, K, Pt.p, nrm64.p, nlo32.p, P64p.p, colsum.p, out_j.p, out_d.p); break;
+        default: knn_run<64>(c, Pdev, n, npad, d, q0, nq, K, Pt.p, nrm64.p, nlo32.p, P64p.p, colsum.p, out_j.p, out_d.p); break;
     }
     SB_CUDA(cudaEventRecord(c->ev1, st));
     copy_to_host(c, out_indices, out_j.p, sizeof(int32_t) * nq * K);
