@@ -114,6 +114,28 @@ if rank == 0:
     assert eigvec_agreement(ev_o, q_o, q_all).min() >= 0.999
     np.testing.assert_allclose(np.linalg.norm(q_all, axis=0), np.linalg.norm(q_o, axis=0), rtol=1e-3)
     print(f"NYSTROM_OK world={world}")
+
+# ---- pp.knn on row shards: every rank passes its rows of the embedding, gets its rows of the graph (global columns);
+#      against the CPU oracle on the whole point set
+from snapatac2_b200 import pp
+rng_k = np.random.default_rng(5)
+centres = rng_k.normal(scale=3.0, size=(6, 30))
+lab = rng_k.integers(0, 6, size=5003)
+P_all = centres[lab] + rng_k.normal(size=(5003, 30)) * 0.3
+kb = dist.equal_row_splits(P_all.shape[0], world)
+ad_k = MiniAnnData(np.ones((int(kb[rank + 1] - kb[rank]), 2)))
+ad_k.obsm["X_spectral"] = P_all[int(kb[rank]):int(kb[rank + 1])]
+pp.knn(ad_k, n_neighbors=30, engine=eng)
+g_local = ad_k.obsp["distances"]
+assert g_local.shape == (int(kb[rank + 1] - kb[rank]), P_all.shape[0])
+parts_k = [None] * world
+td.gather_object((g_local.indices, g_local.data), parts_k if rank == 0 else None, dst=0)
+if rank == 0:
+    import oracle
+    want = oracle.knn.nearest_neighbour_graph_kdtree(P_all, 30)
+    np.testing.assert_array_equal(np.concatenate([p[0] for p in parts_k]), want.indices)
+    np.testing.assert_array_equal(np.concatenate([p[1] for p in parts_k]), want.data)
+    print(f"KNN_OK world={world}")
 td.barrier()
 eng.close()
 td.destroy_process_group()

@@ -29,3 +29,4 @@ def test_shard_invariance(mode):
     assert "MULTI_OK" in res.stdout
     assert "MULTIVIEW_OK" in res.stdout
     assert "NYSTROM_OK" in res.stdout
+    assert "KNN_OK" in res.stdout

@@ -176,6 +176,11 @@ assert np.allclose(got, want[r0:r0 + mine.shape[0]], rtol=1e-12, atol=0), np.abs
 assert [c for c, _, _ in dist.chunk_overlaps(r0, mine.shape[0], chunk)] == ([0, 1] if rank == 0 else [1, 2])
 assert np.array_equal(dist.allreduce_array(np.array([rank + 1.0, 5.0]), "sum"), [3.0, 10.0])
 assert np.array_equal(dist.allreduce_array(np.array([rank + 1.0]), "min"), [1.0])
+# pp.knn on row shards: the points are all-gathered on the host, the rank's query range starts at its first row
+from snapatac2_b200 import pp
+pts_full = rng.standard_normal((spec.n, 6))
+pts_all, q0 = pp._gather_points(pts_full[r0:r0 + mine.shape[0]])
+assert q0 == r0 and np.array_equal(pts_all, pts_full)
 td.barrier()
 td.destroy_process_group()
 print("ok", rank)
