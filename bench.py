@@ -396,6 +396,7 @@ def run_ours(args):
     #      staging, the H2D copies, prepare, eigsh, the eigenvectors back in a fresh numpy array.
     e2e = None
     e2e_skipped = None
+    knn = None
     if not args.no_e2e:
         import psutil
         need = 16 * nnz_local * world          # int64 indices + float32 values + the int32 export, all ranks of this box
@@ -455,9 +456,24 @@ def run_ours(args):
                "host_threads": int(st_e2e["host_threads"]), "ms_load": st_e2e["ms_load"],
                "ms_prepare": st_e2e["ms_prepare_wall"], "ms_eigsh": st_e2e["ms_eigsh"],
                "note": "values are scanned on the host (all ones -> not shipped), on background threads while the GPU already "
-                       "prepares and solves; h2d bytes = indptr + int32 indices",
+                       "prepares and solves; h2d bytes = indptr + the indices as 16-bit differences with a side list "
+                       "(csrc/delta_encode.h; 4 bytes per index with SNAPB200_NO_DELTA=1)",
                "setup_s": t_build}
         del adata, X, np_idx, np_val
+        # ---- the consumer next to the path, on what the call above returned (outside every timed region of the
+        #      headline metric; one GPU only): pp.knn = exact 50-nearest-neighbour graph of the embedding
+        if world == 1 and not args.no_knn and n <= 2_000_000:
+            try:
+                from snapatac2_b200 import pp
+                t0 = time.perf_counter()
+                adj = pp.knn(emb_e2e, n_neighbors=50, engine=eng)
+                dt_knn = time.perf_counter() - t0
+                knn = {"api": "pp.knn(X_spectral of the e2e call, n_neighbors=50)", "points": int(emb_e2e.shape[0]),
+                       "dims": int(emb_e2e.shape[1]), "ms": 1e3 * dt_knn, "ms_device": eng.stats()["ms_knn"],
+                       "cells_per_s": emb_e2e.shape[0] / dt_knn, "nnz": int(adj.nnz)}
+                del adj
+            except Exception as exc:          # never let the side leg take the headline line down
+                knn = {"error": str(exc)[:300]}
 
     # ---- CPU baseline beside it (rank 0, N=1 only)
     cpu = None
@@ -483,7 +499,7 @@ def run_ours(args):
                        "parallelism": f"rows/{world}", "l2": "inputs larger than L2 (index stream >> 126 MB)"
                        if nnz_local * 4 > (256 << 20) else "inputs fit L2; operator_time flushes L2 between iterations"},
             "clocks": clocks, "e2e": e2e if e2e is not None else ({"skipped": e2e_skipped} if e2e_skipped else None),
-            "nystrom": nystrom, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "nystrom": nystrom, "knn": knn, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "timing": {"device_ms_total": total_ms, "wall_ms_total": wall_ms, "generate_s": t_gen,
                        "last_step_call_ms": call_ms, "step_wall_ms": step_wall,
                        "pool_mallocs_in_timed_region": stats["pool_mallocs"] - st0["pool_mallocs"],
@@ -657,6 +673,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-slab", action="store_true", help="skip the 100k-row slab leg of the CPU baseline")
+    ap.add_argument("--no-knn", action="store_true", help="skip the pp.knn side leg on the embedding of the e2e call")
     ap.add_argument("--nystrom", type=int, default=0,
                     help="also time the Nystrom path (reference: sample_size) with this many landmarks on the same resident data")
     args = ap.parse_args()

@@ -269,6 +269,7 @@ void grow_keep(snapb200_ctx* c, DevBuf<T>& buf, int64_t used, int64_t need) {
 
 void load_begin(snapb200_ctx* c, int64_t m, int64_t rows_hint, int64_t nnz_hint) {
     SB_CHECK(m >= 1 && m < (1ll << 31), "load_begin: m must be in [1, 2^31)");
+    join_value_scan(c);      // a background scan of the previous matrix's values must not outlive it
     Csr& X = c->X;
     c->loaded = false;
     c->prepared = false;

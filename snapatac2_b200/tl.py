@@ -129,26 +129,6 @@ class RowBlocks:
             yield from src
 
 
-def _load(engine: Engine, X, chunk_size=20000):
-    """Load ``X`` (scipy CSR or :class:`RowBlocks`) as this rank's shard; returns ``(n_global, row0)``."""
-    rank, ws = dist.world()
-    if isinstance(X, RowBlocks):
-        engine.load_blocks(X.blocks(chunk_size), X.n_vars)
-        n_local = engine.n_local
-        if ws > 1:
-            n_locals = dist.allgather_ints(n_local)
-            engine.set_geometry(sum(n_locals), dist.shard_offsets(n_locals)[rank])
-        return engine.n_global, engine.row0
-    n_local = X.shape[0]
-    if ws > 1:
-        n_locals = dist.allgather_ints(n_local)
-        n_global, row0 = sum(n_locals), dist.shard_offsets(n_locals)[rank]
-    else:
-        n_global, row0 = n_local, 0
-    engine.load_csr(X, n_global=n_global, row0=row0)
-    return n_global, row0
-
-
 def spectral_embedding(engine: Engine, X, selected_features, n_components, random_state,
                        feature_weights=None, *, n_global=None, row0=0, binarized=None,
                        tol=0.0, block=0, max_basis=0, max_ops=0, return_parts=False, scale_by_sqrt_eval=False,
