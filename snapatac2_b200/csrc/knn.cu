@@ -69,7 +69,7 @@ template <int DP>
 __global__ void __launch_bounds__(256) knn_prep_kernel(const double* __restrict__ P, int64_t n, int64_t npad, int d,
                                                        const double* __restrict__ sum, double shrink, float* __restrict__ Pt,
                                                        double* __restrict__ nrm64, float* __restrict__ nlo32,
-                                                       double* __restrict__ P64p) {
+                                                       double* __restrict__ P64p, int* __restrict__ bad) {
     const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (j >= npad) return;
     double nn = 0.0;
@@ -86,6 +86,8 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const double* __restrict_
             Pt[k * npad + j] = static_cast<float>(a);
             P64p[j * DP + k] = v;
         }
+        // NaN / inf coordinates (the reference's kd-tree refuses them: NonFiniteCoordinate), or a spread float32 cannot hold
+        if (!(nn <= 3.0e38)) *bad = 1;
     } else {
 #pragma unroll
         for (int k = 0; k < DP; ++k) {
@@ -425,12 +427,19 @@ template <int DP>
 void knn_run(snapb200_ctx* c, const double* P64, int64_t n, int64_t npad, int d, int64_t q0, int64_t nq, int K,
              float* Pt, double* nrm64, float* nlo32, double* P64p, double* colsum, int32_t* out_j, double* out_d) {
     cudaStream_t st = c->stream;
+    DevBuf<int> bad;
+    bad.alloc(1);
+    SB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
     const double shrink = 1.0 - static_cast<double>(DP + 8) * 5.9604644775390625e-08;   // (DP + 8) * 2^-24
     SB_CUDA(cudaMemsetAsync(colsum, 0, sizeof(double) * kKnnMaxDim, st));
     knn_colsum_kernel<DP><<<c->num_sms * 2, 256, 0, st>>>(P64, n, d, colsum);
     SB_LAUNCH_CHECK();
-    knn_prep_kernel<DP><<<static_cast<unsigned>(ceil_div(npad, 256)), 256, 0, st>>>(P64, n, npad, d, colsum, shrink, Pt, nrm64, nlo32, P64p);
+    knn_prep_kernel<DP><<<static_cast<unsigned>(ceil_div(npad, 256)), 256, 0, st>>>(P64, n, npad, d, colsum, shrink, Pt, nrm64, nlo32, P64p, bad.p);
     SB_LAUNCH_CHECK();
+    int hbad = 0;
+    SB_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SB_CUDA(cudaStreamSynchronize(st));
+    SB_CHECK(hbad == 0, "knn: the points contain a non-finite coordinate (or span more than float32 can hold)");
     constexpr int kSmemMax = 232448;
     const int probe = getenv("SNAPB200_KNN_PROBE") ? atoi(getenv("SNAPB200_KNN_PROBE")) : 0;
     bool stage_q = true;

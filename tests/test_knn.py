@@ -159,6 +159,19 @@ def test_cuda_graph_on_hard_inputs(engine):
 
 
 @pytest.mark.gpu
+def test_cuda_refuses_non_finite_points(engine):
+    """The reference's kd-tree refuses NaN / inf coordinates (kdtree: NonFiniteCoordinate, unwrapped at knn.rs:20)."""
+    P = _blobs(500, 8, 3)
+    for bad in (np.nan, np.inf, -np.inf):
+        Q = P.copy()
+        Q[123, 4] = bad
+        with pytest.raises(RuntimeError, match="non-finite"):
+            engine.knn(Q, 10)
+    idx, _ = engine.knn(P, 10)          # the context is usable afterwards
+    assert idx.shape == (500, 10)
+
+
+@pytest.mark.gpu
 def test_cuda_query_ranges_and_reproducibility(engine):
     """A rank of a row-sharded run searches its own rows against all points; three runs are bit-identical
     (the reference's test_reproducibility, tests/test_tools.py:111-115)."""
