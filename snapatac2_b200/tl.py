@@ -117,6 +117,46 @@ class RowBlocks:
         self.source = source
         self.n_vars = int(n_vars)
 
+    @classmethod
+    def from_csr_group(cls, group, n_vars=None):
+        """The on-disk CSR layout of an ``.h5ad`` / anndata-rs file (``src/utils/anndata.rs:213-229`` reads it
+        through ``chunked_X``): a group with the datasets ``indptr``, ``indices``, ``data`` and the attribute
+        ``shape``.  ``group`` is an ``h5py.Group`` / ``zarr`` group -- anything whose members slice like arrays;
+        one block of rows is read per step, nothing else is held in memory."""
+        attrs = getattr(group, "attrs", {})
+        enc = attrs.get("encoding-type", "csr_matrix")
+        if isinstance(enc, bytes):
+            enc = enc.decode()
+        if enc not in ("csr_matrix", "csr_array"):
+            raise ValueError(f"X is stored as {enc!r}: the cosine path reads rows, a CSR layout is required")
+        indptr, indices, data = group["indptr"], group["indices"], group["data"]
+        n_obs = int(indptr.shape[0]) - 1
+        shape = attrs.get("shape", None)
+        if n_vars is None:
+            if shape is None:
+                raise ValueError("n_vars is neither given nor stored in the group's 'shape' attribute")
+            n_vars = int(shape[1])
+
+        def blocks(chunk_size):
+            for i in range(0, n_obs, chunk_size):
+                j = min(i + chunk_size, n_obs)
+                ptr = np.asarray(indptr[i:j + 1], dtype=np.int64)
+                lo, hi = int(ptr[0]), int(ptr[-1])
+                yield sp.csr_matrix((np.asarray(data[lo:hi]), np.asarray(indices[lo:hi]), ptr - lo), shape=(j - i, n_vars))
+
+        src = type("CsrGroupRows", (), {"chunked": staticmethod(blocks)})()
+        return cls(src, n_vars)
+
+    @classmethod
+    def from_h5ad(cls, path, key="X"):
+        """Rows of ``path[key]`` (an ``.h5ad`` written by anndata / SnapATAC2 with a CSR ``X``), read block by
+        block with h5py.  h5py is not part of this image: the import happens here, on use."""
+        import h5py      # noqa: deliberately late
+        f = h5py.File(path, "r")
+        rb = cls.from_csr_group(f[key])
+        rb._file = f     # keep the file open as long as the view lives
+        return rb
+
     def blocks(self, chunk_size):
         src = self.source
         if hasattr(src, "chunked"):

@@ -226,6 +226,21 @@ def test_row_blocks_sources():
         got = sp.vstack(blocks, format="csr")
         assert (got != X).nnz == 0 and got.shape == X.shape
 
+    # the on-disk CSR group of an .h5ad (h5py is absent here: numpy arrays slice the same way)
+    class Group(dict):
+        attrs = {"encoding-type": "csr_matrix", "shape": np.array([53, 40])}
+
+    g = Group(indptr=X.indptr, indices=X.indices, data=X.data)
+    rb = tl.RowBlocks.from_csr_group(g)
+    assert rb.n_vars == 40
+    for chunk in (1, 16, 53, 1000):
+        got = sp.vstack(list(rb.blocks(chunk)), format="csr")
+        assert (got != X).nnz == 0 and got.shape == X.shape
+    Group.attrs = {"encoding-type": "csc_matrix", "shape": np.array([53, 40])}
+    with pytest.raises(ValueError, match="CSR layout"):
+        tl.RowBlocks.from_csr_group(g)
+    Group.attrs = {"encoding-type": "csr_matrix", "shape": np.array([53, 40])}
+
     class FakeAnn:
         def __init__(self, x):
             self.X, self.n_vars, self.n_obs = x, 40, 53
