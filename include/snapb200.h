@@ -73,6 +73,7 @@ typedef struct snapb200_stats {
                               delta-encoded, see csrc/ingest.cu; 4 otherwise)                               */
     double ms_knn;         /* last knn: device time of centring + filter/exact scan (CUDA events)          */
     double ms_knn_wall;    /* last knn: wall clock of the call, uploads and the copy of the result included */
+    int64_t knn_mma;       /* last knn: 1 = the filter ran on the tensor cores (mma.sync tf32 x 3, SNAPB200_KNN_MMA) */
 } snapb200_stats;
 
 /* Library / error plumbing. */

@@ -43,7 +43,7 @@ class Stats(C.Structure):
         ("ms_pool", C.c_double), ("pool_mallocs", C.c_int64),
         ("converged", C.c_int64), ("n_spec_ops", C.c_int64), ("ms_d2h", C.c_double),
         ("bytes_h2d", C.c_int64), ("host_threads", C.c_int64), ("fused_allreduce", C.c_int64), ("bytes_h2d_indices", C.c_int64),
-        ("ms_knn", C.c_double), ("ms_knn_wall", C.c_double),
+        ("ms_knn", C.c_double), ("ms_knn_wall", C.c_double), ("knn_mma", C.c_int64),
     ]
 
     def as_dict(self):

@@ -19,9 +19,9 @@
 // exact search on the CPU; ties at the k-th distance are broken by the smaller index (the kd-tree's tie
 // order is unspecified).  The expected number of float64 evaluations per query is ~k ln(n / k).
 //
-// Float64 tensor-core MMA does not apply (the filter is float32, the exact stage is scalar by
-// construction of the reference's summation order); a tcgen05 tf32x3 version of the filter is the
-// obvious next step and is not done here.
+// The filter has two implementations: FFMA (below) and mma.sync tf32 x 3 (further down, the default where it fits);
+// the exact stage is scalar by construction of the reference's summation order.  A tcgen05 version of the filter
+// is the obvious next step and is not done here.
 #include "ctx.cuh"
 
 #include <cuda_pipeline.h>
@@ -61,6 +61,22 @@ __global__ void __launch_bounds__(256) knn_colsum_kernel(const double* __restric
     if (threadIdx.x < d) atomicAdd(&sum[threadIdx.x], s_sum[threadIdx.x]);
 }
 
+__device__ __forceinline__ float to_tf32(float x) {
+    unsigned r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
+
+// Tensor-core operand layout (Ptf): per tile of 128 points one contiguous block of DP x 128 x 2 floats, ordered
+// [k / 8][point / 8][lane][hi b0, hi b1, lo b0, lo b1] where lane = (point % 8) * 4 + k % 4 holds the B fragment of
+// mma.m16n8k8 (b0: k % 8 < 4, b1: k % 8 >= 4): a warp reads its fragment, hi and lo, with one 16-byte load per lane.
+template <int DP>
+__device__ __forceinline__ int64_t knn_frag_index(int64_t j, int k) {
+    const int64_t tile = j >> 7;
+    const int pl = static_cast<int>(j & 127), kk = k & 7;
+    return (((tile * (DP / 8) + (k >> 3)) * 16 + (pl >> 3)) * 32 + (pl & 7) * 4 + (kk & 3)) * 4 + (kk >> 2);
+}
+
 // Per point: the centred float32 copy, dimension-major (Pt[k * npad + j]); the float64 squared norm of the
 // centred point and its shrunk float32 lower bound; the original float64 row padded to DP terms (P64p, the
 // exact stage reads it with compile-time trip counts: trailing (0 - 0)^2 terms add +0.0, which changes no sum).
@@ -69,7 +85,8 @@ template <int DP>
 __global__ void __launch_bounds__(256) knn_prep_kernel(const double* __restrict__ P, int64_t n, int64_t npad, int d,
                                                        const double* __restrict__ sum, double shrink, float* __restrict__ Pt,
                                                        double* __restrict__ nrm64, float* __restrict__ nlo32,
-                                                       double* __restrict__ P64p, int* __restrict__ bad) {
+                                                       double* __restrict__ P64p, int* __restrict__ bad,
+                                                       float* __restrict__ Ptf) {
     const int64_t j = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
     if (j >= npad) return;
     double nn = 0.0;
@@ -85,6 +102,12 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const double* __restrict_
             nn += a * a;
             Pt[k * npad + j] = static_cast<float>(a);
             P64p[j * DP + k] = v;
+            if (Ptf != nullptr) {          // tf32 split for the tensor-core filter: a = hi + lo + O(2^-22 |a|)
+                const float hi = to_tf32(static_cast<float>(a));
+                const int64_t at = knn_frag_index<DP>(j, k);
+                Ptf[at] = hi;
+                Ptf[at + 2] = to_tf32(static_cast<float>(a - static_cast<double>(hi)));
+            }
         }
         // NaN / inf coordinates (the reference's kd-tree refuses them: NonFiniteCoordinate), or a spread float32 cannot hold
         if (!(nn <= 3.0e38)) *bad = 1;
@@ -93,6 +116,11 @@ __global__ void __launch_bounds__(256) knn_prep_kernel(const double* __restrict_
         for (int k = 0; k < DP; ++k) {
             Pt[k * npad + j] = 0.f;
             P64p[j * DP + k] = 0.0;
+            if (Ptf != nullptr) {
+                const int64_t at = knn_frag_index<DP>(j, k);
+                Ptf[at] = 0.f;
+                Ptf[at + 2] = 0.f;
+            }
         }
         nn = CUDART_NAN;
     }
@@ -423,6 +451,271 @@ knn_scan_kernel(const float* __restrict__ Pt, const double* __restrict__ nrm64, 
     }
 }
 
+// ---- tensor-core variant of the filter (the default where it fits; SNAPB200_KNN_MMA=0 turns it off) ----------
+// The dot products of a tile through `mma.sync.m16n8k8` on tf32 operands, three passes per product
+// (lo*hi + hi*lo + hi*hi with a = hi + lo split in the prep kernel), fp32 accumulation.  The hardware's
+// accumulation order and rounding are not documented, so the norms are shrunk by 2^-14 instead of (DP + 8) 2^-24:
+// ~40x what the split (2^-21 relative) and ~100 fp32 accumulations can lose, still ~1 % of a typical k-th
+// distance.  Everything behind the filter (queue, exact float64 stage, lists) is the code above, unchanged.
+// A warp owns 64 queries x 32 points of the tile: 4 x 4 fragments of 16 x 8, 64 accumulator registers.
+struct KnnSmemM {
+    int nlo64, list_d, Af, Bf, Bn, Tq, qcnt, redo, list_j, queue, total;
+};
+
+inline KnnSmemM knn_smem_layout_mma(int DP, int K) {
+    KnnSmemM s;
+    int o = 0;
+    auto take = [&](int bytes) { const int at = o; o += (bytes + 15) & ~15; return at; };
+    s.nlo64 = take(kT * 8);
+    s.list_d = take(kT * K * 8);
+    s.Af = take(DP * kT * 2 * 4);          // [k / 8][query / 16][lane][hi a0..a3, lo a0..a3]
+    s.Bf = take(2 * DP * kT * 2 * 4);      // two buffers, each a verbatim copy of a tile of Ptf
+    s.Bn = take(2 * kT * 4);
+    s.Tq = take(kT * 4);
+    s.qcnt = take(2 * kConsumers * 4);
+    s.redo = take(2 * kConsumers * 4);
+    s.list_j = take(kT * K * 4);
+    s.queue = take(2 * kConsumers * kQueueSlots * 2);
+    s.total = o;
+    return s;
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const unsigned (&a)[4], const unsigned (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int DP, bool DBG>
+__global__ void __launch_bounds__(kScanThreads, 1)
+knn_scan_mma_kernel(const float* __restrict__ Ptf, const double* __restrict__ nrm64,
+                    const float* __restrict__ nlo32, const double* __restrict__ P64p, int64_t n, int64_t npad, int64_t q0,
+                    int64_t nq, int K, double shrink, KnnSmemM L, int32_t* __restrict__ out_j, double* __restrict__ out_d,
+                    unsigned long long* __restrict__ dbg) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* nlo64 = reinterpret_cast<double*>(smem + L.nlo64);
+    double* list_d = reinterpret_cast<double*>(smem + L.list_d);
+    float* Af = reinterpret_cast<float*>(smem + L.Af);
+    float* Bf = reinterpret_cast<float*>(smem + L.Bf);
+    float* Bn = reinterpret_cast<float*>(smem + L.Bn);
+    float* Tq = reinterpret_cast<float*>(smem + L.Tq);
+    int* qcnt = reinterpret_cast<int*>(smem + L.qcnt);
+    unsigned* redo = reinterpret_cast<unsigned*>(smem + L.redo);
+    int* list_j = reinterpret_cast<int*>(smem + L.list_j);
+    unsigned short* queue = reinterpret_cast<unsigned short*>(smem + L.queue);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool producer = warp < kProducers;
+    const int64_t qlocal0 = static_cast<int64_t>(blockIdx.x) * kT;
+    const int64_t qbase = q0 + qlocal0;
+
+    for (int e = tid; e < DP * kT; e += kScanThreads) {
+        const int k = e >> 7, q = e & (kT - 1);
+        const int64_t i = qbase + q;
+        const bool valid = qlocal0 + q < nq && i < n;
+        // A fragment of mma.m16n8k8 (row = query, col = k): a0 (g, t), a1 (g + 8, t), a2 (g, t + 4), a3 (g + 8, t + 4)
+        const int kk = k & 7, qq = q & 15;
+        const int dst = ((((k >> 3) * 8 + (q >> 4)) * 32 + (qq & 7) * 4 + (kk & 3)) * 8) + (kk >> 2) * 2 + (qq >> 3);
+        const int64_t src = knn_frag_index<DP>(valid ? i : 0, k);
+        Af[dst] = valid ? Ptf[src] : 0.f;
+        Af[dst + 4] = valid ? Ptf[src + 2] : 0.f;
+    }
+    if (tid < kT) {
+        const int64_t i = qbase + tid;
+        const bool valid = qlocal0 + tid < nq && i < n;
+        nlo64[tid] = valid ? nrm64[i] * shrink : 0.0;
+        Tq[tid] = valid ? CUDART_INF_F : -CUDART_INF_F;
+    }
+    if (tid < 2 * kConsumers) { qcnt[tid] = 0; redo[tid] = 0u; }
+    for (int e = tid; e < kT * K; e += kScanThreads) {
+        list_d[e] = CUDART_INF;
+        list_j[e] = 0x7fffffff;
+    }
+    const double* qrows = P64p + qbase * DP;
+
+    const int64_t n_tiles = npad / kT;
+    constexpr int kTileFloats = DP * kT * 2;
+    auto fetch = [&](int64_t t) {
+        const int64_t tile0 = t * kT;
+        float* dst = Bf + (t & 1) * kTileFloats;
+        const float* src = Ptf + t * kTileFloats;
+#pragma unroll
+        for (int r = 0; r < DP / 4; ++r) {
+            const int e4 = tid + 32 * kProducers * r;       // 16-byte chunk of the tile: DP * 64 of them
+            __pipeline_memcpy_async(dst + e4 * 4, src + e4 * 4, 16);
+        }
+        if (tid < kT / 4) __pipeline_memcpy_async(Bn + (t & 1) * kT + tid * 4, nlo32 + tile0 + tid * 4, 16);
+        __pipeline_commit();
+    };
+    if (producer) {
+        fetch(0);
+        __pipeline_wait_prior(0);
+    }
+    __syncthreads();
+
+    const KnnLists S{list_d, list_j, Tq, nlo64, K};
+    const int g = lane >> 2, t4 = lane & 3;            // fragment coordinates of this lane
+    const int qw = (warp & 1) * 64, pw = ((warp >> 1) & 3) * 32;
+
+    long long c_work = 0, c_wait = 0, c_cand = 0, c_redo = 0;
+    for (int64_t t = 0; t <= n_tiles; ++t) {
+        const int buf = static_cast<int>(t & 1);
+        const long long t_begin = DBG ? clock64() : 0;
+        if (producer) {
+            if (t < n_tiles) {
+                if (t + 1 < n_tiles) fetch(t + 1);
+                const float* bf = Bf + buf * kTileFloats;
+                float c[4][4][4];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) c[mt][nt][r] = 0.f;
+#pragma unroll
+                for (int ks = 0; ks < DP / 8; ++ks) {
+                    unsigned bhi[4][2], blo[4][2];
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const float4 v = *reinterpret_cast<const float4*>(bf + ((ks * 16 + (pw >> 3) + nt) * 32 + lane) * 4);
+                        bhi[nt][0] = __float_as_uint(v.x);
+                        bhi[nt][1] = __float_as_uint(v.y);
+                        blo[nt][0] = __float_as_uint(v.z);
+                        blo[nt][1] = __float_as_uint(v.w);
+                    }
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) {
+                        const float* ap = Af + ((ks * 8 + (qw >> 4) + mt) * 32 + lane) * 8;
+                        const float4 h = *reinterpret_cast<const float4*>(ap);
+                        const float4 l = *reinterpret_cast<const float4*>(ap + 4);
+                        const unsigned ahi[4] = {__float_as_uint(h.x), __float_as_uint(h.y), __float_as_uint(h.z), __float_as_uint(h.w)};
+                        const unsigned alo[4] = {__float_as_uint(l.x), __float_as_uint(l.y), __float_as_uint(l.z), __float_as_uint(l.w)};
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt) {
+                            mma_tf32(c[mt][nt], alo, bhi[nt]);
+                            mma_tf32(c[mt][nt], ahi, blo[nt]);
+                            mma_tf32(c[mt][nt], ahi, bhi[nt]);
+                        }
+                    }
+                }
+                // ---- filter.  Fragment element r of (mt, nt): query qw + 16 mt + g + 8 (r >> 1), point pw + 8 nt + 2 t4 + (r & 1)
+                float bn[4][2], tq[4][2];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const float2 v = *reinterpret_cast<const float2*>(Bn + buf * kT + pw + nt * 8 + 2 * t4);
+                    bn[nt][0] = v.x;
+                    bn[nt][1] = v.y;
+                }
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) {
+                    tq[mt][0] = *reinterpret_cast<volatile float*>(Tq + qw + mt * 16 + g);
+                    tq[mt][1] = *reinterpret_cast<volatile float*>(Tq + qw + mt * 16 + g + 8);
+                }
+                bool any = false;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) any |= fmaf(-2.f, c[mt][nt][r], bn[nt][r & 1]) <= tq[mt][r >> 1];
+                if (any) {
+                    unsigned m0 = 0u, m1 = 0u;        // bit (2 (mt & 1) + (r >> 1)) * 8 + 2 nt + (r & 1); m0: mt < 2, m1: mt >= 2
+#pragma unroll
+                    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+                            for (int r = 0; r < 4; ++r) {
+                                const int bit = (2 * mt + (r >> 1)) * 8 + 2 * nt + (r & 1);
+                                m0 |= (fmaf(-2.f, c[mt][nt][r], bn[nt][r & 1]) <= tq[mt][r >> 1] ? 1u : 0u) << bit;
+                                m1 |= (fmaf(-2.f, c[mt + 2][nt][r], bn[nt][r & 1]) <= tq[mt + 2][r >> 1] ? 1u : 0u) << bit;
+                            }
+#pragma unroll 1
+                    for (int half = 0; half < 2; ++half) {
+                        unsigned m = half ? m1 : m0;
+                        while (m) {
+                            const int bit = __ffs(m) - 1;
+                            m &= m - 1;
+                            const int row = bit >> 3, col = bit & 7;
+                            const int q = qw + (2 * half + (row >> 1)) * 16 + g + 8 * (row & 1);
+                            const int p = pw + (col >> 1) * 8 + 2 * t4 + (col & 1);
+                            const int owner = q / kConsQueries;
+                            const int pos = atomicAdd(&qcnt[buf * kConsumers + owner], 1);
+                            if (pos < kQueueSlots) queue[(buf * kConsumers + owner) * kQueueSlots + pos] = static_cast<unsigned short>((q << 7) | p);
+                            else atomicOr(&redo[buf * kConsumers + owner], 1u << (q % kConsQueries));
+                        }
+                    }
+                }
+                __pipeline_wait_prior(0);
+            }
+        } else if (t > 0) {
+            const int cw = warp - kProducers;
+            const int pb = buf ^ 1;
+            const int64_t tile0 = (t - 1) * kT;
+            const int ne = min(qcnt[pb * kConsumers + cw], kQueueSlots);
+            const unsigned flagged = redo[pb * kConsumers + cw];
+            if (DBG) {
+                c_cand += ne;
+                c_redo += __popc(flagged);
+            }
+            const unsigned short* Q = queue + (pb * kConsumers + cw) * kQueueSlots;
+            for (int base = 0; base < ne; base += 32) {
+                const int e = base + lane;
+                const bool have = e < ne;
+                const int code = have ? Q[e] : (cw * kConsQueries) << 7;
+                const int q = code >> 7, p = code & (kT - 1);
+                const int64_t i = qbase + q, j = tile0 + p;
+                const bool ok = have && j < n && j != i && !((flagged >> (q % kConsQueries)) & 1u);
+                double d2 = CUDART_INF;
+                if (ok) d2 = exact_d2<DP>(qrows + q * DP, P64p + j * DP);
+                knn_offer(S, ok, q, static_cast<int>(j), d2, lane);
+            }
+            for (unsigned f = flagged; f; f &= f - 1) {
+                const int q = cw * kConsQueries + (__ffs(f) - 1);
+                const int64_t i = qbase + q;
+                for (int p = lane; p < kT; p += 32) {
+                    const int64_t j = tile0 + p;
+                    const bool ok = j < n && j != i;
+                    double d2 = CUDART_INF;
+                    if (ok) d2 = exact_d2<DP>(qrows + q * DP, P64p + j * DP);
+                    knn_offer(S, ok, q, static_cast<int>(j), d2, lane);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                qcnt[pb * kConsumers + cw] = 0;
+                redo[pb * kConsumers + cw] = 0u;
+            }
+        }
+        const long long t_mid = DBG ? clock64() : 0;
+        __syncthreads();
+        if (DBG) {
+            c_work += t_mid - t_begin;
+            c_wait += clock64() - t_mid;
+        }
+    }
+    if (DBG && lane == 0) {
+        if (warp == 0) { atomicAdd(dbg + 0, static_cast<unsigned long long>(c_work)); atomicAdd(dbg + 1, static_cast<unsigned long long>(c_wait)); }
+        if (warp == kProducers) { atomicAdd(dbg + 2, static_cast<unsigned long long>(c_work)); atomicAdd(dbg + 3, static_cast<unsigned long long>(c_wait)); }
+        if (!producer) { atomicAdd(dbg + 4, static_cast<unsigned long long>(c_cand)); atomicAdd(dbg + 5, static_cast<unsigned long long>(c_redo)); }
+        if (warp == 0) atomicAdd(dbg + 6, 1ull);
+    }
+
+    if (!producer) {
+        const int cw = warp - kProducers;
+        for (int q = cw * kConsQueries; q < (cw + 1) * kConsQueries; ++q) {
+            if (qlocal0 + q >= nq || list_j[q * K + K - 1] == 0x7fffffff) continue;
+            for (int s = lane; s < K; s += 32) {
+                const int j = list_j[q * K + s];
+                int rank = 0;
+                for (int u = 0; u < K; ++u) rank += list_j[q * K + u] < j;
+                out_j[(qlocal0 + q) * K + rank] = j;
+                out_d[(qlocal0 + q) * K + rank] = sqrt(list_d[q * K + s]);
+            }
+        }
+    }
+}
+
 template <int DP>
 void knn_run(snapb200_ctx* c, const double* P64, int64_t n, int64_t npad, int d, int64_t q0, int64_t nq, int K,
              float* Pt, double* nrm64, float* nlo32, double* P64p, double* colsum, int32_t* out_j, double* out_d) {
@@ -430,18 +723,27 @@ void knn_run(snapb200_ctx* c, const double* P64, int64_t n, int64_t npad, int d,
     DevBuf<int> bad;
     bad.alloc(1);
     SB_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
-    const double shrink = 1.0 - static_cast<double>(DP + 8) * 5.9604644775390625e-08;   // (DP + 8) * 2^-24
+    constexpr int kSmemMax = 232448;
+    const int probe = getenv("SNAPB200_KNN_PROBE") ? atoi(getenv("SNAPB200_KNN_PROBE")) : 0;
+    // tensor-core filter (default; SNAPB200_KNN_MMA=0 selects the FFMA filter): at most 32 dimensions and lists
+    // that leave room for the split operand tiles (K <= 74 at DP = 32), otherwise the FFMA filter
+    const KnnSmemM LM = knn_smem_layout_mma(DP, K);
+    const bool mma_off = getenv("SNAPB200_KNN_MMA") != nullptr && atoi(getenv("SNAPB200_KNN_MMA")) == 0;
+    const bool use_mma = DP <= 32 && LM.total <= kSmemMax && !mma_off && probe != 1;
+    DevBuf<float> Ptf;
+    if (use_mma) Ptf.alloc(npad * DP * 2);
+    const double shrink = use_mma ? 1.0 - 6.103515625e-05                                           // 2^-14
+                                  : 1.0 - static_cast<double>(DP + 8) * 5.9604644775390625e-08;     // (DP + 8) * 2^-24
     SB_CUDA(cudaMemsetAsync(colsum, 0, sizeof(double) * kKnnMaxDim, st));
     knn_colsum_kernel<DP><<<c->num_sms * 2, 256, 0, st>>>(P64, n, d, colsum);
     SB_LAUNCH_CHECK();
-    knn_prep_kernel<DP><<<static_cast<unsigned>(ceil_div(npad, 256)), 256, 0, st>>>(P64, n, npad, d, colsum, shrink, Pt, nrm64, nlo32, P64p, bad.p);
+    knn_prep_kernel<DP><<<static_cast<unsigned>(ceil_div(npad, 256)), 256, 0, st>>>(P64, n, npad, d, colsum, shrink, Pt, nrm64, nlo32, P64p, bad.p,
+                                                                                     Ptf.p);
     SB_LAUNCH_CHECK();
     int hbad = 0;
     SB_CUDA(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
     SB_CUDA(cudaStreamSynchronize(st));
     SB_CHECK(hbad == 0, "knn: the points contain a non-finite coordinate (or span more than float32 can hold)");
-    constexpr int kSmemMax = 232448;
-    const int probe = getenv("SNAPB200_KNN_PROBE") ? atoi(getenv("SNAPB200_KNN_PROBE")) : 0;
     bool stage_q = true;
     KnnSmem L = knn_smem_layout(DP, K, true);
     if (L.total > kSmemMax) {
@@ -460,6 +762,20 @@ void knn_run(snapb200_ctx* c, const double* P64, int64_t n, int64_t npad, int d,
     if (probe == 4) {
         dbg.alloc(8);
         SB_CUDA(cudaMemsetAsync(dbg.p, 0, 64, st));
+    }
+    if constexpr (DP <= 32) {
+        if (use_mma) {
+            auto launch_mma = [&](auto kernel, unsigned long long* dbg_ptr) {
+                SB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LM.total));
+                kernel<<<grid, kScanThreads, LM.total, st>>>(Ptf.p, nrm64, nlo32, P64p, n, npad, q0, nq, K, shrink, LM, out_j, out_d, dbg_ptr);
+            };
+            if (probe == 4) launch_mma(knn_scan_mma_kernel<DP, true>, dbg.p);
+            else launch_mma(knn_scan_mma_kernel<DP, false>, nullptr);
+        }
+    }
+    if (use_mma) {
+        stage_q = false;
+    } else if (probe == 4) {
         launch(knn_scan_kernel<DP, true, 4>, dbg.p);
     } else if (unroll == 4) {
         launch(knn_scan_kernel<DP, false, 4>, nullptr);
@@ -476,6 +792,7 @@ void knn_run(snapb200_ctx* c, const double* P64, int64_t n, int64_t npad, int d,
                 "queued candidates %.2f, flagged queries %.4f (stage_q=%d)\n", ctas, static_cast<long long>(npad / kT), h[0] / tiles, h[1] / tiles,
                 h[2] / tiles, h[3] / tiles, h[4] / tiles, h[5] / tiles, stage_q ? 1 : 0);
     }
+    c->stats.knn_mma = use_mma ? 1 : 0;
     count_launch(c, 3);
 }
 
