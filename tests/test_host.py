@@ -287,3 +287,23 @@ def test_delta_encoding_of_the_index_transfer_round_trips(dtype):
     # (4) nothing but wide gaps: the side list cannot hold a chunk -> the caller is told to ship plain int32
     wide = (np.arange(3 << 20, dtype=np.int64) % 2) * 100_000
     assert _delta_selftest(wide.astype(dtype))[0] == 1
+
+
+def test_delta_encoding_property_random_streams():
+    """Random index streams (hypothesis): whatever the mix of gaps, repeats, descents and run lengths, the chunk
+    format either replays to the input or reports that the side list would overflow (never a mismatch)."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(seed=st.integers(0, 2**31 - 1), n=st.integers(1, 70_000),
+           wide=st.floats(0.0, 1.0), dtype=st.sampled_from([np.int32, np.int64]))
+    def run(seed, n, wide, dtype):
+        rng = np.random.default_rng(seed)
+        steps = np.where(rng.random(n) < wide, rng.integers(-(2**31 - 1), 2**31 - 1, size=n), rng.integers(0, 70_000, size=n))
+        idx = np.abs(np.cumsum(steps)) % (2**31 - 1)
+        rc, n_side = _delta_selftest(idx.astype(dtype))
+        assert rc in (0, 1)
+        if rc == 0:
+            assert n_side >= (n + 2047) // 2048
+
+    run()
