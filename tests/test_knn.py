@@ -92,6 +92,45 @@ def test_wrapper_argument_handling_needs_no_gpu():
         pp.knn(MiniAnnData(np.ones((4, 3))))      # no X_spectral yet
 
 
+class _OracleBackedEngine:
+    """Stands where snapatac2_b200.Engine would: answers ``knn`` from the oracle, so the host-side mirror
+    (argument handling, CSR assembly, dtype per method, where the result goes) is checked without a GPU."""
+
+    def __init__(self):
+        self.calls = []
+
+    def knn(self, points, n_neighbors, q0=0, nq=None):
+        n = points.shape[0]
+        nq = n - q0 if nq is None else nq
+        self.calls.append((points.shape, n_neighbors, q0, nq))
+        g = oracle.knn.nearest_neighbour_graph(points, n_neighbors, rows=np.arange(q0, q0 + nq))
+        K = max(0, min(n_neighbors, n - 1))
+        return g.indices.reshape(nq, K).astype(np.int32), g.data.reshape(nq, K)
+
+
+def test_host_mirror_equals_reference_wrapper_vectors_with_a_stub_engine():
+    z = _golden()
+    P = z["points"]
+    eng = _OracleBackedEngine()
+    ad = MiniAnnData(np.ones((400, 3)))
+    ad.obsm["X_spectral"] = P
+    ad.obsm["other"] = P[:, ::-1].copy()
+    _same_graph(pp.knn(ad, n_neighbors=10, inplace=False, engine=eng), _csr(z, "k10"))
+    _same_graph(pp.knn(ad, n_neighbors=10, use_dims=5, inplace=False, engine=eng), _csr(z, "k10_dims5"))
+    _same_graph(pp.knn(ad, n_neighbors=10, use_dims=[0, 3, 7], inplace=False, engine=eng), _csr(z, "k10_dimslist"))
+    _same_graph(pp.knn(ad, n_neighbors=7, use_rep="other", inplace=False, engine=eng), _csr(z, "k7_other"))
+    assert pp.knn(ad, n_neighbors=25, engine=eng) is None                     # inplace by default: stored, nothing returned
+    _same_graph(ad.obsp["distances"], _csr(z, "k25_inplace"))
+    _same_graph(pp.knn(P, n_neighbors=10, inplace=True, engine=eng), _csr(z, "k10_ndarray"))   # ndarray: returned
+    big = pp.knn(ad, n_neighbors=450, inplace=False, engine=eng)              # more neighbours than other points
+    np.testing.assert_array_equal(np.diff(big.indptr), z["k450_row_lengths"])
+    np.testing.assert_array_equal(big.data[: big.indptr[1]], z["k450_row0_data"])
+    assert pp.knn(P, n_neighbors=10, method="hora", engine=eng).dtype == np.float32
+    assert eng.calls[0] == ((400, 12), 10, 0, 400) and eng.calls[1][0] == (400, 5) and eng.calls[2][0] == (400, 3)
+    one = pp.knn(P[:1], n_neighbors=5, engine=eng)                             # a single observation: an empty graph
+    assert one.shape == (1, 1) and one.nnz == 0
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 
 @pytest.mark.gpu
